@@ -1,0 +1,953 @@
+// C ABI of libhtm_b200.so (include/htm_b200.h): handle, host-side table building, launches,
+// result fetches.  All compute is on the device; nothing here evaluates the forward model or
+// steps a chain on the CPU.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "htm_kernels.hpp"
+
+using namespace htm;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct htm_handle_s {
+  htm_config cfg;
+  std::string err;
+  int E = 0, E_total = 0, ev_off = 0, S = 0, R = 0, K = 0, C = 0;
+  size_t rs = 4;  // sizeof(real)
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool have_sta = false, have_obs = false, have_prior = false, tables_ok = false, chains_ready = false;
+  std::vector<double> sta_x, sta_y, sta_z, t_obs, t_stdv, a_obs, a_stdv, x_mu, y_mu;
+  double g_vs = 0, g_qs = 0;
+  std::vector<double> g_tc, g_ac;
+  // device tables
+  void *d_sta4 = nullptr, *d_obs4 = nullptr, *d_obs4_raw = nullptr, *d_evc4 = nullptr, *d_prior_xy = nullptr;
+  double* d_prior_xy64 = nullptr;
+  // mode B state
+  void *d_x = nullptr, *d_y = nullptr, *d_z = nullptr, *d_L = nullptr, *d_T = nullptr;
+  unsigned long long* d_counts = nullptr;
+  uint32_t* d_hist = nullptr;
+  void* d_samples = nullptr;
+  int rec_cap = 0, rec_origin = 0, rec_pending = 0;
+  std::vector<int> cur_samp, cur_lik;  // per rank, in recorded iterations consumed
+  std::vector<char> host_samples;      // host copy of the pending part of the ring
+  bool host_samples_valid = false;
+  // mode A state
+  double *d_hypo = nullptr, *d_tc = nullptr, *d_ac = nullptr, *d_vs = nullptr, *d_qs = nullptr, *d_temp = nullptr,
+         *d_Lc = nullptr;
+  unsigned long long* d_chain_counts = nullptr;
+  long long* d_cursor = nullptr;
+  int32_t* d_status = nullptr;
+  // stats
+  bool timed = false;
+  int64_t last_launches = 0, last_proposals = 0;
+};
+
+namespace {
+
+int32_t fail(htm_handle h, int32_t code, const std::string& msg) {
+  if (h)
+    h->err = msg;
+  else
+    g_create_error = msg;
+  return code;
+}
+#define HTM_CK(h, call)                                                                      \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(h, HTM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+
+void free_dev(void* p) {
+  if (p) cudaFree(p);
+}
+
+void shard_bounds(int n, int rank, int count, int* lo, int* hi) {
+  const int base = n / count, rem = n % count;
+  *lo = rank * base + (rank < rem ? rank : rem);
+  *hi = *lo + base + (rank < rem ? 1 : 0);
+}
+
+// Build and upload sta4 / obs4 / obs4_raw / evc4 / prior_xy (layouts: htm_forward.cuh).
+// init_forward's rule for degenerate sigmas is applied here (src/cls_forward.f90:78-90):
+// the branch looks at t_stdv only; the "else" sets precision 1 and log sigma := 1.0.
+template <typename real>
+int32_t build_tables_t(htm_handle h) {
+  const int E = h->E, S = h->S;
+  const double l2ph = 0.5 * std::log(2.0 * std::acos(-1.0));
+  const bool ut = h->cfg.use_time != 0, ua = h->cfg.use_amp != 0;
+  std::vector<real> sta(4 * static_cast<size_t>(S)), obs(4 * static_cast<size_t>(E) * S),
+      raw(4 * static_cast<size_t>(E) * S), evc(4 * static_cast<size_t>(E)), pxy(2 * static_cast<size_t>(E));
+  for (int j = 0; j < S; ++j) {
+    sta[4 * j] = static_cast<real>(h->sta_x[j]);
+    sta[4 * j + 1] = static_cast<real>(h->sta_y[j]);
+    sta[4 * j + 2] = static_cast<real>(h->sta_z[j]);
+    sta[4 * j + 3] = 0;
+  }
+  for (int e = 0; e < E; ++e) {
+    double Ce = 0.0, swt = 0.0, swa = 0.0;
+    for (int j = 0; j < S; ++j) {
+      const size_t k = static_cast<size_t>(e) * S + j;
+      double wt, wa, lt, la;
+      if (h->t_stdv[k] > 1.e-16) {
+        lt = std::log(h->t_stdv[k]);
+        wt = 1.0 / (h->t_stdv[k] * h->t_stdv[k]);
+        la = std::log(h->a_stdv[k]);
+        wa = 1.0 / (h->a_stdv[k] * h->a_stdv[k]);
+      } else {
+        lt = 1.0;
+        wt = 1.0;
+        la = 1.0;
+        wa = 1.0;
+      }
+      if (!ut) wt = 0.0;
+      if (!ua) wa = 0.0;
+      if (ut) Ce += l2ph + lt;
+      if (ua) Ce += l2ph + la;
+      swt += wt;
+      swa += wa;
+      raw[4 * k] = static_cast<real>(h->t_obs[k]);
+      raw[4 * k + 1] = static_cast<real>(wt);
+      raw[4 * k + 2] = static_cast<real>(h->a_obs[k]);
+      raw[4 * k + 3] = static_cast<real>(wa);
+      obs[4 * k] = static_cast<real>(h->t_obs[k] + h->g_tc[j]);
+      obs[4 * k + 1] = static_cast<real>(wt);
+      obs[4 * k + 2] = static_cast<real>(h->a_obs[k] + h->g_ac[j]);
+      obs[4 * k + 3] = static_cast<real>(wa);
+    }
+    evc[4 * e] = static_cast<real>(Ce);
+    evc[4 * e + 1] = static_cast<real>(swt > 0 ? 1.0 / swt : 0.0);
+    evc[4 * e + 2] = static_cast<real>(swa > 0 ? 1.0 / swa : 0.0);
+    evc[4 * e + 3] = 0;
+    pxy[2 * e] = static_cast<real>(h->have_prior ? h->x_mu[e] : 0.0);
+    pxy[2 * e + 1] = static_cast<real>(h->have_prior ? h->y_mu[e] : 0.0);
+  }
+  auto up = [&](void** d, const std::vector<real>& v) -> cudaError_t {
+    if (!*d) {
+      cudaError_t e = cudaMalloc(d, v.size() * sizeof(real));
+      if (e != cudaSuccess) return e;
+    }
+    return cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(real), cudaMemcpyHostToDevice, h->stream);
+  };
+  HTM_CK(h, up(&h->d_sta4, sta));
+  HTM_CK(h, up(&h->d_obs4, obs));
+  HTM_CK(h, up(&h->d_obs4_raw, raw));
+  HTM_CK(h, up(&h->d_evc4, evc));
+  HTM_CK(h, up(&h->d_prior_xy, pxy));
+  if (h->cfg.mode == HTM_MODE_REPLAY) {
+    std::vector<double> p64(2 * static_cast<size_t>(E));
+    for (int e = 0; e < E; ++e) {
+      p64[2 * e] = h->have_prior ? h->x_mu[e] : 0.0;
+      p64[2 * e + 1] = h->have_prior ? h->y_mu[e] : 0.0;
+    }
+    if (!h->d_prior_xy64) HTM_CK(h, cudaMalloc(&h->d_prior_xy64, p64.size() * sizeof(double)));
+    HTM_CK(h, cudaMemcpyAsync(h->d_prior_xy64, p64.data(), p64.size() * sizeof(double), cudaMemcpyHostToDevice,
+                              h->stream));
+  }
+  HTM_CK(h, cudaStreamSynchronize(h->stream));  // the staging vectors die here
+  h->tables_ok = true;
+  return HTM_OK;
+}
+
+int32_t ensure_tables(htm_handle h) {
+  if (h->tables_ok) return HTM_OK;
+  if (!h->have_sta) return fail(h, HTM_ERR_STATE, "stations not set (htm_set_stations)");
+  if (!h->have_obs) return fail(h, HTM_ERR_STATE, "observations not set (htm_set_observations)");
+  return h->cfg.precision == HTM_PRECISION_F64 ? build_tables_t<double>(h) : build_tables_t<float>(h);
+}
+
+Tables tables_of(htm_handle h) {
+  Tables t;
+  t.sta4 = h->d_sta4;
+  t.obs4 = h->d_obs4;
+  t.obs4_raw = h->d_obs4_raw;
+  t.evc4 = h->d_evc4;
+  t.prior_xy = h->d_prior_xy;
+  return t;
+}
+
+FactLaunch fact_launch_of(htm_handle h) {
+  FactLaunch a;
+  a.precision = h->cfg.precision;
+  a.kernel = h->cfg.kernel == HTM_KERNEL_AUTO ? HTM_KERNEL_LANE_PER_CHAIN : h->cfg.kernel;
+  a.slots = h->cfg.lane_slots;  // 0 = choose
+  a.tab = tables_of(h);
+  a.x = h->d_x;
+  a.y = h->d_y;
+  a.z = h->d_z;
+  a.L = h->d_L;
+  a.T = h->d_T;
+  a.E = h->E;
+  a.S = h->S;
+  a.R = h->R;
+  a.K = h->K;
+  a.n_cool = h->cfg.n_cool;
+  a.n_burn = h->cfg.n_burn;
+  a.n_interval = h->cfg.n_interval;
+  a.seed = h->cfg.seed;
+  a.event_offset = static_cast<uint32_t>(h->ev_off);
+  a.vs = h->g_vs;
+  a.qs = h->g_qs;
+  a.prior_z = h->cfg.prior_z;
+  a.width_z = h->cfg.prior_width_z;
+  a.width_xy = h->cfg.prior_width_xy;
+  a.step_xy = h->cfg.step_size_xy;
+  a.step_z = h->cfg.step_size_z;
+  a.counts = h->d_counts;
+  a.samples = h->d_samples;
+  a.rec_origin = h->rec_origin;
+  a.rec_cap = h->rec_cap;
+  a.hist = h->d_hist;
+  a.hist_bins = h->cfg.hist_bins;
+  a.hist_hw = h->cfg.hist_xy_halfwidth;
+  a.hist_zmax = h->cfg.hist_z_max;
+  return a;
+}
+
+int32_t alloc_state(htm_handle h) {
+  const size_t nB = static_cast<size_t>(h->E) * h->R * h->K;
+  if (h->cfg.mode == HTM_MODE_FACTORISED) {
+    for (void** p : {&h->d_x, &h->d_y, &h->d_z, &h->d_L, &h->d_T}) {
+      HTM_CK(h, cudaMalloc(p, nB * h->rs));
+      HTM_CK(h, cudaMemset(*p, 0, nB * h->rs));
+    }
+    if (h->cfg.hist_bins > 0) {
+      const size_t nh = static_cast<size_t>(h->E) * 3 * h->cfg.hist_bins * sizeof(uint32_t);
+      HTM_CK(h, cudaMalloc(&h->d_hist, nh));
+      HTM_CK(h, cudaMemset(h->d_hist, 0, nh));
+    }
+    if (h->cfg.max_samples > 0) {
+      h->rec_cap = h->cfg.max_samples;
+      const size_t ns = static_cast<size_t>(h->rec_cap) * h->R * h->cfg.n_cool * h->E * 4 * h->rs;
+      HTM_CK(h, cudaMalloc(&h->d_samples, ns));
+    }
+    h->cur_samp.assign(h->R, 0);
+    h->cur_lik.assign(h->R, 0);
+  } else if (h->cfg.mode == HTM_MODE_REPLAY) {
+    const size_t C = h->C;
+    HTM_CK(h, cudaMalloc(&h->d_hypo, C * 3 * h->E * sizeof(double)));
+    HTM_CK(h, cudaMalloc(&h->d_tc, C * h->S * sizeof(double)));
+    HTM_CK(h, cudaMalloc(&h->d_ac, C * h->S * sizeof(double)));
+    HTM_CK(h, cudaMalloc(&h->d_vs, C * sizeof(double)));
+    HTM_CK(h, cudaMalloc(&h->d_qs, C * sizeof(double)));
+    HTM_CK(h, cudaMalloc(&h->d_temp, C * sizeof(double)));
+    HTM_CK(h, cudaMalloc(&h->d_Lc, C * sizeof(double)));
+    HTM_CK(h, cudaMalloc(&h->d_chain_counts, C * 14 * sizeof(unsigned long long)));
+    HTM_CK(h, cudaMemset(h->d_chain_counts, 0, C * 14 * sizeof(unsigned long long)));
+    HTM_CK(h, cudaMalloc(&h->d_cursor, h->R * sizeof(long long)));
+    HTM_CK(h, cudaMalloc(&h->d_status, sizeof(int32_t)));
+  }
+  HTM_CK(h, cudaMalloc(&h->d_counts, 14 * sizeof(unsigned long long)));
+  HTM_CK(h, cudaMemset(h->d_counts, 0, 14 * sizeof(unsigned long long)));
+  return HTM_OK;
+}
+
+// recorded iterations (mod(it, n_interval) == 1) inside [first, last]: ids m = (it-1)/n_interval
+bool record_ids(int first, int last, int n_interval, int* m_lo, int* m_hi) {
+  if (n_interval <= 1) return false;  // mod(i,1) == 1 is never true (reference quirk Q6)
+  const int lo = (first - 1 + n_interval - 1) / n_interval;
+  const int hi = (last - 1) / n_interval;
+  if (hi < lo) return false;
+  *m_lo = lo;
+  *m_hi = hi;
+  return true;
+}
+
+int32_t pull_samples(htm_handle h) {
+  if (h->host_samples_valid) return HTM_OK;
+  const size_t per_rec = static_cast<size_t>(h->R) * h->cfg.n_cool * h->E * 4 * h->rs;
+  h->host_samples.resize(per_rec * h->rec_pending);
+  if (h->rec_pending > 0) {
+    HTM_CK(h, cudaMemcpyAsync(h->host_samples.data(), h->d_samples, h->host_samples.size(), cudaMemcpyDeviceToHost,
+                              h->stream));
+    HTM_CK(h, cudaStreamSynchronize(h->stream));
+  }
+  h->host_samples_valid = true;
+  return HTM_OK;
+}
+inline double sample_at(htm_handle h, int rec, int rank, int m, int e, int comp) {
+  const size_t i = (((static_cast<size_t>(rec) * h->R + rank) * h->cfg.n_cool + m) * h->E + e) * 4 + comp;
+  return h->rs == 8 ? reinterpret_cast<const double*>(h->host_samples.data())[i]
+                    : static_cast<double>(reinterpret_cast<const float*>(h->host_samples.data())[i]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t htm_config_default(htm_config* c) {
+  if (!c) return HTM_ERR_ARG;
+  std::memset(c, 0, sizeof(*c));
+  c->abi_version = HTM_ABI_VERSION;
+  c->seed = 20231001ull;
+  c->temp_high = 200.0;  // sample/hypo_tremor.in:148
+  c->prior_z = 0.0;
+  c->prior_width_z = 10.0;
+  c->prior_width_xy = 30.0;
+  c->prior_vs = 3.0;
+  c->prior_width_vs = 1.0;
+  c->prior_qs = 250.0;
+  c->prior_width_qs = 100.0;
+  c->prior_t_corr = 0.0;
+  c->prior_width_t_corr = 0.5;
+  c->prior_a_corr = 0.0;
+  c->prior_width_a_corr = 0.02;
+  c->step_size_z = 0.4;
+  c->step_size_xy = 2.0;
+  c->step_size_vs = 0.2;
+  c->step_size_qs = 5.0;
+  c->step_size_t_corr = 0.03;
+  c->step_size_a_corr = 0.005;
+  c->hist_xy_halfwidth = 100.0;
+  c->hist_z_max = 60.0;
+  c->n_procs = 1;
+  c->n_chains = 5;
+  c->n_cool = 1;
+  c->n_iter = 4000000;
+  c->n_burn = 2000000;
+  c->n_interval = 1000;
+  c->solve_vs = c->solve_t_corr = c->solve_qs = c->solve_a_corr = 1;
+  c->use_time = c->use_amp = 1;
+  c->mode = HTM_MODE_BLOCKED_GIBBS;
+  c->precision = HTM_PRECISION_F32;
+  c->ladder = HTM_LADDER_RANDOM;
+  c->kernel = HTM_KERNEL_AUTO;
+  c->shard_count = 1;
+  return HTM_OK;
+}
+
+int32_t htm_create(htm_handle* out, const htm_config* cfg) {
+  if (!out || !cfg) return fail(nullptr, HTM_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != HTM_ABI_VERSION) return fail(nullptr, HTM_ERR_ARG, "abi_version mismatch");
+  if (cfg->n_sta < 1 || cfg->n_events < 1) return fail(nullptr, HTM_ERR_ARG, "n_sta and n_events must be >= 1");
+  if (cfg->n_procs < 1 || cfg->n_chains < 1) return fail(nullptr, HTM_ERR_ARG, "n_procs and n_chains must be >= 1");
+  if (cfg->n_cool < 1 || cfg->n_cool > cfg->n_chains)
+    return fail(nullptr, HTM_ERR_ARG, "n_cool must be in 1..n_chains");
+  if (cfg->n_interval < 1) return fail(nullptr, HTM_ERR_ARG, "n_interval must be >= 1");
+  if (cfg->precision != HTM_PRECISION_F64 && cfg->precision != HTM_PRECISION_F32)
+    return fail(nullptr, HTM_ERR_ARG, "precision must be 32 or 64");
+  if (cfg->shard_count < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count)
+    return fail(nullptr, HTM_ERR_ARG, "bad shard_rank / shard_count");
+  if (cfg->temp_high < 1.0) return fail(nullptr, HTM_ERR_ARG, "temp_high must be >= 1");
+  const bool any_solve = cfg->solve_vs || cfg->solve_t_corr || cfg->solve_qs || cfg->solve_a_corr;
+  if (cfg->mode == HTM_MODE_FACTORISED && any_solve)
+    return fail(nullptr, HTM_ERR_ARG,
+                "factorised mode needs solve_vs = solve_t_corr = solve_qs = solve_a_corr = F "
+                "(the posterior only factorises over events when the shared parameters are fixed)");
+  if (cfg->mode == HTM_MODE_REPLAY && cfg->precision != HTM_PRECISION_F64)
+    return fail(nullptr, HTM_ERR_ARG, "replay mode is float64 only");
+  if (cfg->mode == HTM_MODE_REPLAY && cfg->shard_count != 1)
+    return fail(nullptr, HTM_ERR_ARG, "replay mode does not shard (replicas only)");
+  if (cfg->mode != HTM_MODE_REPLAY && cfg->mode != HTM_MODE_FACTORISED && cfg->mode != HTM_MODE_BLOCKED_GIBBS)
+    return fail(nullptr, HTM_ERR_ARG, "unknown mode");
+  if (cfg->hist_bins < 0 || cfg->max_samples < 0) return fail(nullptr, HTM_ERR_ARG, "negative hist_bins/max_samples");
+
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev == 0)
+    return fail(nullptr, HTM_ERR_CUDA,
+                std::string("no CUDA device (libhtm_b200 has no CPU fallback): ") +
+                    (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0"));
+  if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, HTM_ERR_ARG, "device ordinal out of range");
+  ce = cudaSetDevice(cfg->device);
+  if (ce != cudaSuccess) return fail(nullptr, HTM_ERR_CUDA, cudaGetErrorString(ce));
+
+  htm_handle h = new htm_handle_s();
+  h->cfg = *cfg;
+  h->E_total = cfg->n_events;
+  int lo, hi;
+  shard_bounds(cfg->n_events, cfg->shard_rank, cfg->shard_count, &lo, &hi);
+  h->ev_off = lo;
+  h->E = hi - lo;
+  h->S = cfg->n_sta;
+  h->R = cfg->n_procs;
+  h->K = cfg->n_chains;
+  h->C = h->R * h->K;
+  h->rs = cfg->precision == HTM_PRECISION_F64 ? 8 : 4;
+  h->g_vs = cfg->prior_vs;
+  h->g_qs = cfg->prior_qs;
+  h->g_tc.assign(h->S, cfg->prior_t_corr);
+  h->g_ac.assign(h->S, cfg->prior_a_corr);
+  if (h->E < 1) {
+    delete h;
+    return fail(nullptr, HTM_ERR_ARG, "this shard holds no events");
+  }
+  ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev1);
+  if (ce != cudaSuccess) {
+    g_create_error = cudaGetErrorString(ce);
+    delete h;
+    return HTM_ERR_CUDA;
+  }
+  const int32_t rc = alloc_state(h);
+  if (rc != HTM_OK) {
+    g_create_error = h->err;
+    htm_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return HTM_OK;
+}
+
+int32_t htm_destroy(htm_handle h) {
+  if (!h) return HTM_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : {h->d_sta4, h->d_obs4, h->d_obs4_raw, h->d_evc4, h->d_prior_xy, static_cast<void*>(h->d_prior_xy64),
+                  h->d_x, h->d_y, h->d_z, h->d_L, h->d_T, static_cast<void*>(h->d_counts),
+                  static_cast<void*>(h->d_hist), h->d_samples, static_cast<void*>(h->d_hypo),
+                  static_cast<void*>(h->d_tc), static_cast<void*>(h->d_ac), static_cast<void*>(h->d_vs),
+                  static_cast<void*>(h->d_qs), static_cast<void*>(h->d_temp), static_cast<void*>(h->d_Lc),
+                  static_cast<void*>(h->d_chain_counts), static_cast<void*>(h->d_cursor),
+                  static_cast<void*>(h->d_status)})
+    free_dev(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return HTM_OK;
+}
+
+int32_t htm_last_error(htm_handle h, char* buf, int32_t len) {
+  if (!buf || len <= 0) return HTM_ERR_ARG;
+  const std::string& s = h ? h->err : g_create_error;
+  std::snprintf(buf, static_cast<size_t>(len), "%s", s.c_str());
+  return HTM_OK;
+}
+
+int32_t htm_set_stations(htm_handle h, const double* sx, const double* sy, const double* sz) {
+  if (!h || !sx || !sy || !sz) return fail(h, HTM_ERR_ARG, "null argument");
+  h->sta_x.assign(sx, sx + h->S);
+  h->sta_y.assign(sy, sy + h->S);
+  h->sta_z.assign(sz, sz + h->S);
+  h->have_sta = true;
+  h->tables_ok = false;
+  return HTM_OK;
+}
+
+int32_t htm_set_observations(htm_handle h, const double* t_obs, const double* t_stdv, const double* a_obs,
+                             const double* a_stdv) {
+  if (!h || !t_obs || !t_stdv || !a_obs || !a_stdv) return fail(h, HTM_ERR_ARG, "null argument");
+  const size_t n = static_cast<size_t>(h->E) * h->S;
+  h->t_obs.assign(t_obs, t_obs + n);
+  h->t_stdv.assign(t_stdv, t_stdv + n);
+  h->a_obs.assign(a_obs, a_obs + n);
+  h->a_stdv.assign(a_stdv, a_stdv + n);
+  h->have_obs = true;
+  h->tables_ok = false;
+  return HTM_OK;
+}
+
+int32_t htm_set_xy_prior(htm_handle h, const double* x_mu, const double* y_mu) {
+  if (!h || !x_mu || !y_mu) return fail(h, HTM_ERR_ARG, "null argument");
+  h->x_mu.assign(x_mu, x_mu + h->E);
+  h->y_mu.assign(y_mu, y_mu + h->E);
+  h->have_prior = true;
+  h->tables_ok = false;
+  return HTM_OK;
+}
+
+int32_t htm_set_globals(htm_handle h, double vs, double qs, const double* t_corr, const double* a_corr) {
+  if (!h) return HTM_ERR_ARG;
+  if (!(vs > 0.0) || !(qs > 0.0)) return fail(h, HTM_ERR_ARG, "vs and qs must be positive");
+  h->g_vs = vs;
+  h->g_qs = qs;
+  if (t_corr) h->g_tc.assign(t_corr, t_corr + h->S);
+  if (a_corr) h->g_ac.assign(a_corr, a_corr + h->S);
+  h->tables_ok = false;
+  return HTM_OK;
+}
+
+int32_t htm_init_chains(htm_handle h) {
+  if (!h) return HTM_ERR_ARG;
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  if (h->cfg.mode == HTM_MODE_REPLAY)
+    return fail(h, HTM_ERR_UNSUPPORTED,
+                "replay mode: chains are initialised by the host's mod_random (htm_set_chain_state)");
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS)
+    return fail(h, HTM_ERR_UNSUPPORTED, "blocked-Gibbs mode is not built yet");
+  if (!h->have_prior) return fail(h, HTM_ERR_STATE, "xy prior not set (htm_set_xy_prior)");
+  int32_t rc = ensure_tables(h);
+  if (rc != HTM_OK) return rc;
+  FactLaunch a = fact_launch_of(h);
+  HTM_CK(h, launch_factorised_init(a, h->cfg.temp_high, h->cfg.ladder, h->stream));
+  HTM_CK(h, cudaMemsetAsync(h->d_counts, 0, 14 * sizeof(unsigned long long), h->stream));
+  if (h->d_hist)
+    HTM_CK(h, cudaMemsetAsync(h->d_hist, 0, static_cast<size_t>(h->E) * 3 * h->cfg.hist_bins * sizeof(uint32_t),
+                              h->stream));
+  h->rec_pending = 0;
+  h->host_samples_valid = false;
+  h->chains_ready = true;
+  return HTM_OK;
+}
+
+int32_t htm_set_chain_state(htm_handle h, int32_t rank, int32_t chain, const double* hypo, const double* t_corr,
+                            const double* a_corr, double vs, double qs, double temp, double log_likelihood) {
+  if (!h || !hypo) return fail(h, HTM_ERR_ARG, "null argument");
+  if (rank < 0 || rank >= h->R || chain < 0 || chain >= h->K) return fail(h, HTM_ERR_ARG, "rank/chain out of range");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  if (h->cfg.mode == HTM_MODE_REPLAY) {
+    if (!t_corr || !a_corr) return fail(h, HTM_ERR_ARG, "t_corr / a_corr required in replay mode");
+    const size_t c = static_cast<size_t>(rank) * h->K + chain;
+    HTM_CK(h, cudaMemcpy(h->d_hypo + c * 3 * h->E, hypo, 3 * h->E * sizeof(double), cudaMemcpyHostToDevice));
+    HTM_CK(h, cudaMemcpy(h->d_tc + c * h->S, t_corr, h->S * sizeof(double), cudaMemcpyHostToDevice));
+    HTM_CK(h, cudaMemcpy(h->d_ac + c * h->S, a_corr, h->S * sizeof(double), cudaMemcpyHostToDevice));
+    HTM_CK(h, cudaMemcpy(h->d_vs + c, &vs, sizeof(double), cudaMemcpyHostToDevice));
+    HTM_CK(h, cudaMemcpy(h->d_qs + c, &qs, sizeof(double), cudaMemcpyHostToDevice));
+    HTM_CK(h, cudaMemcpy(h->d_temp + c, &temp, sizeof(double), cudaMemcpyHostToDevice));
+    HTM_CK(h, cudaMemcpy(h->d_Lc + c, &log_likelihood, sizeof(double), cudaMemcpyHostToDevice));
+    h->chains_ready = true;
+    return HTM_OK;
+  }
+  if (h->cfg.mode == HTM_MODE_FACTORISED) {
+    // hypocentres and temperature of chain (rank, chain) for every event; the per-event
+    // log-likelihoods are recomputed on the device by htm_refresh (next run)
+    return fail(h, HTM_ERR_UNSUPPORTED, "htm_set_chain_state: factorised mode initialises with htm_init_chains");
+  }
+  return fail(h, HTM_ERR_UNSUPPORTED, "blocked-Gibbs mode is not built yet");
+}
+
+int32_t htm_get_chain_state(htm_handle h, int32_t rank, int32_t chain, double* hypo, double* t_corr, double* a_corr,
+                            double* vs, double* qs, double* temp, double* log_likelihood) {
+  if (!h) return HTM_ERR_ARG;
+  if (rank < 0 || rank >= h->R || chain < 0 || chain >= h->K) return fail(h, HTM_ERR_ARG, "rank/chain out of range");
+  if (!h->chains_ready) return fail(h, HTM_ERR_STATE, "chains not initialised");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  HTM_CK(h, cudaStreamSynchronize(h->stream));
+  if (h->cfg.mode == HTM_MODE_REPLAY) {
+    const size_t c = static_cast<size_t>(rank) * h->K + chain;
+    if (hypo) HTM_CK(h, cudaMemcpy(hypo, h->d_hypo + c * 3 * h->E, 3 * h->E * sizeof(double), cudaMemcpyDeviceToHost));
+    if (t_corr) HTM_CK(h, cudaMemcpy(t_corr, h->d_tc + c * h->S, h->S * sizeof(double), cudaMemcpyDeviceToHost));
+    if (a_corr) HTM_CK(h, cudaMemcpy(a_corr, h->d_ac + c * h->S, h->S * sizeof(double), cudaMemcpyDeviceToHost));
+    if (vs) HTM_CK(h, cudaMemcpy(vs, h->d_vs + c, sizeof(double), cudaMemcpyDeviceToHost));
+    if (qs) HTM_CK(h, cudaMemcpy(qs, h->d_qs + c, sizeof(double), cudaMemcpyDeviceToHost));
+    if (temp) HTM_CK(h, cudaMemcpy(temp, h->d_temp + c, sizeof(double), cudaMemcpyDeviceToHost));
+    if (log_likelihood) HTM_CK(h, cudaMemcpy(log_likelihood, h->d_Lc + c, sizeof(double), cudaMemcpyDeviceToHost));
+    return HTM_OK;
+  }
+  if (h->cfg.mode == HTM_MODE_FACTORISED) {
+    const size_t n = static_cast<size_t>(h->E) * h->R * h->K;
+    std::vector<char> bx(n * h->rs), by(n * h->rs), bz(n * h->rs), bL(n * h->rs), bT(n * h->rs);
+    HTM_CK(h, cudaMemcpy(bx.data(), h->d_x, n * h->rs, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(by.data(), h->d_y, n * h->rs, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(bz.data(), h->d_z, n * h->rs, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(bL.data(), h->d_L, n * h->rs, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(bT.data(), h->d_T, n * h->rs, cudaMemcpyDeviceToHost));
+    auto at = [&](const std::vector<char>& b, size_t i) -> double {
+      return h->rs == 8 ? reinterpret_cast<const double*>(b.data())[i]
+                        : static_cast<double>(reinterpret_cast<const float*>(b.data())[i]);
+    };
+    double ls = 0.0;
+    for (int e = 0; e < h->E; ++e) {
+      const size_t i = (static_cast<size_t>(e) * h->R + rank) * h->K + chain;
+      if (hypo) {
+        hypo[3 * e] = at(bx, i);
+        hypo[3 * e + 1] = at(by, i);
+        hypo[3 * e + 2] = at(bz, i);
+      }
+      ls += at(bL, i);
+    }
+    if (t_corr) std::memcpy(t_corr, h->g_tc.data(), h->S * sizeof(double));
+    if (a_corr) std::memcpy(a_corr, h->g_ac.data(), h->S * sizeof(double));
+    if (vs) *vs = h->g_vs;
+    if (qs) *qs = h->g_qs;
+    if (temp) *temp = at(bT, (static_cast<size_t>(0) * h->R + rank) * h->K + chain);
+    if (log_likelihood) *log_likelihood = ls;
+    return HTM_OK;
+  }
+  return fail(h, HTM_ERR_UNSUPPORTED, "blocked-Gibbs mode is not built yet");
+}
+
+int32_t htm_loglik(htm_handle h, int32_t n_models, const double* hypo, const double* t_corr, const double* a_corr,
+                   const double* vs, const double* qs, double* log_likelihood, double* per_event) {
+  if (!h || !hypo || !t_corr || !a_corr || !vs || !qs || !log_likelihood) return fail(h, HTM_ERR_ARG, "null argument");
+  if (n_models < 1) return fail(h, HTM_ERR_ARG, "n_models must be >= 1");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  int32_t rc = ensure_tables(h);
+  if (rc != HTM_OK) return rc;
+  const size_t M_ = n_models, E = h->E, S = h->S;
+  double *d_h = nullptr, *d_tc = nullptr, *d_ac = nullptr, *d_vs = nullptr, *d_qs = nullptr, *d_pe = nullptr,
+         *d_L = nullptr;
+  auto cleanup = [&]() {
+    for (double* p : {d_h, d_tc, d_ac, d_vs, d_qs, d_pe, d_L}) free_dev(p);
+  };
+  cudaError_t e = cudaSuccess;
+  auto up = [&](double** d, const double* src, size_t n) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(d, n * sizeof(double));
+    if (e == cudaSuccess && src) e = cudaMemcpyAsync(*d, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  };
+  up(&d_h, hypo, M_ * 3 * E);
+  up(&d_tc, t_corr, M_ * S);
+  up(&d_ac, a_corr, M_ * S);
+  up(&d_vs, vs, M_);
+  up(&d_qs, qs, M_);
+  up(&d_pe, nullptr, M_ * E);
+  up(&d_L, nullptr, M_);
+  if (e == cudaSuccess)
+    e = launch_loglik(h->cfg.precision, tables_of(h), h->E, h->S, n_models, d_h, d_tc, d_ac, d_vs, d_qs, d_pe, d_L,
+                      h->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(log_likelihood, d_L, M_ * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && per_event)
+    e = cudaMemcpyAsync(per_event, d_pe, M_ * E * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (e != cudaSuccess) return fail(h, HTM_ERR_CUDA, std::string("htm_loglik: ") + cudaGetErrorString(e));
+  return HTM_OK;
+}
+
+static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm_step_trace* d_trace,
+                        htm_swap_trace* d_swaps) {
+  if (!h) return HTM_ERR_ARG;
+  if (iter_first < 1 || iter_last < iter_first) return fail(h, HTM_ERR_ARG, "need 1 <= iter_first <= iter_last");
+  if (h->cfg.mode == HTM_MODE_REPLAY) return fail(h, HTM_ERR_UNSUPPORTED, "replay mode runs through htm_replay");
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) return fail(h, HTM_ERR_UNSUPPORTED, "blocked-Gibbs mode is not built yet");
+  if (!h->chains_ready) return fail(h, HTM_ERR_STATE, "chains not initialised (htm_init_chains)");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  int32_t rc = ensure_tables(h);
+  if (rc != HTM_OK) return rc;
+  // sample ring bookkeeping
+  int m_lo = 0, m_hi = -1;
+  const bool recs = record_ids(iter_first, iter_last, h->cfg.n_interval, &m_lo, &m_hi);
+  if (h->d_samples && recs) {
+    bool all_consumed = true;
+    for (int r = 0; r < h->R; ++r)
+      if (h->cur_samp[r] < h->rec_pending || h->cur_lik[r] < h->rec_pending) all_consumed = false;
+    if (h->rec_pending == 0 || all_consumed) {
+      h->rec_origin = m_lo;
+      h->rec_pending = 0;
+      h->cur_samp.assign(h->R, 0);
+      h->cur_lik.assign(h->R, 0);
+    }
+    if (m_lo != h->rec_origin + h->rec_pending)
+      return fail(h, HTM_ERR_STATE, "iterations must continue where the previous htm_run stopped while samples are pending");
+    if (m_hi - h->rec_origin + 1 > h->rec_cap)
+      return fail(h, HTM_ERR_STATE,
+                  "sample ring full: fetch samples and likelihood of every rank (or htm_discard_samples) "
+                  "before running further, or raise max_samples");
+    h->rec_pending = m_hi - h->rec_origin + 1;
+    h->host_samples_valid = false;
+  }
+  FactLaunch a = fact_launch_of(h);
+  a.iter_first = iter_first;
+  a.iter_last = iter_last;
+  a.trace = d_trace;
+  a.swaps = d_swaps;
+  int nl = 0;
+  const char* why = "";
+  HTM_CK(h, cudaEventRecord(h->ev0, h->stream));
+  cudaError_t e = launch_factorised(a, h->stream, &nl, &why);
+  if (e != cudaSuccess)
+    return fail(h, e == cudaErrorInvalidValue && why[0] ? HTM_ERR_UNSUPPORTED : HTM_ERR_CUDA,
+                why[0] ? std::string(why) : std::string("launch_factorised: ") + cudaGetErrorString(e));
+  HTM_CK(h, cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  h->last_launches = nl;
+  h->last_proposals = static_cast<int64_t>(iter_last - iter_first + 1) * h->E * h->R * h->K;
+  return HTM_OK;
+}
+
+int32_t htm_run(htm_handle h, int32_t iter_first, int32_t iter_last) {
+  return run_impl(h, iter_first, iter_last, nullptr, nullptr);
+}
+
+// Validation entry point: htm_run that also returns the per-step and per-swap records
+// ([n_it][E][R][K] and [n_it][E][R]) so the kernels can be compared step by step with the
+// oracle's statement of the same schedule.  Synchronous.
+int32_t htm_run_traced(htm_handle h, int32_t iter_first, int32_t iter_last, htm_step_trace* trace,
+                       htm_swap_trace* swaps) {
+  if (!h) return HTM_ERR_ARG;
+  if (iter_first < 1 || iter_last < iter_first) return fail(h, HTM_ERR_ARG, "need 1 <= iter_first <= iter_last");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  const size_t n_it = static_cast<size_t>(iter_last - iter_first + 1);
+  const size_t nt = n_it * h->E * h->R * h->K, ns = n_it * h->E * h->R;
+  htm_step_trace* d_t = nullptr;
+  htm_swap_trace* d_s = nullptr;
+  if (trace) {
+    HTM_CK(h, cudaMalloc(&d_t, nt * sizeof(htm_step_trace)));
+    HTM_CK(h, cudaMemset(d_t, 0, nt * sizeof(htm_step_trace)));
+  }
+  if (swaps) {
+    HTM_CK(h, cudaMalloc(&d_s, ns * sizeof(htm_swap_trace)));
+    HTM_CK(h, cudaMemset(d_s, 0, ns * sizeof(htm_swap_trace)));
+  }
+  int32_t rc = run_impl(h, iter_first, iter_last, d_t, d_s);
+  cudaError_t e = cudaSuccess;
+  if (rc == HTM_OK) e = cudaStreamSynchronize(h->stream);
+  if (rc == HTM_OK && e == cudaSuccess && trace)
+    e = cudaMemcpy(trace, d_t, nt * sizeof(htm_step_trace), cudaMemcpyDeviceToHost);
+  if (rc == HTM_OK && e == cudaSuccess && swaps)
+    e = cudaMemcpy(swaps, d_s, ns * sizeof(htm_swap_trace), cudaMemcpyDeviceToHost);
+  free_dev(d_t);
+  free_dev(d_s);
+  if (rc != HTM_OK) return rc;
+  if (e != cudaSuccess) return fail(h, HTM_ERR_CUDA, std::string("htm_run_traced: ") + cudaGetErrorString(e));
+  return HTM_OK;
+}
+
+int32_t htm_synchronize(htm_handle h) {
+  if (!h) return HTM_ERR_ARG;
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  HTM_CK(h, cudaStreamSynchronize(h->stream));
+  return HTM_OK;
+}
+
+int32_t htm_replay(htm_handle h, int32_t iter_first, int32_t iter_last, const int32_t* const* draws,
+                   const int64_t* n_draws, htm_step_trace* trace, htm_swap_trace* swaps, int64_t* n_used) {
+  if (!h || !draws || !n_draws) return fail(h, HTM_ERR_ARG, "null argument");
+  if (h->cfg.mode != HTM_MODE_REPLAY) return fail(h, HTM_ERR_STATE, "handle was not created in replay mode");
+  if (iter_first < 1 || iter_last < iter_first) return fail(h, HTM_ERR_ARG, "need 1 <= iter_first <= iter_last");
+  if (!h->chains_ready) return fail(h, HTM_ERR_STATE, "chains not initialised (htm_set_chain_state)");
+  if (!h->have_prior) return fail(h, HTM_ERR_STATE, "xy prior not set (htm_set_xy_prior)");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  int32_t rc = ensure_tables(h);
+  if (rc != HTM_OK) return rc;
+  const int R = h->R;
+  std::vector<long long> off(R + 1, 0);
+  for (int r = 0; r < R; ++r) {
+    if (n_draws[r] < 0 || (n_draws[r] > 0 && !draws[r])) return fail(h, HTM_ERR_ARG, "bad draw stream");
+    off[r + 1] = off[r] + n_draws[r];
+  }
+  const size_t n_it = static_cast<size_t>(iter_last - iter_first + 1);
+  int32_t* d_draws = nullptr;
+  long long* d_off = nullptr;
+  htm_step_trace* d_t = nullptr;
+  htm_swap_trace* d_s = nullptr;
+  cudaError_t e = cudaMalloc(&d_draws, (off[R] > 0 ? off[R] : 1) * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_off, (R + 1) * sizeof(long long));
+  for (int r = 0; r < R && e == cudaSuccess; ++r)
+    if (n_draws[r] > 0)
+      e = cudaMemcpyAsync(d_draws + off[r], draws[r], n_draws[r] * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_off, off.data(), (R + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->d_cursor, 0, R * sizeof(long long), h->stream);
+  if (e == cudaSuccess && trace) e = cudaMalloc(&d_t, n_it * h->C * sizeof(htm_step_trace));
+  if (e == cudaSuccess && swaps) {
+    e = cudaMalloc(&d_s, n_it * sizeof(htm_swap_trace));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_s, 0, n_it * sizeof(htm_swap_trace), h->stream);
+  }
+  int32_t status = 0;
+  if (e == cudaSuccess) {
+    ReplayLaunch a;
+    a.tab = tables_of(h);
+    a.E = h->E;
+    a.S = h->S;
+    a.R = R;
+    a.K = h->K;
+    a.iter_first = iter_first;
+    a.iter_last = iter_last;
+    // proposal probabilities, src/cls_mcmc.f90:91-108
+    a.p_vs = h->cfg.solve_vs ? 0.025 : 0.0;
+    a.p_t_corr = h->cfg.solve_t_corr ? 0.025 : 0.0;
+    a.p_qs = h->cfg.solve_qs ? 0.025 : 0.0;
+    a.p_a_corr = h->cfg.solve_a_corr ? 0.025 : 0.0;
+    a.prior_xy = h->d_prior_xy64;
+    a.prior_z = h->cfg.prior_z;
+    a.width_z = h->cfg.prior_width_z;
+    a.width_xy = h->cfg.prior_width_xy;
+    a.step_xy = h->cfg.step_size_xy;
+    a.step_z = h->cfg.step_size_z;
+    a.prior_vs = h->cfg.prior_vs;
+    a.width_vs = h->cfg.prior_width_vs;
+    a.step_vs = h->cfg.step_size_vs;
+    a.prior_qs = h->cfg.prior_qs;
+    a.width_qs = h->cfg.prior_width_qs;
+    a.step_qs = h->cfg.step_size_qs;
+    a.prior_tc = h->cfg.prior_t_corr;
+    a.width_tc = h->cfg.prior_width_t_corr;
+    a.step_tc = h->cfg.step_size_t_corr;
+    a.prior_ac = h->cfg.prior_a_corr;
+    a.width_ac = h->cfg.prior_width_a_corr;
+    a.step_ac = h->cfg.step_size_a_corr;
+    a.hypo = h->d_hypo;
+    a.tc = h->d_tc;
+    a.ac = h->d_ac;
+    a.vs = h->d_vs;
+    a.qs = h->d_qs;
+    a.temp = h->d_temp;
+    a.L = h->d_Lc;
+    a.chain_counts = h->d_chain_counts;
+    a.draws = d_draws;
+    a.draw_off = reinterpret_cast<const int64_t*>(d_off);
+    a.cursor = reinterpret_cast<int64_t*>(h->d_cursor);
+    a.trace = d_t;
+    a.swaps = d_s;
+    a.status = h->d_status;
+    cudaEventRecord(h->ev0, h->stream);
+    e = launch_replay(a, h->stream);
+    cudaEventRecord(h->ev1, h->stream);
+    h->timed = true;
+    h->last_launches = 1;
+    h->last_proposals = static_cast<int64_t>(n_it) * h->C;
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(&status, h->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && trace) e = cudaMemcpy(trace, d_t, n_it * h->C * sizeof(htm_step_trace), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && swaps) e = cudaMemcpy(swaps, d_s, n_it * sizeof(htm_swap_trace), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && n_used) {
+    std::vector<long long> cur(R);
+    e = cudaMemcpy(cur.data(), h->d_cursor, R * sizeof(long long), cudaMemcpyDeviceToHost);
+    for (int r = 0; r < R; ++r) n_used[r] = cur[r];
+  }
+  free_dev(d_draws);
+  free_dev(d_off);
+  free_dev(d_t);
+  free_dev(d_s);
+  if (e != cudaSuccess) return fail(h, HTM_ERR_CUDA, std::string("htm_replay: ") + cudaGetErrorString(e));
+  if (status != 0) return fail(h, HTM_ERR_DRAWS, "htm_replay: the supplied draw stream was exhausted");
+  return HTM_OK;
+}
+
+int32_t htm_fetch_samples(htm_handle h, int32_t rank, int32_t max_records, int32_t* n_records, int32_t* iter,
+                          double* vs, double* qs, double* hypo, double* t_corr, double* a_corr) {
+  if (!h || !n_records) return fail(h, HTM_ERR_ARG, "null argument");
+  *n_records = 0;
+  if (rank < 0 || rank >= h->R) return fail(h, HTM_ERR_ARG, "rank out of range");
+  if (h->cfg.mode != HTM_MODE_FACTORISED) return fail(h, HTM_ERR_UNSUPPORTED, "samples: factorised mode only for now");
+  if (!h->d_samples) return HTM_OK;  // max_samples = 0: nothing is recorded
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  int32_t rc = pull_samples(h);
+  if (rc != HTM_OK) return rc;
+  const int nc = h->cfg.n_cool, E = h->E, S = h->S;
+  int n = 0;
+  int rec = h->cur_samp[rank];
+  for (; rec < h->rec_pending; ++rec) {
+    const int it = (h->rec_origin + rec) * h->cfg.n_interval + 1;
+    if (it <= h->cfg.n_burn) continue;  // samples start after burn-in, :272
+    if (n + nc > max_records) break;
+    for (int m = 0; m < nc; ++m, ++n) {
+      if (iter) iter[n] = it;
+      if (vs) vs[n] = h->g_vs;
+      if (qs) qs[n] = h->g_qs;
+      if (hypo)
+        for (int e = 0; e < E; ++e)
+          for (int c = 0; c < 3; ++c) hypo[static_cast<size_t>(n) * 3 * E + 3 * e + c] = sample_at(h, rec, rank, m, e, c);
+      if (t_corr) std::memcpy(t_corr + static_cast<size_t>(n) * S, h->g_tc.data(), S * sizeof(double));
+      if (a_corr) std::memcpy(a_corr + static_cast<size_t>(n) * S, h->g_ac.data(), S * sizeof(double));
+    }
+  }
+  h->cur_samp[rank] = rec;
+  *n_records = n;
+  return HTM_OK;
+}
+
+int32_t htm_fetch_likelihood(htm_handle h, int32_t rank, int32_t max_records, int32_t* n_records, int32_t* iter,
+                             double* log_likelihood) {
+  if (!h || !n_records) return fail(h, HTM_ERR_ARG, "null argument");
+  *n_records = 0;
+  if (rank < 0 || rank >= h->R) return fail(h, HTM_ERR_ARG, "rank out of range");
+  if (h->cfg.mode != HTM_MODE_FACTORISED) return fail(h, HTM_ERR_UNSUPPORTED, "likelihood: factorised mode only for now");
+  if (!h->d_samples) return HTM_OK;
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  int32_t rc = pull_samples(h);
+  if (rc != HTM_OK) return rc;
+  const int nc = h->cfg.n_cool, E = h->E;
+  int n = 0;
+  int rec = h->cur_lik[rank];
+  for (; rec < h->rec_pending; ++rec) {
+    if (n + nc > max_records) break;
+    const int it = (h->rec_origin + rec) * h->cfg.n_interval + 1;
+    for (int m = 0; m < nc; ++m, ++n) {
+      double s = 0.0;
+      for (int e = 0; e < E; ++e) s += sample_at(h, rec, rank, m, e, 3);
+      if (iter) iter[n] = it;
+      if (log_likelihood) log_likelihood[n] = s;
+    }
+  }
+  h->cur_lik[rank] = rec;
+  *n_records = n;
+  return HTM_OK;
+}
+
+// Drop every pending record (for callers that only want histograms / counts).
+int32_t htm_discard_samples(htm_handle h) {
+  if (!h) return HTM_ERR_ARG;
+  h->rec_pending = 0;
+  h->host_samples_valid = false;
+  h->cur_samp.assign(h->R, 0);
+  h->cur_lik.assign(h->R, 0);
+  return HTM_OK;
+}
+
+int32_t htm_get_counts(htm_handle h, int64_t n_propose[7], int64_t n_accept[7]) {
+  if (!h || !n_propose || !n_accept) return fail(h, HTM_ERR_ARG, "null argument");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  HTM_CK(h, cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 7; ++k) n_propose[k] = n_accept[k] = 0;
+  if (h->cfg.mode == HTM_MODE_REPLAY) {
+    std::vector<unsigned long long> c(static_cast<size_t>(h->C) * 14);
+    HTM_CK(h, cudaMemcpy(c.data(), h->d_chain_counts, c.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < h->C; ++i)
+      for (int k = 0; k < 7; ++k) {
+        n_propose[k] += static_cast<int64_t>(c[static_cast<size_t>(i) * 14 + k]);
+        n_accept[k] += static_cast<int64_t>(c[static_cast<size_t>(i) * 14 + 7 + k]);
+      }
+    return HTM_OK;
+  }
+  unsigned long long c[14];
+  HTM_CK(h, cudaMemcpy(c, h->d_counts, sizeof(c), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 7; ++k) {
+    n_propose[k] = static_cast<int64_t>(c[k]);
+    n_accept[k] = static_cast<int64_t>(c[7 + k]);
+  }
+  return HTM_OK;
+}
+
+int32_t htm_get_histograms(htm_handle h, uint32_t* hist) {
+  if (!h || !hist) return fail(h, HTM_ERR_ARG, "null argument");
+  if (!h->d_hist) return fail(h, HTM_ERR_STATE, "histograms are off (hist_bins = 0)");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  HTM_CK(h, cudaStreamSynchronize(h->stream));
+  HTM_CK(h, cudaMemcpy(hist, h->d_hist, static_cast<size_t>(h->E) * 3 * h->cfg.hist_bins * sizeof(uint32_t),
+                       cudaMemcpyDeviceToHost));
+  return HTM_OK;
+}
+
+int32_t htm_device_ptr(htm_handle h, int32_t what, void** ptr, int64_t* n_bytes) {
+  if (!h || !ptr || !n_bytes) return fail(h, HTM_ERR_ARG, "null argument");
+  if (what == 0) {
+    if (!h->d_hist) return fail(h, HTM_ERR_STATE, "histograms are off (hist_bins = 0)");
+    *ptr = h->d_hist;
+    *n_bytes = static_cast<int64_t>(h->E) * 3 * h->cfg.hist_bins * sizeof(uint32_t);
+    return HTM_OK;
+  }
+  if (what == 1) {
+    *ptr = h->d_counts;
+    *n_bytes = 14 * sizeof(unsigned long long);
+    return HTM_OK;
+  }
+  return fail(h, HTM_ERR_ARG, "unknown device buffer id");
+}
+
+int32_t htm_last_run_stats(htm_handle h, double* ms, int64_t* n_launches, int64_t* n_proposals) {
+  if (!h) return HTM_ERR_ARG;
+  if (!h->timed) return fail(h, HTM_ERR_STATE, "nothing was run yet");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  HTM_CK(h, cudaEventSynchronize(h->ev1));
+  float t = 0;
+  HTM_CK(h, cudaEventElapsedTime(&t, h->ev0, h->ev1));
+  if (ms) *ms = t;
+  if (n_launches) *n_launches = h->last_launches;
+  if (n_proposals) *n_proposals = h->last_proposals;
+  return HTM_OK;
+}
+
+int32_t htm_measure_fp32_peak(int32_t device, double* tflops, double* mufu_gops) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(nullptr, HTM_ERR_CUDA, "no CUDA device");
+  cudaError_t e = measure_fp32_peak(device, tflops, mufu_gops);
+  if (e != cudaSuccess) return fail(nullptr, HTM_ERR_CUDA, cudaGetErrorString(e));
+  return HTM_OK;
+}
+
+}  // extern "C"

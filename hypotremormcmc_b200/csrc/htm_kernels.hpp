@@ -1,0 +1,84 @@
+// Host-visible launch interface of the CUDA translation units of libhtm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/htm_b200.h"
+
+namespace htm {
+
+// device tables of one shard (see htm_forward.cuh for the layouts); pointers are real4 /
+// real2 arrays of the handle's precision
+struct Tables {
+  const void* sta4 = nullptr;      // [S]
+  const void* obs4 = nullptr;      // [E][S], fixed globals folded in (mode B)
+  const void* obs4_raw = nullptr;  // [E][S], no station terms folded (loglik, modes A and C)
+  const void* evc4 = nullptr;      // [E]
+  const void* prior_xy = nullptr;  // [E] real2 {x_mu, y_mu}
+};
+
+// everything a factorised-mode launch needs
+struct FactLaunch {
+  int precision = 32;
+  int kernel = HTM_KERNEL_LANE_PER_CHAIN;
+  int slots = 0;  // lane kernel: chains per thread (1, 2 or 4); 0 = choose
+  Tables tab;
+  void *x = nullptr, *y = nullptr, *z = nullptr, *L = nullptr, *T = nullptr;  // real[E*R*K]
+  int E = 0, S = 0, R = 0, K = 0, n_cool = 0;
+  int iter_first = 0, iter_last = 0, n_burn = 0, n_interval = 1;
+  uint64_t seed = 0;
+  uint32_t event_offset = 0;
+  double vs = 0, qs = 0;
+  double prior_z = 0, width_z = 0, width_xy = 0, step_xy = 0, step_z = 0;
+  unsigned long long* counts = nullptr;  // [14]: n_propose[7], n_accept[7]
+  void* samples = nullptr;               // real4 [cap][R][n_cool][E] or null
+  int rec_origin = 0;                    // record id ((it-1)/n_interval) stored in slot 0
+  int rec_cap = 0;
+  uint32_t* hist = nullptr;  // [E][3][bins] or null
+  int hist_bins = 0;
+  double hist_hw = 0, hist_zmax = 0;
+  htm_step_trace* trace = nullptr;  // debug: [n_it][E][R][K]
+  htm_swap_trace* swaps = nullptr;  // debug: [n_it][E][R]
+};
+
+// returns the number of kernels launched through *n_launches
+cudaError_t launch_factorised(const FactLaunch& a, cudaStream_t stream, int* n_launches, const char** why);
+// generate_model + temperatures + initial log-likelihood of every chain (Philox)
+cudaError_t launch_factorised_init(const FactLaunch& a, double temp_high, int ladder, cudaStream_t stream);
+
+// batched full log-likelihood: hypo[M][3E], tc[M][S], ac[M][S], vs[M], qs[M] (device, double)
+// -> per_event[M][E] (device, double), L[M] (device, double)
+cudaError_t launch_loglik(int precision, const Tables& tab, int E, int S, int M, const double* hypo,
+                          const double* tc, const double* ac, const double* vs, const double* qs,
+                          double* per_event, double* L, cudaStream_t stream);
+
+// mode A replay (float64)
+struct ReplayLaunch {
+  Tables tab;  // double tables, obs4_raw
+  int E = 0, S = 0, R = 0, K = 0;
+  int iter_first = 0, iter_last = 0;
+  double p_vs = 0, p_t_corr = 0, p_qs = 0, p_a_corr = 0;
+  // per-parameter prior / step tables
+  const double* prior_xy = nullptr;  // [E][2]
+  double prior_z = 0, width_z = 0, width_xy = 0, step_xy = 0, step_z = 0;
+  double prior_vs = 0, width_vs = 0, step_vs = 0, prior_qs = 0, width_qs = 0, step_qs = 0;
+  double prior_tc = 0, width_tc = 0, step_tc = 0, prior_ac = 0, width_ac = 0, step_ac = 0;
+  // chain state [R*K]...
+  double* hypo = nullptr;  // [C][3E]
+  double* tc = nullptr;    // [C][S]
+  double* ac = nullptr;    // [C][S]
+  double *vs = nullptr, *qs = nullptr, *temp = nullptr, *L = nullptr;  // [C]
+  unsigned long long* chain_counts = nullptr;                           // [C][14]
+  const int32_t* draws = nullptr;   // concatenated per-rank streams
+  const int64_t* draw_off = nullptr;  // [R+1] offsets into draws
+  int64_t* cursor = nullptr;        // [R] consumed words (in/out)
+  htm_step_trace* trace = nullptr;
+  htm_swap_trace* swaps = nullptr;
+  int32_t* status = nullptr;  // 0 ok, 1 draws exhausted
+};
+cudaError_t launch_replay(const ReplayLaunch& a, cudaStream_t stream);
+
+// FFMA / MUFU microbenchmark (roofline denominators)
+cudaError_t measure_fp32_peak(int device, double* tflops, double* mufu_gops);
+
+}  // namespace htm

@@ -1,0 +1,207 @@
+"""TEST INFRASTRUCTURE -- ctypes wrapper of oracle/libhtm_oracle.so (the C++ restatement of
+the reference hot path).  Never imported by the product package."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from hypotremormcmc_b200.config import (HtmConfig, copy_config, STEP_TRACE_DTYPE, SWAP_TRACE_DTYPE,
+                                        MODE_FACTORISED)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "libhtm_oracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libhtm_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = ctypes.CDLL(path)
+        L.hto_create.restype = ctypes.c_void_p
+        L.hto_partial_update.restype = ctypes.c_double
+        L.hto_perturb.restype = ctypes.c_double
+        L.hto_run_threaded.restype = ctypes.c_double
+        L.hto_n_draws.restype = ctypes.c_int64
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
+
+
+def rng_seeds(rank):
+    out = (ctypes.c_int32 * 4)()
+    lib().hto_rng_seeds(rank, out)
+    return list(out)
+
+
+def rng_draw(rank, kind, n):
+    """kind: 0 rand_u, 1 rand_u2, 2 rand_g, 3 rand_r, 4 raw w"""
+    out = np.empty(n)
+    lib().hto_rng_draw(rank, kind, n, _d(out))
+    return out
+
+
+def philox(seed, c0, c1, c2, c3):
+    out = (ctypes.c_uint32 * 4)()
+    lib().hto_philox(ctypes.c_uint64(seed), ctypes.c_uint32(c0), ctypes.c_uint32(c1), ctypes.c_uint32(c2),
+                     ctypes.c_uint32(c3), out)
+    return list(out)
+
+
+def perturb(x_old, mu, sigma, step, prior_type, g):
+    lpr, ok = ctypes.c_double(), ctypes.c_int32()
+    f = lib().hto_perturb
+    f.argtypes = [ctypes.c_double] * 4 + [ctypes.c_int32, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
+                                          ctypes.POINTER(ctypes.c_int32)]
+    xn = f(x_old, mu, sigma, step, prior_type, g, ctypes.byref(lpr), ctypes.byref(ok))
+    return xn, lpr.value, bool(ok.value)
+
+
+def judge_swap(t1, t2, l1, l2, r):
+    f = lib().hto_judge_swap
+    f.argtypes = [ctypes.c_double] * 5
+    return bool(f(t1, t2, l1, l2, r))
+
+
+class Oracle:
+    def __init__(self, cfg, syn, event_offset=0):
+        self.L = lib()
+        self.cfg = copy_config(cfg)
+        self.cfg.n_events = syn.n_events
+        self.E, self.S = syn.n_events, syn.n_sta
+        self.R, self.K = cfg.n_procs, cfg.n_chains
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in
+                (syn.sta_x, syn.sta_y, syn.sta_z, syn.t_obs, syn.t_stdv, syn.a_obs, syn.a_stdv,
+                 syn.x_mu, syn.y_mu)]
+        self._keep = arrs
+        self.h = ctypes.c_void_p(self.L.hto_create(ctypes.byref(self.cfg), *[_d(a) for a in arrs]))
+        if event_offset:
+            self.L.hto_set_event_offset(self.h, ctypes.c_int32(event_offset))
+
+    def close(self):
+        if self.h:
+            self.L.hto_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_globals(self, vs, qs, t_corr, a_corr):
+        tc = np.ascontiguousarray(t_corr, dtype=np.float64)
+        ac = np.ascontiguousarray(a_corr, dtype=np.float64)
+        self.L.hto_set_globals(self.h, ctypes.c_double(vs), ctypes.c_double(qs), _d(tc), _d(ac))
+
+    def loglik(self, hypo, t_corr, a_corr, vs, qs, per_event=False):
+        hypo = np.ascontiguousarray(hypo, dtype=np.float64)
+        M = hypo.shape[0]
+        tc = np.ascontiguousarray(t_corr, dtype=np.float64)
+        ac = np.ascontiguousarray(a_corr, dtype=np.float64)
+        vs = np.ascontiguousarray(vs, dtype=np.float64)
+        qs = np.ascontiguousarray(qs, dtype=np.float64)
+        L = np.empty(M)
+        pe = np.empty((M, self.E)) if per_event else None
+        self.L.hto_loglik(self.h, ctypes.c_int32(M), _d(hypo), _d(tc), _d(ac), _d(vs), _d(qs), _d(L), _d(pe))
+        return (L, pe) if per_event else L
+
+    def partial_update(self, evt_id, hypo_old, ll_old, hypo_new, t_corr, vs, a_corr, qs):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (hypo_old, hypo_new, t_corr, a_corr)]
+        return self.L.hto_partial_update(self.h, ctypes.c_int32(evt_id), _d(a[0]), ctypes.c_double(ll_old),
+                                         _d(a[1]), _d(a[2]), ctypes.c_double(vs), _d(a[3]), ctypes.c_double(qs))
+
+    def forward_tables(self):
+        n = (self.E, self.S)
+        t = [np.empty(n) for _ in range(4)]
+        self.L.hto_forward_tables(self.h, *[_d(a) for a in t])
+        return dict(t_precision=t[0], log_t_stdv=t[1], a_precision=t[2], log_a_stdv=t[3])
+
+    def record_draws(self, on=True):
+        self.L.hto_record_draws(self.h, ctypes.c_int32(1 if on else 0))
+
+    def init_chains(self):
+        self.L.hto_init_chains(self.h)
+
+    def get_chain_state(self, rank, chain):
+        h = np.empty(3 * self.E)
+        tc, ac = np.empty(self.S), np.empty(self.S)
+        s = [ctypes.c_double() for _ in range(4)]
+        self.L.hto_get_chain_state(self.h, ctypes.c_int32(rank), ctypes.c_int32(chain), _d(h), _d(tc), _d(ac),
+                                   *[ctypes.byref(v) for v in s])
+        return dict(hypo=h, t_corr=tc, a_corr=ac, vs=s[0].value, qs=s[1].value, temp=s[2].value,
+                    log_likelihood=s[3].value)
+
+    def factorised_state(self):
+        shp = (self.E, self.R, self.K)
+        a = [np.empty(shp) for _ in range(5)]
+        self.L.hto_get_factorised_state(self.h, *[_d(v) for v in a])
+        return dict(x=a[0], y=a[1], z=a[2], L=a[3], T=a[4])
+
+    def run(self, iter_first, iter_last, trace=True):
+        n_it = iter_last - iter_first + 1
+        if self.cfg.mode == MODE_FACTORISED:
+            tr = np.zeros((n_it, self.E, self.R, self.K), dtype=STEP_TRACE_DTYPE)
+            sw = np.zeros((n_it, self.E, self.R), dtype=SWAP_TRACE_DTYPE)
+        else:
+            tr = np.zeros((n_it, self.R, self.K), dtype=STEP_TRACE_DTYPE)
+            sw = np.zeros(n_it, dtype=SWAP_TRACE_DTYPE)
+        if trace:
+            self.L.hto_run(self.h, ctypes.c_int32(iter_first), ctypes.c_int32(iter_last),
+                           ctypes.c_void_p(tr.ctypes.data), ctypes.c_void_p(sw.ctypes.data))
+            return tr, sw
+        self.L.hto_run(self.h, ctypes.c_int32(iter_first), ctypes.c_int32(iter_last), None, None)
+        return None, None
+
+    def run_threaded(self, iter_first, iter_last):
+        """mode A with one thread per virtual rank; returns wall seconds"""
+        return self.L.hto_run_threaded(self.h, ctypes.c_int32(iter_first), ctypes.c_int32(iter_last))
+
+    def draws(self, rank):
+        n = self.L.hto_n_draws(self.h, ctypes.c_int32(rank))
+        buf = np.empty(n, dtype=np.int32)
+        if n:
+            self.L.hto_get_draws(self.h, ctypes.c_int32(rank), buf.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+        return buf
+
+    def clear_draws(self):
+        self.L.hto_clear_draws(self.h)
+
+    def get_counts(self):
+        p, a = np.zeros(7, dtype=np.int64), np.zeros(7, dtype=np.int64)
+        lp = ctypes.POINTER(ctypes.c_int64)
+        self.L.hto_get_counts(self.h, p.ctypes.data_as(lp), a.ctypes.data_as(lp))
+        return p, a
+
+    def fetch_samples(self, rank):
+        n = self.L.hto_n_samples(self.h, ctypes.c_int32(rank))
+        cap = max(n, 1)
+        it = np.empty(cap, dtype=np.int32)
+        vs, qs = np.empty(cap), np.empty(cap)
+        hypo = np.empty((cap, 3 * self.E))
+        tc, ac = np.empty((cap, self.S)), np.empty((cap, self.S))
+        k = ctypes.c_int32()
+        self.L.hto_fetch_samples(self.h, ctypes.c_int32(rank), ctypes.c_int32(cap), ctypes.byref(k),
+                                 it.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _d(vs), _d(qs), _d(hypo),
+                                 _d(tc), _d(ac))
+        k = k.value
+        return dict(iter=it[:k], vs=vs[:k], qs=qs[:k], hypo=hypo[:k], t_corr=tc[:k], a_corr=ac[:k])
+
+    def fetch_likelihood(self, rank):
+        n = self.L.hto_n_likelihood(self.h, ctypes.c_int32(rank))
+        cap = max(n, 1)
+        it = np.empty(cap, dtype=np.int32)
+        lik = np.empty(cap)
+        k = ctypes.c_int32()
+        self.L.hto_fetch_likelihood(self.h, ctypes.c_int32(rank), ctypes.c_int32(cap), ctypes.byref(k),
+                                    it.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _d(lik))
+        return it[:k.value], lik[:k.value]
