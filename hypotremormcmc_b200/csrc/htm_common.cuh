@@ -12,7 +12,7 @@ constexpr double kPi = 3.141592653589793238462643383279502884;
 constexpr double kFreq = 5.0;                     // src/cls_forward.f90:190,234
 constexpr double kLog2PiHalf = 0.91893853320467274178;  // 0.5*log(2*pi), src/cls_forward.f90:5
 
-// Philox counter word c2 ("purpose"); must match oracle/htm_oracle.hpp
+// Philox counter word c2 ("purpose"); the test oracle uses the same numbering
 enum : uint32_t { PHX_STEP = 0, PHX_SWAP = 1, PHX_INIT = 2, PHX_GLOBAL = 3, PHX_TEMP = 4 };
 
 // ---- Philox4x32-10 (replaces mod_random in modes B and C) ---------------------------------

@@ -4,8 +4,8 @@
 // src/hypo_tremor_mcmc.f90:236-284 (propose -> forward -> judge -> record -> swap) runs
 // in-kernel for iter_first..iter_last; chain state stays in registers for the launch.
 //
-// Per-step rules restated from the reference (and from oracle/htm_oracle_run.hpp, which is
-// the CPU statement of exactly this schedule):
+// Per-step rules restated from the reference (the test oracle under oracle/ holds
+// the CPU statement of exactly this schedule and is never linked here):
 //   component  icmp = int(u*3): 0 -> z, 1 -> y, 2 -> x        src/cls_mcmc.f90:161-163
 //   perturb    x' = x + N(0,1)*step; prior ratio               src/cls_model.f90:170-187
 //   judge      ln r <= (L'-L)/T + ln prior ratio                src/cls_mcmc.f90:193-203

@@ -1,0 +1,385 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs ("Tolerances"), plus size-independent properties at
+BASELINE.json's full sizes.
+
+Tolerances (stated here because the reference states none):
+  loglik float64   |L_gpu - L_oracle| <= 1e-12 * max(1, |L|) per event
+  loglik float32   <= 2e-3 absolute per event at S = 50 (measured ~3e-4)
+  replay (mode A)  proposal type / index / prior_ok / accept flags and swap records IDENTICAL at
+                   every step; |L_gpu - L_oracle| <= 1e-9 * max(1, |L|)
+  factorised f64   same, against the oracle's statement of the factorised schedule
+  factorised f32   statistical: two-sample KS against float64 oracle samples
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+import hypotremormcmc_b200 as H
+from oracle.pyoracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+NOSOLVE = dict(solve_vs=0, solve_t_corr=0, solve_qs=0, solve_a_corr=0)
+FLAGS = ("proposal_type", "index", "prior_ok", "accepted")
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))
+
+
+def models(syn, rng, M):
+    E, S = syn.n_events, syn.n_sta
+    hypo = np.stack([np.stack([syn.true_x + rng.normal(0, 3, E), syn.true_y + rng.normal(0, 3, E),
+                               syn.true_z + rng.normal(0, 1, E)], axis=1).ravel() for _ in range(M)])
+    return (hypo, rng.normal(0, 0.2, (M, S)), rng.normal(0, 0.02, (M, S)), rng.uniform(2.6, 3.4, M),
+            rng.uniform(180, 320, M))
+
+
+# ---- cls_forward ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("E,S", [(1, 10), (37, 20), (100, 50), (5, 33), (3, 1), (2, 97)])
+def test_loglik_float64(E, S):
+    syn = H.Synthetic(E, S, 100 + E)
+    args = models(syn, np.random.default_rng(E), 5)
+    cfg = H.default_config(n_sta=S, n_events=E, mode=H.MODE_REPLAY, precision=64)
+    Lo, po_ = Oracle(cfg, syn).loglik(*args, per_event=True)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        Lg, pg = g.loglik(*args, per_event=True)
+    assert rel(pg, po_) <= 1e-12
+    assert rel(Lg, Lo) <= 1e-12
+
+
+def test_loglik_float32_tolerance():
+    syn = H.Synthetic(200, 50, 7)
+    args = models(syn, np.random.default_rng(3), 4)
+    cfg = H.default_config(n_sta=50, n_events=200, mode=H.MODE_FACTORISED, precision=32, **NOSOLVE)
+    Lo, po_ = Oracle(cfg, syn).loglik(*args, per_event=True)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        Lg, pg = g.loglik(*args, per_event=True)
+    assert np.max(np.abs(pg - po_)) <= 2e-3
+    assert rel(Lg, Lo) <= 1e-5
+
+
+def test_loglik_golden_and_degenerate_sigma():
+    import os
+    import types
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "forward_golden.npz"))
+    s = types.SimpleNamespace()
+    s.sta_x, s.sta_y, s.sta_z = G["sta"]
+    s.t_obs, s.t_stdv, s.a_obs, s.a_stdv = G["t_obs"], G["t_stdv"], G["a_obs"], G["a_stdv"]
+    s.n_events, s.n_sta = s.t_obs.shape
+    s.x_mu, s.y_mu = np.zeros(s.n_events), np.zeros(s.n_events)
+    for tag, ut, ua in (("both", 1, 1), ("time", 1, 0), ("amp", 0, 1)):
+        cfg = H.default_config(n_sta=s.n_sta, n_events=s.n_events, mode=H.MODE_REPLAY, precision=64, use_time=ut,
+                               use_amp=ua)
+        with H.HypoTremorB200(cfg) as g:
+            g.load(s)
+            L, pe = g.loglik(G["hypo"], G["t_corr"], G["a_corr"], G["vs"], G["qs"], per_event=True)
+        assert np.allclose(L, G["L_" + tag], rtol=1e-12)
+        assert np.allclose(pe, G["per_event_" + tag], rtol=1e-12, atol=1e-12)
+
+
+def test_loglik_linearity_property_full_size():
+    # size-independent property at C3 size: shifting every observation of an event by a constant
+    # leaves L unchanged (weighted demean, src/cls_forward.f90:166-173)
+    syn = H.Synthetic(10000, 50, 8)
+    args = models(syn, np.random.default_rng(4), 1)
+    cfg = H.default_config(n_sta=50, n_events=10000, mode=H.MODE_REPLAY, precision=64)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        L0, p0 = g.loglik(*args, per_event=True)
+        rng = np.random.default_rng(5)
+        g.set_observations(syn.t_obs + rng.normal(0, 5, (10000, 1)), syn.t_stdv,
+                           syn.a_obs + rng.normal(0, 2, (10000, 1)), syn.a_stdv)
+        L1, p1 = g.loglik(*args, per_event=True)
+    assert rel(p1, p0) <= 1e-10
+    assert abs(L0[0] - p0.sum()) <= 1e-9 * abs(L0[0])
+
+
+# ---- mode A replay (BASELINE config 5) --------------------------------------------------------------
+def replay_case(E, S, R, K, n_it, seed, **kw):
+    syn = H.Synthetic(E, S, seed)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=n_it, n_burn=n_it // 4,
+                           n_interval=10, mode=H.MODE_REPLAY, precision=64, **kw)
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    st = [[o.get_chain_state(r, j) for j in range(K)] for r in range(R)]
+    o.record_draws(True)
+    tr_o, sw_o = o.run(1, n_it)
+    draws = [o.draws(r) for r in range(R)]
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        for r in range(R):
+            for j in range(K):
+                s = st[r][j]
+                g.set_chain_state(r, j, s["hypo"], s["t_corr"], s["a_corr"], s["vs"], s["qs"], s["temp"],
+                                  s["log_likelihood"])
+        tr_g, sw_g, used = g.replay(1, n_it, draws)
+        cg = g.get_counts()
+        fin = [[g.get_chain_state(r, j) for j in range(K)] for r in range(R)]
+    for f in FLAGS:
+        assert np.array_equal(tr_o[f], tr_g[f]), f
+    assert np.array_equal(sw_o, sw_g)
+    assert rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
+    assert np.array_equal(used, [len(d) for d in draws])
+    co = o.get_counts()
+    assert np.array_equal(co[0], cg[0]) and np.array_equal(co[1], cg[1])
+    for r in range(R):
+        for j in range(K):
+            so = o.get_chain_state(r, j)
+            assert np.allclose(fin[r][j]["hypo"], so["hypo"], rtol=1e-11, atol=1e-11)
+            assert fin[r][j]["temp"] == so["temp"]
+            assert abs(fin[r][j]["vs"] - so["vs"]) < 1e-12 and np.allclose(fin[r][j]["t_corr"], so["t_corr"], atol=1e-12)
+
+
+def test_replay_config5_100_events_50_stations():
+    replay_case(100, 50, 4, 5, 3000, 20231006)
+
+
+def test_replay_config1_single_event():
+    replay_case(1, 10, 4, 5, 4000, 20231002)
+
+
+def test_replay_fixed_globals_and_many_ranks():
+    replay_case(6, 7, 11, 2, 600, 31, **NOSOLVE)
+
+
+def test_replay_reports_exhausted_draws():
+    syn = H.Synthetic(3, 6, 1)
+    cfg = H.default_config(n_sta=6, n_events=3, n_procs=2, n_chains=2, n_iter=50, n_burn=0, n_interval=10,
+                           mode=H.MODE_REPLAY, precision=64)
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    o.record_draws(True)
+    o.run(1, 50)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        for r in range(2):
+            for j in range(2):
+                g.set_chain_state(r, j, np.ones(9) * 5, np.zeros(6), np.zeros(6), 3.0, 250.0, 1.0, -9e300)
+        with pytest.raises(H.HtmError) as ei:
+            g.replay(1, 50, [o.draws(0)[:40], o.draws(1)[:40]])
+        assert ei.value.code == H.config.HTM_ERR_DRAWS
+
+
+# ---- mode B factorised: step-exact in float64 against the oracle's statement of the schedule --------
+@pytest.mark.parametrize("kernel,slots", [(2, 1), (2, 2), (2, 4), (1, 0)])
+@pytest.mark.parametrize("E,S,R,K", [(6, 10, 4, 5), (5, 50, 2, 16), (3, 20, 3, 1), (4, 33, 5, 7), (2, 12, 1, 32)])
+def test_factorised_float64_step_exact(kernel, slots, E, S, R, K):
+    if kernel == 1 and K > 16:
+        pytest.skip("warp-per-chain kernel: n_chains <= 16")
+    syn = H.Synthetic(E, S, 13 + E)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=80, n_burn=20, n_interval=8,
+                           mode=H.MODE_FACTORISED, precision=64, kernel=kernel, lane_slots=slots, max_samples=16,
+                           hist_bins=16, **NOSOLVE)
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    tr_o, sw_o = o.run(1, 80)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        tr_g, sw_g = g.run_traced(1, 80)
+        cg = g.get_counts()
+        smp = [g.fetch_samples(r) for r in range(R)]
+        lik = [g.fetch_likelihood(r) for r in range(R)]
+        hist = g.get_histograms()
+    for f in FLAGS:
+        assert np.array_equal(tr_o[f], tr_g[f]), f
+    if K >= 2:
+        assert np.array_equal(sw_o, sw_g)
+    assert rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
+    co = o.get_counts()
+    assert np.array_equal(co[0], cg[0]) and np.array_equal(co[1], cg[1])
+    for r in range(R):
+        so = o.fetch_samples(r)
+        assert np.array_equal(so["iter"], smp[r]["iter"])
+        assert np.allclose(so["hypo"], smp[r]["hypo"], rtol=1e-10, atol=1e-10)
+        lo = o.fetch_likelihood(r)
+        assert np.array_equal(lo[0], lik[r][0]) and np.allclose(lo[1], lik[r][1], rtol=1e-10)
+    # every post-burn-in cold sample landed in exactly one bin per coordinate
+    n_rec_post = sum(len(s["iter"]) for s in smp)
+    assert hist.sum() == 3 * n_rec_post * E
+
+
+def test_factorised_two_cold_chains_and_geometric_ladder():
+    syn = H.Synthetic(4, 15, 3)
+    cfg = H.default_config(n_sta=15, n_events=4, n_procs=2, n_chains=6, n_cool=2, n_iter=60, n_burn=0, n_interval=6,
+                           mode=H.MODE_FACTORISED, precision=64, ladder=H.LADDER_GEOMETRIC, max_samples=16, **NOSOLVE)
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    tr_o, sw_o = o.run(1, 60)
+    for kernel in (1, 2):
+        c = H.copy_config(cfg, kernel=kernel)
+        with H.HypoTremorB200(c) as g:
+            g.load(syn)
+            g.init_chains()
+            tr_g, sw_g = g.run_traced(1, 60)
+            s0 = g.fetch_samples(0)
+        for f in FLAGS:
+            assert np.array_equal(tr_o[f], tr_g[f])
+        assert np.array_equal(sw_o, sw_g)
+    so = o.fetch_samples(0)
+    assert len(so["iter"]) == 20 and np.allclose(so["hypo"], s0["hypo"], rtol=1e-10, atol=1e-10)
+
+
+def test_factorised_fixed_globals_are_folded_exactly():
+    syn = H.Synthetic(3, 9, 5)
+    rng = np.random.default_rng(6)
+    tc, ac = rng.normal(0, 0.2, 9), rng.normal(0, 0.02, 9)
+    cfg = H.default_config(n_sta=9, n_events=3, n_procs=1, n_chains=4, n_iter=50, n_burn=0, n_interval=5,
+                           mode=H.MODE_FACTORISED, precision=64, **NOSOLVE)
+    o = Oracle(cfg, syn)
+    o.set_globals(2.7, 310.0, tc, ac)
+    o.init_chains()
+    tr_o, _ = o.run(1, 50)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.set_globals(2.7, 310.0, tc, ac)
+        g.init_chains()
+        tr_g, _ = g.run_traced(1, 50)
+    for f in FLAGS:
+        assert np.array_equal(tr_o[f], tr_g[f])
+    assert rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
+
+
+# ---- size-independent properties at BASELINE sizes ------------------------------------------------------
+def fact_cfg(E, S, R, K, **kw):
+    base = dict(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=400, n_burn=0, n_interval=50,
+                mode=H.MODE_FACTORISED, precision=32, **NOSOLVE)
+    base.update(kw)
+    return H.default_config(**base)
+
+
+def final_state(g, R, K):
+    return [g.get_chain_state(r, k) for r in range(R) for k in (0, K - 1)]
+
+
+def test_chunked_runs_equal_one_run_config2():
+    # idempotence of the launch boundary: run(1,400) == run(1,150) + run(151,400), bit for bit
+    syn = H.Synthetic(1000, 20, 20231002)
+    cfg = fact_cfg(1000, 20, 4, 16, hist_bins=32)
+    with H.HypoTremorB200(cfg) as a, H.HypoTremorB200(cfg) as b:
+        for g in (a, b):
+            g.load(syn)
+            g.init_chains()
+        a.run(1, 400)
+        b.run(1, 150)
+        b.run(151, 400)
+        sa, sb = final_state(a, 4, 16), final_state(b, 4, 16)
+        for x, y in zip(sa, sb):
+            assert np.array_equal(x["hypo"], y["hypo"]) and x["log_likelihood"] == y["log_likelihood"]
+        assert np.array_equal(a.get_histograms(), b.get_histograms())
+        assert np.array_equal(a.get_counts()[0], b.get_counts()[0])
+
+
+def test_kernel_layouts_agree_config2():
+    # lane-per-chain (1, 2, 4 slots) and warp-per-chain run the same chains: identical accept counts in
+    # float64; in float32 the summation order differs, so compare statistically
+    syn = H.Synthetic(500, 20, 77)
+    counts = []
+    for kernel, slots in ((2, 1), (2, 2), (2, 4), (1, 0)):
+        cfg = fact_cfg(500, 20, 4, 16, precision=64, kernel=kernel, lane_slots=slots, n_iter=100)
+        with H.HypoTremorB200(cfg) as g:
+            g.load(syn)
+            g.init_chains()
+            g.run(1, 100)
+            counts.append(g.get_counts())
+    for c in counts[1:]:
+        assert np.array_equal(c[0], counts[0][0])
+        assert np.array_equal(c[1], counts[0][1])
+
+
+def test_event_sharding_is_invariant_config2():
+    # events shard with no exchange step: a shard reproduces its slice of the unsharded run exactly
+    syn = H.Synthetic(1000, 20, 20231002)
+    full_cfg = fact_cfg(1000, 20, 4, 16, n_iter=200)
+    with H.HypoTremorB200(full_cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        g.run(1, 200)
+        full = g.get_chain_state(2, 0)
+        full_counts = g.get_counts()
+    tot = [np.zeros(7, dtype=np.int64), np.zeros(7, dtype=np.int64)]
+    for rank in range(3):
+        sh = syn.shard(rank, 3)
+        cfg = H.copy_config(full_cfg, shard_rank=rank, shard_count=3)
+        with H.HypoTremorB200(cfg) as g:
+            g.load(sh)
+            g.init_chains()
+            g.run(1, 200)
+            part = g.get_chain_state(2, 0)
+            c = g.get_counts()
+        lo = sh.event_offset
+        assert np.array_equal(part["hypo"], full["hypo"][3 * lo:3 * (lo + sh.n_events)])
+        tot[0] += c[0]
+        tot[1] += c[1]
+    assert np.array_equal(tot[0], full_counts[0]) and np.array_equal(tot[1], full_counts[1])
+
+
+def test_counts_and_temperatures_conserved_100k_chains():
+    # >= 100k tempered chains of a 50-station network in lockstep (north_star target size)
+    E, S, R, K = 2000, 50, 4, 16      # 128,000 chains
+    syn = H.Synthetic(E, S, 9)
+    cfg = fact_cfg(E, S, R, K, n_iter=300, n_interval=10, hist_bins=16)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        g.run(1, 300)
+        p, a = g.get_counts()
+        hist = g.get_histograms()
+    assert p[:4].sum() == 0 and p[4:].sum() == 300 * E * R      # exactly one cold chain per group, every step
+    assert np.all(a <= p) and 0.05 < a.sum() / p.sum() < 0.95
+    assert hist.sum() == 3 * 30 * E * R
+
+
+# ---- float32 throughput path: posterior marginals against the float64 reference-schedule oracle -----------
+def test_float32_posterior_matches_reference_schedule_oracle():
+    # correctness part (2) of the north star: posterior marginals of x, y, depth from the B200 float32
+    # factorised kernel vs the oracle's reference schedule (mode A, joint chain, mod_random).
+    # Pass: two-sample KS p > 1e-3 on thinned samples for every marginal, medians within 0.15 sigma.
+    syn = H.Synthetic(2, 8, 23)
+    base = dict(n_sta=8, n_events=2, n_procs=2, n_chains=4, n_cool=1, n_burn=5000, **NOSOLVE)
+    cfgA = H.default_config(mode=H.MODE_REPLAY, precision=64, n_iter=600000, n_interval=11, **base)
+    o = Oracle(cfgA, syn)
+    o.init_chains()
+    o.run(1, cfgA.n_iter, trace=False)
+    sa = np.concatenate([o.fetch_samples(r)["hypo"] for r in range(2)])
+    n_it, interval = 200000, 7
+    for kernel in (1, 2):
+        cfgB = H.default_config(mode=H.MODE_FACTORISED, precision=32, n_iter=n_it, n_interval=interval, kernel=kernel,
+                                max_samples=n_it // interval + 2, **base)
+        with H.HypoTremorB200(cfgB) as g:
+            g.load(syn)
+            g.init_chains()
+            g.run(1, n_it)
+            sb = np.concatenate([g.fetch_samples(r)["hypo"] for r in range(2)])
+        assert len(sb) > 50000
+        for c in range(6):
+            xa, xb = sa[::60, c], sb[::30, c]
+            assert stats.ks_2samp(xa, xb).pvalue > 1e-3, "kernel %d marginal %d" % (kernel, c)
+            assert abs(np.median(xa) - np.median(xb)) < 0.15 * np.std(xa)
+            qa, qb = np.quantile(xa, [0.025, 0.975]), np.quantile(xb, [0.025, 0.975])
+            assert np.all(np.abs(qa - qb) < 0.35 * np.std(xa))
+
+
+def test_float32_prior_only_samples_the_priors():
+    syn = H.Synthetic(64, 6, 22)
+    cfg = H.default_config(n_sta=6, n_events=64, n_procs=2, n_chains=4, n_cool=1, n_iter=20000, n_burn=500,
+                           n_interval=5, mode=H.MODE_FACTORISED, precision=32, use_time=0, use_amp=0,
+                           step_size_xy=45.0, step_size_z=12.0, max_samples=4002, **NOSOLVE)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        g.run(1, 20000)
+        s = np.concatenate([g.fetch_samples(r)["hypo"] for r in range(2)])
+    x = (s[::10, 0::3] - syn.x_mu[None, :]).ravel()
+    z = (s[::10, 2::3] - cfg.prior_z).ravel()
+    assert stats.kstest(x, stats.norm(0, cfg.prior_width_xy).cdf).pvalue > 1e-3
+    assert stats.kstest(z, stats.rayleigh(scale=cfg.prior_width_z).cdf).pvalue > 1e-3
+
+
+def test_fp32_peak_microbenchmark_is_sane():
+    tf, mufu = H.api.measure_fp32_peak(0)
+    assert 30.0 < tf < 90.0          # nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s
+    assert 2000.0 < mufu < 6000.0    # nominal 148 SM x 16 /clk x 1.965 GHz = 4653 Gop/s
