@@ -51,27 +51,63 @@ __device__ __forceinline__ uint32_t below(uint32_t w, uint32_t n) {
 template <typename real>
 struct M;
 
+// raw MUFU approximations, flush-to-zero: no denormal fix-up code around them (inputs here are
+// squared distances, uniforms in (0,1) and temperatures -- never denormal)
+__device__ __forceinline__ float mufu_rsq(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_cos(float x) {
+  float y;
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <>
 struct M<float> {
   typedef float4 real4;
+  static constexpr float kLn2 = 0.6931471805599453f;
   static __device__ __forceinline__ float u_co(uint32_t w) { return static_cast<float>(w >> 8) * (1.0f / 16777216.0f); }
   static __device__ __forceinline__ float u_oo(uint32_t w) {
     return (static_cast<float>(w >> 9) + 0.5f) * (1.0f / 8388608.0f);
   }
-  static __device__ __forceinline__ float log(float x) { return __logf(x); }
-  static __device__ __forceinline__ float sqrt(float x) { return __fsqrt_rn(x); }
+  static __device__ __forceinline__ float log(float x) { return kLn2 * mufu_lg2(x); }
+  static __device__ __forceinline__ float sqrt(float x) { return mufu_sqrt(x); }
   static __device__ __forceinline__ float gauss(uint32_t wa, uint32_t wb) {
-    // sqrt(-2 ln u1) cos(2 pi u2); cos.approx is accurate for |x| <= 2 pi
-    const float r = __fsqrt_rn(-2.0f * __logf(u_oo(wa)));
-    return r * __cosf(6.283185307179586f * u_oo(wb));
+    // sqrt(-2 ln u1) cos(2 pi u2) = sqrt(-2 ln2 lg2 u1) cos(2 pi u2)
+    const float r = mufu_sqrt(-2.0f * kLn2 * mufu_lg2(u_oo(wa)));
+    return r * mufu_cos(6.283185307179586f * u_oo(wb));
   }
   // distance and ln(distance) from the squared distance: two independent MUFU ops
   static __device__ __forceinline__ void dist(float d2, float& d, float& lnd) {
-    d = d2 * rsqrtf(d2);
-    lnd = 0.34657359027997264f * __log2f(d2);  // 0.5*ln2*lg2(d2)
+    d = d2 * mufu_rsq(d2);
+    lnd = 0.34657359027997264f * mufu_lg2(d2);  // 0.5*ln2*lg2(d2)
   }
-  static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
-  static __device__ __forceinline__ float exp(float x) { return __expf(x); }
+  static __device__ __forceinline__ float rcp(float x) { return mufu_rcp(x); }
+  static __device__ __forceinline__ float exp(float x) { return mufu_ex2(x * 1.4426950408889634f); }
+  // a / b where b's reciprocal ib is already known
+  static __device__ __forceinline__ float div(float a, float /*b*/, float ib) { return a * ib; }
 };
 
 template <>
@@ -93,6 +129,8 @@ struct M<double> {
   }
   static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
   static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+  // the reference divides (src/cls_mcmc.f90:194); keep the IEEE division in the parity path
+  static __device__ __forceinline__ double div(double a, double b, double /*ib*/) { return a / b; }
 };
 
 // ---- warp helpers --------------------------------------------------------------------------------

@@ -137,26 +137,27 @@ __device__ __forceinline__ void hist_add(const FactParams<real>& p, int e, real 
 // ================================================================================================
 // Lane-per-chain kernel
 // ================================================================================================
-constexpr int kLaneWarps = 4;  // warps per CTA; every warp is independent (no block barrier)
-
+// Per-chain registers: x, y, z, L, T, 1/T, ln(z - prior_z).  Every warp is independent (own
+// shared-memory slice, own mbarrier, no block barrier), so the CTA size (1, 2 or 4 warps) is
+// chosen by the launcher only to balance warps over the 148 SMs.
 template <typename real, int NSLOT, bool TRACE>
-__global__ void __launch_bounds__(kLaneWarps * 32) fact_lane_kernel(const FactParams<real> p) {
+__global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p) {
   typedef typename M<real>::real4 real4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int K = p.K, S = p.S, R = p.R;
   const int gpw = min(R, 32 / K);   // tempering groups side by side in one slot row
   const int lanes_used = gpw * K;
   const int gps = gpw * NSLOT;      // groups per warp
   const int wpe = (R + gps - 1) / gps;
-  const long gw = static_cast<long>(blockIdx.x) * kLaneWarps + warp;
+  const long gw = static_cast<long>(blockIdx.x) * wpb + warp;
   if (gw >= static_cast<long>(p.E) * wpe) return;  // whole warp leaves; no block barrier below
   const int e = static_cast<int>(gw / wpe), we = static_cast<int>(gw % wpe);
 
   // --- stage this event's tables with 1-D bulk TMA into the warp's slice of shared memory ---
   real4* s_sta = reinterpret_cast<real4*>(smem_raw) + static_cast<size_t>(warp) * 2 * S;
   real4* s_obs = s_sta + S;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(kLaneWarps) * 2 * S * sizeof(real4)) + warp;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(wpb) * 2 * S * sizeof(real4)) + warp;
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -173,10 +174,17 @@ __global__ void __launch_bounds__(kLaneWarps * 32) fact_lane_kernel(const FactPa
   const int gl = lane_ok ? lane / K : 0, k = lane_ok ? lane % K : 0;
   const int base = gl * K;
   const uint32_t gmask = (K == 32 ? 0xffffffffu : ((1u << K) - 1u)) << base;
+  const uint32_t below_me = (1u << lane) - 1u;
+  const real4 evc = p.evc4[e];
+  const typename R2<real>::type pxy = p.prior_xy[e];
+  const Glob<real> g = make_glob<real>(p.vs, p.qs);
+  const uint32_t eg = static_cast<uint32_t>(e) + p.event_offset;
+  const real inv2s2_xy = static_cast<real>(1) / (static_cast<real>(2) * p.width_xy * p.width_xy);
+  const real inv2s2_z = static_cast<real>(1) / (static_cast<real>(2) * p.width_z * p.width_z);
   bool valid[NSLOT];
   int rr[NSLOT];
   size_t ci[NSLOT];
-  real x[NSLOT], y[NSLOT], z[NSLOT], L[NSLOT], T[NSLOT];
+  real x[NSLOT], y[NSLOT], z[NSLOT], L[NSLOT], T[NSLOT], iT[NSLOT], lgz[NSLOT];
   uint32_t cnt_p[3] = {0, 0, 0}, cnt_a[3] = {0, 0, 0};
 #pragma unroll
   for (int q = 0; q < NSLOT; ++q) {
@@ -189,35 +197,65 @@ __global__ void __launch_bounds__(kLaneWarps * 32) fact_lane_kernel(const FactPa
     z[q] = p.z[ci[q]];
     L[q] = p.L[ci[q]];
     T[q] = p.T[ci[q]];
+    iT[q] = static_cast<real>(1) / T[q];
+    lgz[q] = M<real>::log(z[q] - p.prior_z);
   }
-  const real4 evc = p.evc4[e];
-  const typename R2<real>::type pxy = p.prior_xy[e];
-  const Glob<real> g = make_glob<real>(p.vs, p.qs);
-  const uint32_t eg = static_cast<uint32_t>(e) + p.event_offset;
+  // swap draws of a group: lane k of the group owns iteration blk*K + k + 1 (Philox is counter
+  // based, so the words are the same whichever lane evaluates them); refilled every K iterations
+  int sw_pair[NSLOT];
+  real sw_lr[NSLOT];
+  int sw_o = (p.iter_first - 1) % K;                  // offset of `it` inside its block of K iterations
+  int sw_blk0 = (p.iter_first - 1) - sw_o;            // (first iteration of the block) - 1
+  bool sw_fill = true;
+  // recording countdown: iterations left until mod(it, n_interval) == 1
+  int rec_left = ((1 - p.iter_first) % p.n_interval + p.n_interval) % p.n_interval;
+  if (p.n_interval == 1) rec_left = -1;  // mod(it, 1) == 1 never holds (reference quirk Q6)
 
   mbar_wait(bar, 0);
 
   for (int it = p.iter_first; it <= p.iter_last; ++it) {
     // ---- propose (all slots) ----
     int icmp[NSLOT];
-    real nx[NSLOT], ny[NSLOT], nz[NSLOT], lpr[NSLOT];
+    real nx[NSLOT], ny[NSLOT], nz[NSLOT], lpr[NSLOT], nlgz[NSLOT];
     bool ok[NSLOT];
     uint32_t wacc[NSLOT];
 #pragma unroll
     for (int q = 0; q < NSLOT; ++q) {
       const uint32_t gid = (eg * R + rr[q]) * K + k;
       const u32x4 w = philox4x32_10(p.seed, static_cast<uint32_t>(it), gid, PHX_STEP, 0u);
-      propose_hypo<real>(w, x[q], y[q], z[q], pxy.x, pxy.y, p, icmp[q], nx[q], ny[q], nz[q], lpr[q], ok[q]);
       wacc[q] = w.v[3];
+      // model_perturb (src/cls_model.f90:162-190) for component icmp: 0 -> z, 1 -> y, 2 -> x
+      const int ic = static_cast<int>(below(w.v[0], 3u));
+      icmp[q] = ic;
+      const real gs = M<real>::gauss(w.v[1], w.v[2]);
+      const bool isz = ic == 0;
+      const real x_old = isz ? z[q] : (ic == 1 ? y[q] : x[q]);
+      const real mu = isz ? p.prior_z : (ic == 1 ? pxy.y : pxy.x);
+      const real step = isz ? p.step_z : p.step_xy;
+      const real x_new = x_old + gs * step;
+      const real dn = x_new - mu, dl = x_old - mu;
+      real lp = -(dn * dn - dl * dl) * (isz ? inv2s2_z : inv2s2_xy);
+      // type-1 prior: + ln(x_new - mu) - ln(x_old - mu); the second log is carried in lgz
+      const real lgn = M<real>::log(isz ? fabs(dn) : static_cast<real>(1));
+      nlgz[q] = isz ? lgn : lgz[q];
+      lp = isz ? (lp + lgn - lgz[q]) : lp;
+      ok[q] = !isz || (x_new > mu);
+      lpr[q] = lp;
+      nx[q] = ic == 2 ? x_new : x[q];
+      ny[q] = ic == 1 ? x_new : y[q];
+      nz[q] = isz ? x_new : z[q];
     }
     // ---- forward: one pass over the stations serves all NSLOT chains of this thread ----
-    real ct[NSLOT], ca[NSLOT], S1t[NSLOT], S1a[NSLOT], S2[NSLOT];
+    real nct[NSLOT], nca[NSLOT], S1t[NSLOT], S1a[NSLOT], S2[NSLOT];
     {
       const real4 st = s_sta[0];
       const real4 ob = s_obs[0];
 #pragma unroll
       for (int q = 0; q < NSLOT; ++q) {
-        station_resid(nx[q], ny[q], nz[q], g, st, ob, static_cast<real>(0), static_cast<real>(0), ct[q], ca[q]);
+        real ct, ca;
+        station_resid(nx[q], ny[q], nz[q], g, st, ob, static_cast<real>(0), static_cast<real>(0), ct, ca);
+        nct[q] = -ct;
+        nca[q] = -ca;
         S1t[q] = 0;
         S1a[q] = 0;
         S2[q] = 0;
@@ -228,22 +266,18 @@ __global__ void __launch_bounds__(kLaneWarps * 32) fact_lane_kernel(const FactPa
       const real4 st = s_sta[j];
       const real4 ob = s_obs[j];
 #pragma unroll
-      for (int q = 0; q < NSLOT; ++q) {
-        real rt, ra;
-        station_resid(nx[q], ny[q], nz[q], g, st, ob, static_cast<real>(0), static_cast<real>(0), rt, ra);
-        const real et = rt - ct[q], ea = ra - ca[q];
-        const real qt = ob.y * et, qa = ob.w * ea;
-        S1t[q] += qt;
-        S1a[q] += qa;
-        S2[q] += qt * et;
-        S2[q] += qa * ea;
-      }
+      for (int q = 0; q < NSLOT; ++q)
+        station_accum(nx[q], ny[q], nz[q], g, nct[q], nca[q], st, ob, S1t[q], S1a[q], S2[q]);
     }
+    const bool rec_now = rec_left == 0;
     // ---- judge, count, record, swap ----
 #pragma unroll
     for (int q = 0; q < NSLOT; ++q) {
       const real Lnew = finish_loglik<real>(S1t[q], S2[q], S1a[q], static_cast<real>(0), evc);
-      const bool acc = judge<real>(Lnew, L[q], T[q], lpr[q], ok[q], wacc[q]);
+      // mcmc_judge_model (src/cls_mcmc.f90:193-203)
+      const real ratio = M<real>::div(Lnew - L[q], T[q], iT[q]) + lpr[q];
+      const real ru = M<real>::u_co(wacc[q]);
+      const bool acc = ok[q] && (ru > static_cast<real>(0)) && (M<real>::log(ru) <= ratio);
       const bool cold = is_cold<real>(T[q]);
       if (cold && valid[q]) {  // invalid lanes clone a valid chain and must not count
 #pragma unroll
@@ -252,12 +286,11 @@ __global__ void __launch_bounds__(kLaneWarps * 32) fact_lane_kernel(const FactPa
           cnt_a[c] += (acc && icmp[q] == c) ? 1u : 0u;
         }
       }
-      if (acc) {
-        x[q] = nx[q];
-        y[q] = ny[q];
-        z[q] = nz[q];
-        L[q] = Lnew;
-      }
+      x[q] = acc ? nx[q] : x[q];
+      y[q] = acc ? ny[q] : y[q];
+      z[q] = acc ? nz[q] : z[q];
+      L[q] = acc ? Lnew : L[q];
+      lgz[q] = acc ? nlgz[q] : lgz[q];
       if (TRACE) {
         if (valid[q] && p.trace) {
           htm_step_trace t;
@@ -270,10 +303,10 @@ __global__ void __launch_bounds__(kLaneWarps * 32) fact_lane_kernel(const FactPa
         }
       }
       // record (src/hypo_tremor_mcmc.f90:270-280)
-      if ((it % p.n_interval) == 1) {
+      if (rec_now) {
         const uint32_t coldmask = __ballot_sync(0xffffffffu, cold && valid[q]);
         if (cold && valid[q]) {
-          const int m = __popc(coldmask & gmask & ((1u << lane) - 1u));
+          const int m = __popc(coldmask & gmask & below_me);
           const int slot = (it - 1) / p.n_interval - p.rec_origin;
           if (p.samples && slot >= 0 && slot < p.rec_cap && m < p.n_cool) {
             real4 rec;
@@ -286,38 +319,58 @@ __global__ void __launch_bounds__(kLaneWarps * 32) fact_lane_kernel(const FactPa
           if (p.hist && it > p.n_burn) hist_add<real>(p, e, x[q], y[q], z[q], pxy.x, pxy.y);
         }
       }
-      // swap inside the tempering group (src/cls_parallel.f90:100-216)
+      // swap inside the tempering group (src/cls_parallel.f90:100-216, 285-302)
       if (K >= 2) {
-        const uint32_t grp = eg * R + rr[q];
-        const u32x4 w = philox4x32_10(p.seed, static_cast<uint32_t>(it), grp, PHX_SWAP, 0u);
-        const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(K)));
-        int i2 = i1 + 1 + static_cast<int>(below(w.v[1], static_cast<uint32_t>(K - 1)));
-        if (i2 >= K) i2 -= K;
-        const real L1 = __shfl_sync(0xffffffffu, L[q], base + i1);
-        const real L2 = __shfl_sync(0xffffffffu, L[q], base + i2);
-        const real T1 = __shfl_sync(0xffffffffu, T[q], base + i1);
-        const real T2 = __shfl_sync(0xffffffffu, T[q], base + i2);
-        const bool sacc = judge_swap<real>(T1, T2, L1, L2, w.v[2]);
-        if (sacc) {
-          if (k == i1)
-            T[q] = T2;
-          else if (k == i2)
-            T[q] = T1;
+        if (sw_fill) {
+          const uint32_t grp = eg * R + rr[q];
+          const u32x4 w = philox4x32_10(p.seed, static_cast<uint32_t>(sw_blk0 + k + 1), grp, PHX_SWAP, 0u);
+          const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(K)));
+          int i2 = i1 + 1 + static_cast<int>(below(w.v[1], static_cast<uint32_t>(K - 1)));
+          if (i2 >= K) i2 -= K;
+          sw_pair[q] = i1 | (i2 << 8);
+          const real ru2 = M<real>::u_co(w.v[2]);
+          // ln r; r = 0 can never be accepted (r >= eps fails, :295): use -inf surrogate
+          sw_lr[q] = ru2 > static_cast<real>(0) ? M<real>::log(ru2) : static_cast<real>(3.0e38);
         }
+        const int pair = __shfl_sync(0xffffffffu, sw_pair[q], base + sw_o);
+        const real lr = __shfl_sync(0xffffffffu, sw_lr[q], base + sw_o);
+        const int i1 = pair & 0xff, i2 = pair >> 8;
+        // the two chains of the pair read each other; every other lane reads garbage it ignores
+        const int partner = (k == i1) ? i2 : i1;
+        const real Lp = __shfl_sync(0xffffffffu, L[q], base + partner);
+        const real Tp = __shfl_sync(0xffffffffu, T[q], base + partner);
+        const real iTp = __shfl_sync(0xffffffffu, iT[q], base + partner);
+        // del_s = (L2 - L1)(1/T1 - 1/T2) is symmetric under exchanging the roles of 1 and 2
+        const real del_s = (Lp - L[q]) * (iT[q] - iTp);
+        const bool sacc = lr <= del_s;
+        const bool mine = (k == i1) || (k == i2);
         if (TRACE) {
+          const int a1 = __shfl_sync(0xffffffffu, sacc ? 1 : 0, base + i1);
           if (valid[q] && k == 0 && p.swaps) {
             htm_swap_trace t;
             t.rank1 = rr[q];
             t.chain1 = i1 + 1;
             t.rank2 = rr[q];
             t.chain2 = i2 + 1;
-            t.accepted = sacc ? 1 : 0;
+            t.accepted = a1;
             t.reserved = 0;
             p.swaps[(static_cast<size_t>(it - p.iter_first) * p.E + e) * R + rr[q]] = t;
           }
         }
+        if (sacc && mine) {
+          T[q] = Tp;
+          iT[q] = iTp;
+        }
       }
     }
+    // advance the swap-draw window and the recording countdown
+    sw_fill = false;
+    if (++sw_o == K) {
+      sw_o = 0;
+      sw_blk0 += K;
+      sw_fill = true;
+    }
+    rec_left = rec_now ? p.n_interval - 1 : rec_left - 1;
   }
 
   // ---- write back ----
@@ -619,20 +672,23 @@ static cudaError_t launch_lane(const FactLaunch& a, cudaStream_t stream) {
   const int gps = gpw * NSLOT;
   const int wpe = (a.R + gps - 1) / gps;
   const long n_warps = static_cast<long>(a.E) * wpe;
-  const unsigned grid = static_cast<unsigned>((n_warps + kLaneWarps - 1) / kLaneWarps);
-  const size_t smem = static_cast<size_t>(kLaneWarps) * (2 * a.S * sizeof(real4) + sizeof(uint64_t));
+  // warps are independent, so the CTA size only sets how evenly they spread over the SMs:
+  // 1-warp CTAs while everything is resident at once (<= 32 CTAs/SM), else 2 or 4
+  const int wpb = n_warps <= 148L * 32 ? 1 : (n_warps <= 148L * 64 ? 2 : 4);
+  const unsigned grid = static_cast<unsigned>((n_warps + wpb - 1) / wpb);
+  const size_t smem = static_cast<size_t>(wpb) * (2 * a.S * sizeof(real4) + sizeof(uint64_t));
   const bool trace = a.trace || a.swaps;
   cudaError_t err;
   if (trace) {
     err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    fact_lane_kernel<real, NSLOT, true><<<grid, kLaneWarps * 32, smem, stream>>>(p);
+    fact_lane_kernel<real, NSLOT, true><<<grid, wpb * 32, smem, stream>>>(p);
   } else {
     err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    fact_lane_kernel<real, NSLOT, false><<<grid, kLaneWarps * 32, smem, stream>>>(p);
+    fact_lane_kernel<real, NSLOT, false><<<grid, wpb * 32, smem, stream>>>(p);
   }
   return cudaGetLastError();
 }
@@ -682,7 +738,7 @@ static cudaError_t launch_factorised_t(const FactLaunch& a, cudaStream_t stream,
     *why = "warp-per-chain kernel supports n_sta <= 128; use the lane-per-chain kernel";
     return cudaErrorInvalidValue;
   }
-  const size_t smem_need = static_cast<size_t>(kLaneWarps) * (2 * a.S * sizeof(typename M<real>::real4) + 8);
+  const size_t smem_need = static_cast<size_t>(4) * (2 * a.S * sizeof(typename M<real>::real4) + 8);
   if (smem_need > 200 * 1024) {
     *why = "n_sta too large for the shared-memory staging of the lane-per-chain kernel";
     return cudaErrorInvalidValue;

@@ -37,9 +37,9 @@ template <typename real>
 __device__ __forceinline__ Glob<real> make_glob(real vs, real qs) {
   Glob<real> g;
   g.beta = vs;
-  g.ivs = M<real>::rcp(vs);
+  g.ivs = static_cast<real>(1) / vs;  // once per launch: exact division, not the MUFU approximation
   g.qbeta = qs * vs;
-  g.B = static_cast<real>(kPi * kFreq) * M<real>::rcp(g.qbeta);
+  g.B = static_cast<real>(kPi * kFreq) / g.qbeta;
   return g;
 }
 
@@ -63,6 +63,37 @@ __device__ __forceinline__ void station_resid(double px, double py, double pz, c
   const double d = ::sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
   rt = (d / g.beta - tc) - ob.x;
   ra = (-d * kPi * kFreq / g.qbeta - ::log(d) - ac) - ob.z;
+}
+
+// One station's contribution to the shifted sums S1t = sum w_t (r_t - c_t), S1a, and
+// S2 = sum w_t (r_t - c_t)^2 + w_a (r_a - c_a)^2, given nct = -c_t, nca = -c_a.
+// float: the shift rides in the FMA addend (18 FP + 2 MUFU per station).
+__device__ __forceinline__ void station_accum(float px, float py, float pz, const Glob<float>& g, float nct,
+                                              float nca, const float4 st, const float4 ob, float& S1t, float& S1a,
+                                              float& S2) {
+  const float dx = px - st.x, dy = py - st.y, dz = pz - st.z;
+  const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+  const float d = d2 * mufu_rsq(d2);
+  const float l2 = mufu_lg2(d2);
+  const float et = fmaf(d, g.ivs, nct) - ob.x;
+  const float ea = fmaf(-0.34657359027997264f, l2, fmaf(-g.B, d, nca)) - ob.z;
+  const float qt = ob.y * et, qa = ob.w * ea;
+  S1t += qt;
+  S1a += qa;
+  S2 = fmaf(qt, et, S2);
+  S2 = fmaf(qa, ea, S2);
+}
+__device__ __forceinline__ void station_accum(double px, double py, double pz, const Glob<double>& g, double nct,
+                                              double nca, const double4 st, const double4 ob, double& S1t,
+                                              double& S1a, double& S2) {
+  double rt, ra;
+  station_resid(px, py, pz, g, st, ob, 0.0, 0.0, rt, ra);
+  const double et = rt + nct, ea = ra + nca;
+  const double qt = ob.y * et, qa = ob.w * ea;
+  S1t += qt;
+  S1a += qa;
+  S2 += qt * et;
+  S2 += qa * ea;
 }
 
 template <typename real>
