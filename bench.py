@@ -47,8 +47,8 @@ def parse():
     ap.add_argument("--stations", type=int, default=20)
     ap.add_argument("--ranks", type=int, default=4, help="virtual ranks = independent tempering groups per event")
     ap.add_argument("--chains", type=int, default=16, help="chains (temperatures) per rank")
-    ap.add_argument("--iters", type=int, default=2000, help="iterations per step")
-    ap.add_argument("--interval", type=int, default=100)
+    ap.add_argument("--iters", type=int, default=20000, help="iterations per step")
+    ap.add_argument("--interval", type=int, default=1000)
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 warp-per-chain, 2 lane-per-chain")
     ap.add_argument("--slots", type=int, default=0)
@@ -76,50 +76,58 @@ def make_cfg(H, a, n_events_total, shard_rank, shard_count, device, max_samples,
 # clocks sampled DURING the timed region
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every 20 ms by a thread."""
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.sm, self.reasons, self.stop_flag, self.max_mhz, self.err = device, [], set(), False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through the UUID-free common case
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.device
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.device])
+                except (ValueError, IndexError):
+                    idx = self.device
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as ex:  # no NVML: report that, do not fail the bench
+            self.err = "nvml unavailable: %r" % (ex,)
+            return
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop(self):
+        nv = self.nv
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, b in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+            except Exception as ex:
+                self.err = repr(ex)
+                break
+            time.sleep(0.02)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 8:
-                continue
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if r[4 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.err and not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "samples": 0, "reasons": [self.err]}
+        self.th.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "reasons": sorted(self.reasons)}
 
 
 # ---------------------------------------------------------------------------------------------

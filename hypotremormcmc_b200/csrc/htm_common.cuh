@@ -40,6 +40,40 @@ __device__ __forceinline__ u32x4 philox4x32_10(uint64_t seed, uint32_t c0, uint3
   o.v[3] = c3;
   return o;
 }
+// Same generator with the 10 round keys precomputed on the host (they live in the kernel's
+// constant bank, so the key schedule costs no instructions and no registers).
+struct PhiloxKeys {
+  uint32_t k[20];
+};
+inline PhiloxKeys philox_keys(uint64_t seed) {
+  PhiloxKeys r;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  for (int i = 0; i < 10; ++i) {
+    r.k[2 * i] = k0;
+    r.k[2 * i + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return r;
+}
+__device__ __forceinline__ u32x4 philox4x32_10(const PhiloxKeys& rk, uint32_t c0, uint32_t c1, uint32_t c2,
+                                               uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ rk.k[2 * r];
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
+    c3 = lo0;
+  }
+  u32x4 o;
+  o.v[0] = c0;
+  o.v[1] = c1;
+  o.v[2] = c2;
+  o.v[3] = c3;
+  return o;
+}
 // int(u*n), u = 24-bit uniform in [0,1)
 __device__ __forceinline__ uint32_t below(uint32_t w, uint32_t n) {
   return static_cast<uint32_t>((static_cast<uint64_t>(w >> 8) * n) >> 24);

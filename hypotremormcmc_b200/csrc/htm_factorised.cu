@@ -21,6 +21,7 @@
 //                     stations across lanes in registers, shuffle-tree reductions, swap
 //                     through shared memory + a named barrier per tempering group.
 #include <cstdio>
+#include <cstdlib>
 
 #include "htm_forward.cuh"
 #include "htm_kernels.hpp"
@@ -50,6 +51,7 @@ struct FactParams {
   int E, S, R, K, n_cool;
   int iter_first, iter_last, n_burn, n_interval;
   uint64_t seed;
+  PhiloxKeys rk;  // Philox round keys of `seed`
   uint32_t event_offset;
   real vs, qs, prior_z, width_z, width_xy, step_xy, step_z;
   unsigned long long* counts;
@@ -140,8 +142,9 @@ __device__ __forceinline__ void hist_add(const FactParams<real>& p, int e, real 
 // Per-chain registers: x, y, z, L, T, 1/T, ln(z - prior_z).  Every warp is independent (own
 // shared-memory slice, own mbarrier, no block barrier), so the CTA size (1, 2 or 4 warps) is
 // chosen by the launcher only to balance warps over the 148 SMs.
-template <typename real, int NSLOT, bool TRACE>
+template <typename real, int NSLOT, bool TRACE, bool PACKED>
 __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p) {
+  static_assert(!PACKED || (sizeof(real) == 4 && NSLOT % 2 == 0), "packed math: float32, even slot count");
   typedef typename M<real>::real4 real4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -155,9 +158,11 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
   const int e = static_cast<int>(gw / wpe), we = static_cast<int>(gw % wpe);
 
   // --- stage this event's tables with 1-D bulk TMA into the warp's slice of shared memory ---
-  real4* s_sta = reinterpret_cast<real4*>(smem_raw) + static_cast<size_t>(warp) * 2 * S;
+  constexpr int kF4PerSta = PACKED ? 6 : 2;  // packed: 2 staged + 4 expanded float4 per station
+  real4* s_sta = reinterpret_cast<real4*>(smem_raw) + static_cast<size_t>(warp) * kF4PerSta * S;
   real4* s_obs = s_sta + S;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(wpb) * 2 * S * sizeof(real4)) + warp;
+  uint64_t* bar =
+      reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(wpb) * kF4PerSta * S * sizeof(real4)) + warp;
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -212,6 +217,19 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
   if (p.n_interval == 1) rec_left = -1;  // mod(it, 1) == 1 never holds (reference quirk Q6)
 
   mbar_wait(bar, 0);
+  if constexpr (PACKED) {
+    // expand the staged tables into the duplicated, sign-folded layout of forward_packed()
+    float4* s_pk = reinterpret_cast<float4*>(s_obs + S);
+    for (int j = lane; j < S; j += 32) {
+      const float4 st = reinterpret_cast<const float4*>(s_sta)[j];
+      const float4 ob = reinterpret_cast<const float4*>(s_obs)[j];
+      s_pk[4 * j] = make_float4(-st.x, -st.x, -st.y, -st.y);
+      s_pk[4 * j + 1] = make_float4(-st.z, -st.z, -ob.x, -ob.x);
+      s_pk[4 * j + 2] = make_float4(ob.y, ob.y, -ob.z, -ob.z);
+      s_pk[4 * j + 3] = make_float4(ob.w, ob.w, 0.f, 0.f);
+    }
+    __syncwarp();
+  }
 
   for (int it = p.iter_first; it <= p.iter_last; ++it) {
     // ---- propose (all slots) ----
@@ -222,7 +240,7 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
 #pragma unroll
     for (int q = 0; q < NSLOT; ++q) {
       const uint32_t gid = (eg * R + rr[q]) * K + k;
-      const u32x4 w = philox4x32_10(p.seed, static_cast<uint32_t>(it), gid, PHX_STEP, 0u);
+      const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(it), gid, PHX_STEP, 0u);
       wacc[q] = w.v[3];
       // model_perturb (src/cls_model.f90:162-190) for component icmp: 0 -> z, 1 -> y, 2 -> x
       const int ic = static_cast<int>(below(w.v[0], 3u));
@@ -246,8 +264,11 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
       nz[q] = isz ? x_new : z[q];
     }
     // ---- forward: one pass over the stations serves all NSLOT chains of this thread ----
-    real nct[NSLOT], nca[NSLOT], S1t[NSLOT], S1a[NSLOT], S2[NSLOT];
-    {
+    real S1t[NSLOT], S1a[NSLOT], S2[NSLOT];
+    if constexpr (PACKED) {
+      forward_packed<NSLOT>(reinterpret_cast<const float4*>(s_obs + S), S, nx, ny, nz, g, S1t, S1a, S2);
+    } else {
+      real nct[NSLOT], nca[NSLOT];
       const real4 st = s_sta[0];
       const real4 ob = s_obs[0];
 #pragma unroll
@@ -260,14 +281,14 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
         S1a[q] = 0;
         S2[q] = 0;
       }
-    }
 #pragma unroll 4
-    for (int j = 1; j < S; ++j) {
-      const real4 st = s_sta[j];
-      const real4 ob = s_obs[j];
+      for (int j = 1; j < S; ++j) {
+        const real4 stj = s_sta[j];
+        const real4 obj = s_obs[j];
 #pragma unroll
-      for (int q = 0; q < NSLOT; ++q)
-        station_accum(nx[q], ny[q], nz[q], g, nct[q], nca[q], st, ob, S1t[q], S1a[q], S2[q]);
+        for (int q = 0; q < NSLOT; ++q)
+          station_accum(nx[q], ny[q], nz[q], g, nct[q], nca[q], stj, obj, S1t[q], S1a[q], S2[q]);
+      }
     }
     const bool rec_now = rec_left == 0;
     // ---- judge, count, record, swap ----
@@ -323,7 +344,7 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
       if (K >= 2) {
         if (sw_fill) {
           const uint32_t grp = eg * R + rr[q];
-          const u32x4 w = philox4x32_10(p.seed, static_cast<uint32_t>(sw_blk0 + k + 1), grp, PHX_SWAP, 0u);
+          const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(sw_blk0 + k + 1), grp, PHX_SWAP, 0u);
           const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(K)));
           int i2 = i1 + 1 + static_cast<int>(below(w.v[1], static_cast<uint32_t>(K - 1)));
           if (i2 >= K) i2 -= K;
@@ -643,6 +664,7 @@ static FactParams<real> make_params(const FactLaunch& a) {
   p.n_burn = a.n_burn;
   p.n_interval = a.n_interval;
   p.seed = a.seed;
+  p.rk = philox_keys(a.seed);
   p.event_offset = a.event_offset;
   p.vs = static_cast<real>(a.vs);
   p.qs = static_cast<real>(a.qs);
@@ -664,8 +686,8 @@ static FactParams<real> make_params(const FactLaunch& a) {
   return p;
 }
 
-template <typename real, int NSLOT>
-static cudaError_t launch_lane(const FactLaunch& a, cudaStream_t stream) {
+template <typename real, int NSLOT, bool PACKED>
+static cudaError_t launch_lane_p(const FactLaunch& a, cudaStream_t stream) {
   typedef typename M<real>::real4 real4;
   const FactParams<real> p = make_params<real>(a);
   const int gpw = a.R < 32 / a.K ? a.R : 32 / a.K;
@@ -676,21 +698,30 @@ static cudaError_t launch_lane(const FactLaunch& a, cudaStream_t stream) {
   // 1-warp CTAs while everything is resident at once (<= 32 CTAs/SM), else 2 or 4
   const int wpb = n_warps <= 148L * 32 ? 1 : (n_warps <= 148L * 64 ? 2 : 4);
   const unsigned grid = static_cast<unsigned>((n_warps + wpb - 1) / wpb);
-  const size_t smem = static_cast<size_t>(wpb) * (2 * a.S * sizeof(real4) + sizeof(uint64_t));
+  const size_t smem = static_cast<size_t>(wpb) * ((PACKED ? 6 : 2) * a.S * sizeof(real4) + sizeof(uint64_t));
   const bool trace = a.trace || a.swaps;
   cudaError_t err;
   if (trace) {
-    err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem));
+    err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, true, PACKED>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    fact_lane_kernel<real, NSLOT, true><<<grid, wpb * 32, smem, stream>>>(p);
+    fact_lane_kernel<real, NSLOT, true, PACKED><<<grid, wpb * 32, smem, stream>>>(p);
   } else {
-    err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem));
+    err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, false, PACKED>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    fact_lane_kernel<real, NSLOT, false><<<grid, wpb * 32, smem, stream>>>(p);
+    fact_lane_kernel<real, NSLOT, false, PACKED><<<grid, wpb * 32, smem, stream>>>(p);
   }
   return cudaGetLastError();
+}
+// float32 with an even slot count runs the packed (FFMA2) forward unless HTM_NO_PACK is set
+template <typename real, int NSLOT>
+static cudaError_t launch_lane(const FactLaunch& a, cudaStream_t stream) {
+  if constexpr (sizeof(real) == 4 && NSLOT % 2 == 0) {
+    static const bool no_pack = std::getenv("HTM_NO_PACK") != nullptr;
+    if (!no_pack) return launch_lane_p<real, NSLOT, true>(a, stream);
+  }
+  return launch_lane_p<real, NSLOT, false>(a, stream);
 }
 
 template <typename real, int SPL>
@@ -738,7 +769,7 @@ static cudaError_t launch_factorised_t(const FactLaunch& a, cudaStream_t stream,
     *why = "warp-per-chain kernel supports n_sta <= 128; use the lane-per-chain kernel";
     return cudaErrorInvalidValue;
   }
-  const size_t smem_need = static_cast<size_t>(4) * (2 * a.S * sizeof(typename M<real>::real4) + 8);
+  const size_t smem_need = static_cast<size_t>(4) * (6 * a.S * sizeof(typename M<real>::real4) + 8);
   if (smem_need > 200 * 1024) {
     *why = "n_sta too large for the shared-memory staging of the lane-per-chain kernel";
     return cudaErrorInvalidValue;

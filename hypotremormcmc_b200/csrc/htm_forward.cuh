@@ -96,6 +96,75 @@ __device__ __forceinline__ void station_accum(double px, double py, double pz, c
   S2 += qa * ea;
 }
 
+// ---- packed float32 (FFMA2 / FADD2 / FMUL2): two chains of one thread per instruction -------
+// Shared-memory record per station, 16 floats, every value duplicated so that one 64-bit
+// register pair feeds both chains:  {-X,-X,-Y,-Y} {-Z,-Z,-t,-t} {w_t,w_t,-a,-a} {w_a,w_a,0,0}
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ void packed_geometry(const float2 px, const float2 py, const float2 pz, const float4 r0,
+                                                const float4 r1, float2& d, float2& l2) {
+  const float2 dx = __fadd2_rn(px, f2(r0.x, r0.y));
+  const float2 dy = __fadd2_rn(py, f2(r0.z, r0.w));
+  const float2 dz = __fadd2_rn(pz, f2(r1.x, r1.y));
+  const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+  d = __fmul2_rn(d2, f2(mufu_rsq(d2.x), mufu_rsq(d2.y)));
+  l2 = f2(mufu_lg2(d2.x), mufu_lg2(d2.y));
+}
+template <int NSLOT>
+__device__ __forceinline__ void forward_packed(const float4* __restrict__ s_pk, const int S, const float (&nx)[NSLOT],
+                                               const float (&ny)[NSLOT], const float (&nz)[NSLOT],
+                                               const Glob<float>& g, float (&S1t)[NSLOT], float (&S1a)[NSLOT],
+                                               float (&S2)[NSLOT]) {
+  constexpr int NP = NSLOT / 2;
+  const float2 ivs2 = f2(g.ivs, g.ivs), nB2 = f2(-g.B, -g.B);
+  const float2 nc2 = f2(-0.34657359027997264f, -0.34657359027997264f);
+  float2 px[NP], py[NP], pz[NP], nct[NP], nca[NP], a1t[NP], a1a[NP], a2[NP];
+  {
+    const float4 r0 = s_pk[0], r1 = s_pk[1], r2 = s_pk[2];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      px[p] = f2(nx[2 * p], nx[2 * p + 1]);
+      py[p] = f2(ny[2 * p], ny[2 * p + 1]);
+      pz[p] = f2(nz[2 * p], nz[2 * p + 1]);
+      float2 d, l2;
+      packed_geometry(px[p], py[p], pz[p], r0, r1, d, l2);
+      // shift = raw residual of station 0; keep its negative
+      const float2 rt = __ffma2_rn(d, ivs2, f2(r1.z, r1.w));
+      const float2 ra = __ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, f2(r2.z, r2.w)));
+      nct[p] = f2(-rt.x, -rt.y);
+      nca[p] = f2(-ra.x, -ra.y);
+      a1t[p] = f2(0.f, 0.f);
+      a1a[p] = f2(0.f, 0.f);
+      a2[p] = f2(0.f, 0.f);
+    }
+  }
+#pragma unroll 2
+  for (int j = 1; j < S; ++j) {
+    const float4 r0 = s_pk[4 * j], r1 = s_pk[4 * j + 1], r2 = s_pk[4 * j + 2];
+    const float2 wa = *reinterpret_cast<const float2*>(s_pk + 4 * j + 3);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      float2 d, l2;
+      packed_geometry(px[p], py[p], pz[p], r0, r1, d, l2);
+      const float2 et = __fadd2_rn(__ffma2_rn(d, ivs2, nct[p]), f2(r1.z, r1.w));
+      const float2 ea = __fadd2_rn(__ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, nca[p])), f2(r2.z, r2.w));
+      const float2 qt = __fmul2_rn(f2(r2.x, r2.y), et), qa = __fmul2_rn(wa, ea);
+      a1t[p] = __fadd2_rn(a1t[p], qt);
+      a1a[p] = __fadd2_rn(a1a[p], qa);
+      a2[p] = __ffma2_rn(qt, et, a2[p]);
+      a2[p] = __ffma2_rn(qa, ea, a2[p]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    S1t[2 * p] = a1t[p].x;
+    S1t[2 * p + 1] = a1t[p].y;
+    S1a[2 * p] = a1a[p].x;
+    S1a[2 * p + 1] = a1a[p].y;
+    S2[2 * p] = a2[p].x;
+    S2[2 * p + 1] = a2[p].y;
+  }
+}
+
 template <typename real>
 __device__ __forceinline__ real finish_loglik(real S1t, real S2t, real S1a, real S2a,
                                               const typename M<real>::real4 evc) {
