@@ -284,6 +284,15 @@ def run_b200(a):
     torch.cuda.synchronize()
     e2e_wall = time.perf_counter() - te
     barrier()
+    # ---- the only collective of the path: gather posterior histograms / reduce counters (NCCL) ----
+    gathered = None
+    if world > 1:
+        from hypotremormcmc_b200.gather import gather_run
+        tg = time.perf_counter()
+        hist_all, counts_all = gather_run(g)
+        torch.cuda.synchronize()
+        gathered = {"histogram_events": int(hist_all.shape[0]), "hist_sum": int(hist_all.sum().item()),
+                    "cold_proposals": int(counts_all[:7].sum().item()), "ms": (time.perf_counter() - tg) * 1e3}
     g.close()
 
     # ---- max over ranks ------------------------------------------------------------------------
@@ -334,6 +343,8 @@ def run_b200(a):
                          "flop_per_proposal": flop_per_prop, "mufu_gops_measured": mufu,
                          "kernel": "fact_lane_kernel" if a.kernel != 1 else "fact_warp_kernel"},
         }
+        if gathered:
+            line["nccl_gather"] = gathered
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -383,3 +383,32 @@ def test_fp32_peak_microbenchmark_is_sane():
     tf, mufu = H.api.measure_fp32_peak(0)
     assert 30.0 < tf < 90.0          # nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s
     assert 2000.0 < mufu < 6000.0    # nominal 148 SM x 16 /clk x 1.965 GHz = 4653 Gop/s
+
+
+def test_nccl_gather_of_histograms_and_counts():
+    # the path's only collective (posterior-histogram gather), here over a 1-rank NCCL group
+    import torch
+    import torch.distributed as dist
+    from hypotremormcmc_b200.gather import gather_run
+    import os, socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        syn = H.Synthetic(300, 20, 5)
+        cfg = fact_cfg(300, 20, 4, 16, n_iter=200, n_interval=10, hist_bins=32)
+        with H.HypoTremorB200(cfg) as g:
+            g.load(syn)
+            g.init_chains()
+            g.run(1, 200)
+            hist, counts = gather_run(g)
+            h_ref = g.get_histograms()
+            p, a = g.get_counts()
+        assert np.array_equal(hist.cpu().numpy().astype(np.uint32), h_ref)
+        assert np.array_equal(counts.cpu().numpy(), np.concatenate([p, a]))
+    finally:
+        dist.destroy_process_group()
