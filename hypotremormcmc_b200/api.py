@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .config import (HtmConfig, StepTrace, SwapTrace, HTM_OK, MODE_FACTORISED, MODE_REPLAY,
+from .config import (HtmConfig, StepTrace, SwapTrace, HTM_OK, MODE_FACTORISED, MODE_REPLAY, MODE_BLOCKED_GIBBS,
                      STEP_TRACE_DTYPE, SWAP_TRACE_DTYPE, copy_config)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -213,8 +213,13 @@ class HypoTremorB200:
 
     def run_traced(self, iter_first, iter_last):
         n_it = iter_last - iter_first + 1
-        tr = np.zeros((n_it, self.n_events, self.n_procs, self.n_chains), dtype=STEP_TRACE_DTYPE)
-        sw = np.zeros((n_it, self.n_events, self.n_procs), dtype=SWAP_TRACE_DTYPE)
+        if self.cfg.mode == MODE_BLOCKED_GIBBS:
+            # row n_events of axis 1 is the shared-parameter step; one swap attempt per iteration
+            tr = np.zeros((n_it, self.n_events + 1, self.n_procs, self.n_chains), dtype=STEP_TRACE_DTYPE)
+            sw = np.zeros(n_it, dtype=SWAP_TRACE_DTYPE)
+        else:
+            tr = np.zeros((n_it, self.n_events, self.n_procs, self.n_chains), dtype=STEP_TRACE_DTYPE)
+            sw = np.zeros((n_it, self.n_events, self.n_procs), dtype=SWAP_TRACE_DTYPE)
         self._ck(self.lib.htm_run_traced(self._h, iter_first, iter_last, tr.ctypes.data, sw.ctypes.data))
         return tr, sw
 
@@ -242,8 +247,8 @@ class HypoTremorB200:
     def fetch_samples(self, rank, max_records=1 << 20):
         E, S = self.n_events, self.n_sta
         n = ctypes.c_int32()
-        # first ask how many fit: allocate for max_records bounded by the ring capacity
-        cap = min(max_records, max(1, self.cfg.max_samples) * self.cfg.n_cool)
+        # bounded by the ring capacity (in blocked-Gibbs mode a rank can momentarily hold every cold chain)
+        cap = min(max_records, max(1, self.cfg.max_samples) * self.cfg.n_cool * self.cfg.n_procs)
         it = np.empty(cap, dtype=np.int32)
         vs, qs = np.empty(cap), np.empty(cap)
         hypo = np.empty((cap, 3 * E))
@@ -256,7 +261,7 @@ class HypoTremorB200:
 
     def fetch_likelihood(self, rank, max_records=1 << 20):
         n = ctypes.c_int32()
-        cap = min(max_records, max(1, self.cfg.max_samples) * self.cfg.n_cool)
+        cap = min(max_records, max(1, self.cfg.max_samples) * self.cfg.n_cool * self.cfg.n_procs)
         it = np.empty(cap, dtype=np.int32)
         lik = np.empty(cap)
         self._ck(self.lib.htm_fetch_likelihood(self._h, rank, cap, ctypes.byref(n),

@@ -44,6 +44,13 @@ struct htm_handle_s {
   unsigned long long* d_chain_counts = nullptr;
   long long* d_cursor = nullptr;
   int32_t* d_status = nullptr;
+  // mode C state (device pointers live in gl)
+  GibbsLaunch gl;
+  std::vector<void*> gibbs_bufs;
+  int n_cold_total = 0;
+  std::vector<char> host_hypo_rec;
+  std::vector<int> host_rec_chain;
+  std::vector<double> host_rec_vs, host_rec_qs, host_rec_L, host_rec_tc, host_rec_ac;
   // stats
   bool timed = false;
   int64_t last_launches = 0, last_proposals = 0;
@@ -246,7 +253,88 @@ int32_t alloc_state(htm_handle h) {
   }
   HTM_CK(h, cudaMalloc(&h->d_counts, 14 * sizeof(unsigned long long)));
   HTM_CK(h, cudaMemset(h->d_counts, 0, 14 * sizeof(unsigned long long)));
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
+    GibbsLaunch& g = h->gl;
+    const size_t J = h->C, E = h->E, S = h->S, nt = (E + 31) / 32;
+    h->n_cold_total = h->R * h->cfg.n_cool;
+    auto grab = [&](void** p, size_t bytes) -> cudaError_t {
+      cudaError_t e = cudaMalloc(p, bytes ? bytes : 8);
+      if (e == cudaSuccess) {
+        h->gibbs_bufs.push_back(*p);
+        e = cudaMemset(*p, 0, bytes ? bytes : 8);
+      }
+      return e;
+    };
+    HTM_CK(h, grab(&g.hx, J * E * h->rs));
+    HTM_CK(h, grab(&g.hy, J * E * h->rs));
+    HTM_CK(h, grab(&g.hz, J * E * h->rs));
+    HTM_CK(h, grab(&g.hLe, J * E * h->rs));
+    HTM_CK(h, grab(&g.hLp, J * E * h->rs));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.g_vs), J * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.g_qs), J * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.g_tc), J * S * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.g_ac), J * S * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.g_T), J * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.g_L), J * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.prop_which), J * 4));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.prop_idx), J * 4));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.a_prev), J * 4));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.slot_of), J * 4));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.prop_xnew), J * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.prop_lpr), J * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.part_cur), J * nt * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.part_prop), J * nt * 8));
+    if (h->cfg.max_samples > 0) {
+      h->rec_cap = h->cfg.max_samples;
+      const size_t n = static_cast<size_t>(h->rec_cap) * h->n_cold_total;
+      HTM_CK(h, grab(&g.hypo_rec, n * E * 4 * h->rs));
+      HTM_CK(h, grab(reinterpret_cast<void**>(&g.rec_chain), n * 4));
+      HTM_CK(h, grab(reinterpret_cast<void**>(&g.rec_vs), n * 8));
+      HTM_CK(h, grab(reinterpret_cast<void**>(&g.rec_qs), n * 8));
+      HTM_CK(h, grab(reinterpret_cast<void**>(&g.rec_L), n * 8));
+      HTM_CK(h, grab(reinterpret_cast<void**>(&g.rec_tc), n * S * 8));
+      HTM_CK(h, grab(reinterpret_cast<void**>(&g.rec_ac), n * S * 8));
+    }
+    h->cur_samp.assign(h->R, 0);
+    h->cur_lik.assign(h->R, 0);
+  }
   return HTM_OK;
+}
+
+// fill the launch-invariant part of the mode-C launch description
+void gibbs_launch_of(htm_handle h) {
+  GibbsLaunch& g = h->gl;
+  g.precision = h->cfg.precision;
+  g.tab = tables_of(h);
+  g.E = h->E;
+  g.S = h->S;
+  g.J = h->C;
+  g.K = h->K;
+  g.n_cool_total = h->n_cold_total;
+  g.n_burn = h->cfg.n_burn;
+  g.n_interval = h->cfg.n_interval;
+  g.seed = h->cfg.seed;
+  g.event_offset = static_cast<uint32_t>(h->ev_off);
+  g.prior_z = h->cfg.prior_z;
+  g.width_z = h->cfg.prior_width_z;
+  g.width_xy = h->cfg.prior_width_xy;
+  g.step_xy = h->cfg.step_size_xy;
+  g.step_z = h->cfg.step_size_z;
+  g.solve[0] = h->cfg.solve_vs;
+  g.solve[1] = h->cfg.solve_t_corr;
+  g.solve[2] = h->cfg.solve_qs;
+  g.solve[3] = h->cfg.solve_a_corr;
+  const double pr[4] = {h->cfg.prior_vs, h->cfg.prior_t_corr, h->cfg.prior_qs, h->cfg.prior_a_corr};
+  const double wd[4] = {h->cfg.prior_width_vs, h->cfg.prior_width_t_corr, h->cfg.prior_width_qs, h->cfg.prior_width_a_corr};
+  const double st[4] = {h->cfg.step_size_vs, h->cfg.step_size_t_corr, h->cfg.step_size_qs, h->cfg.step_size_a_corr};
+  for (int t = 0; t < 4; ++t) {
+    g.g_prior[t] = pr[t];
+    g.g_width[t] = wd[t];
+    g.g_step[t] = st[t];
+  }
+  g.counts = h->d_counts;
+  g.rec_origin = h->rec_origin;
+  g.rec_cap = h->rec_cap;
 }
 
 // recorded iterations (mod(it, n_interval) == 1) inside [first, last]: ids m = (it-1)/n_interval
@@ -258,6 +346,30 @@ bool record_ids(int first, int last, int n_interval, int* m_lo, int* m_hi) {
   *m_lo = lo;
   *m_hi = hi;
   return true;
+}
+
+int32_t pull_samples_gibbs(htm_handle h) {
+  if (h->host_samples_valid) return HTM_OK;
+  const size_t n = static_cast<size_t>(h->rec_pending) * h->n_cold_total, E = h->E, S = h->S;
+  h->host_hypo_rec.resize(n * E * 4 * h->rs);
+  h->host_rec_chain.resize(n);
+  h->host_rec_vs.resize(n);
+  h->host_rec_qs.resize(n);
+  h->host_rec_L.resize(n);
+  h->host_rec_tc.resize(n * S);
+  h->host_rec_ac.resize(n * S);
+  if (n > 0) {
+    HTM_CK(h, cudaStreamSynchronize(h->stream));
+    HTM_CK(h, cudaMemcpy(h->host_hypo_rec.data(), h->gl.hypo_rec, h->host_hypo_rec.size(), cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(h->host_rec_chain.data(), h->gl.rec_chain, n * 4, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(h->host_rec_vs.data(), h->gl.rec_vs, n * 8, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(h->host_rec_qs.data(), h->gl.rec_qs, n * 8, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(h->host_rec_L.data(), h->gl.rec_L, n * 8, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(h->host_rec_tc.data(), h->gl.rec_tc, n * S * 8, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(h->host_rec_ac.data(), h->gl.rec_ac, n * S * 8, cudaMemcpyDeviceToHost));
+  }
+  h->host_samples_valid = true;
+  return HTM_OK;
 }
 
 int32_t pull_samples(htm_handle h) {
@@ -349,6 +461,10 @@ int32_t htm_create(htm_handle* out, const htm_config* cfg) {
   if (cfg->mode != HTM_MODE_REPLAY && cfg->mode != HTM_MODE_FACTORISED && cfg->mode != HTM_MODE_BLOCKED_GIBBS)
     return fail(nullptr, HTM_ERR_ARG, "unknown mode");
   if (cfg->hist_bins < 0 || cfg->max_samples < 0) return fail(nullptr, HTM_ERR_ARG, "negative hist_bins/max_samples");
+  if (cfg->mode == HTM_MODE_BLOCKED_GIBBS && cfg->shard_count != 1)
+    return fail(nullptr, HTM_ERR_UNSUPPORTED,
+                "blocked-Gibbs mode on sharded events needs an all-reduce of the per-chain sums per "
+                "iteration; not built yet (single GPU only)");
 
   int n_dev = 0;
   cudaError_t ce = cudaGetDeviceCount(&n_dev);
@@ -410,6 +526,7 @@ int32_t htm_destroy(htm_handle h) {
                   static_cast<void*>(h->d_chain_counts), static_cast<void*>(h->d_cursor),
                   static_cast<void*>(h->d_status)})
     free_dev(p);
+  for (void* p : h->gibbs_bufs) free_dev(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -473,11 +590,19 @@ int32_t htm_init_chains(htm_handle h) {
   if (h->cfg.mode == HTM_MODE_REPLAY)
     return fail(h, HTM_ERR_UNSUPPORTED,
                 "replay mode: chains are initialised by the host's mod_random (htm_set_chain_state)");
-  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS)
-    return fail(h, HTM_ERR_UNSUPPORTED, "blocked-Gibbs mode is not built yet");
   if (!h->have_prior) return fail(h, HTM_ERR_STATE, "xy prior not set (htm_set_xy_prior)");
   int32_t rc = ensure_tables(h);
   if (rc != HTM_OK) return rc;
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
+    gibbs_launch_of(h);
+    HTM_CK(h, launch_gibbs_init(h->gl, h->cfg.temp_high, h->cfg.ladder, h->cfg.n_cool, h->stream));
+    HTM_CK(h, cudaMemsetAsync(h->gl.a_prev, 0, h->C * sizeof(int), h->stream));
+    HTM_CK(h, cudaMemsetAsync(h->d_counts, 0, 14 * sizeof(unsigned long long), h->stream));
+    h->rec_pending = 0;
+    h->host_samples_valid = false;
+    h->chains_ready = true;
+    return HTM_OK;
+  }
   FactLaunch a = fact_launch_of(h);
   HTM_CK(h, launch_factorised_init(a, h->cfg.temp_high, h->cfg.ladder, h->stream));
   HTM_CK(h, cudaMemsetAsync(h->d_counts, 0, 14 * sizeof(unsigned long long), h->stream));
@@ -513,7 +638,8 @@ int32_t htm_set_chain_state(htm_handle h, int32_t rank, int32_t chain, const dou
     // log-likelihoods are recomputed on the device by htm_refresh (next run)
     return fail(h, HTM_ERR_UNSUPPORTED, "htm_set_chain_state: factorised mode initialises with htm_init_chains");
   }
-  return fail(h, HTM_ERR_UNSUPPORTED, "blocked-Gibbs mode is not built yet");
+  return fail(h, HTM_ERR_UNSUPPORTED,
+              "htm_set_chain_state: blocked-Gibbs mode initialises with htm_init_chains");
 }
 
 int32_t htm_get_chain_state(htm_handle h, int32_t rank, int32_t chain, double* hypo, double* t_corr, double* a_corr,
@@ -564,7 +690,31 @@ int32_t htm_get_chain_state(htm_handle h, int32_t rank, int32_t chain, double* h
     if (log_likelihood) *log_likelihood = ls;
     return HTM_OK;
   }
-  return fail(h, HTM_ERR_UNSUPPORTED, "blocked-Gibbs mode is not built yet");
+  // blocked Gibbs: chain c = rank*n_chains + chain
+  {
+    const size_t c = static_cast<size_t>(rank) * h->K + chain, E = h->E, S = h->S;
+    std::vector<char> bx(E * h->rs), by(E * h->rs), bz(E * h->rs);
+    HTM_CK(h, cudaMemcpy(bx.data(), static_cast<char*>(h->gl.hx) + c * E * h->rs, E * h->rs, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(by.data(), static_cast<char*>(h->gl.hy) + c * E * h->rs, E * h->rs, cudaMemcpyDeviceToHost));
+    HTM_CK(h, cudaMemcpy(bz.data(), static_cast<char*>(h->gl.hz) + c * E * h->rs, E * h->rs, cudaMemcpyDeviceToHost));
+    auto at = [&](const std::vector<char>& b, size_t i) -> double {
+      return h->rs == 8 ? reinterpret_cast<const double*>(b.data())[i]
+                        : static_cast<double>(reinterpret_cast<const float*>(b.data())[i]);
+    };
+    if (hypo)
+      for (size_t e = 0; e < E; ++e) {
+        hypo[3 * e] = at(bx, e);
+        hypo[3 * e + 1] = at(by, e);
+        hypo[3 * e + 2] = at(bz, e);
+      }
+    if (t_corr) HTM_CK(h, cudaMemcpy(t_corr, h->gl.g_tc + c * S, S * 8, cudaMemcpyDeviceToHost));
+    if (a_corr) HTM_CK(h, cudaMemcpy(a_corr, h->gl.g_ac + c * S, S * 8, cudaMemcpyDeviceToHost));
+    if (vs) HTM_CK(h, cudaMemcpy(vs, h->gl.g_vs + c, 8, cudaMemcpyDeviceToHost));
+    if (qs) HTM_CK(h, cudaMemcpy(qs, h->gl.g_qs + c, 8, cudaMemcpyDeviceToHost));
+    if (temp) HTM_CK(h, cudaMemcpy(temp, h->gl.g_T + c, 8, cudaMemcpyDeviceToHost));
+    if (log_likelihood) HTM_CK(h, cudaMemcpy(log_likelihood, h->gl.g_L + c, 8, cudaMemcpyDeviceToHost));
+    return HTM_OK;
+  }
 }
 
 int32_t htm_loglik(htm_handle h, int32_t n_models, const double* hypo, const double* t_corr, const double* a_corr,
@@ -611,7 +761,6 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
   if (!h) return HTM_ERR_ARG;
   if (iter_first < 1 || iter_last < iter_first) return fail(h, HTM_ERR_ARG, "need 1 <= iter_first <= iter_last");
   if (h->cfg.mode == HTM_MODE_REPLAY) return fail(h, HTM_ERR_UNSUPPORTED, "replay mode runs through htm_replay");
-  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) return fail(h, HTM_ERR_UNSUPPORTED, "blocked-Gibbs mode is not built yet");
   if (!h->chains_ready) return fail(h, HTM_ERR_STATE, "chains not initialised (htm_init_chains)");
   HTM_CK(h, cudaSetDevice(h->cfg.device));
   int32_t rc = ensure_tables(h);
@@ -619,7 +768,8 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
   // sample ring bookkeeping
   int m_lo = 0, m_hi = -1;
   const bool recs = record_ids(iter_first, iter_last, h->cfg.n_interval, &m_lo, &m_hi);
-  if (h->d_samples && recs) {
+  const bool have_ring = h->cfg.mode == HTM_MODE_BLOCKED_GIBBS ? h->gl.hypo_rec != nullptr : h->d_samples != nullptr;
+  if (have_ring && recs) {
     bool all_consumed = true;
     for (int r = 0; r < h->R; ++r)
       if (h->cur_samp[r] < h->rec_pending || h->cur_lik[r] < h->rec_pending) all_consumed = false;
@@ -637,6 +787,21 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
                   "before running further, or raise max_samples");
     h->rec_pending = m_hi - h->rec_origin + 1;
     h->host_samples_valid = false;
+  }
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
+    gibbs_launch_of(h);
+    h->gl.iter_first = iter_first;
+    h->gl.iter_last = iter_last;
+    h->gl.trace = d_trace;
+    h->gl.swaps = d_swaps;
+    int nlg = 0;
+    HTM_CK(h, cudaEventRecord(h->ev0, h->stream));
+    HTM_CK(h, launch_gibbs(h->gl, h->stream, &nlg));
+    HTM_CK(h, cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->last_launches = nlg;
+    h->last_proposals = static_cast<int64_t>(iter_last - iter_first + 1) * (static_cast<int64_t>(h->E) + 1) * h->C;
+    return HTM_OK;
   }
   FactLaunch a = fact_launch_of(h);
   a.iter_first = iter_first;
@@ -670,7 +835,10 @@ int32_t htm_run_traced(htm_handle h, int32_t iter_first, int32_t iter_last, htm_
   if (iter_first < 1 || iter_last < iter_first) return fail(h, HTM_ERR_ARG, "need 1 <= iter_first <= iter_last");
   HTM_CK(h, cudaSetDevice(h->cfg.device));
   const size_t n_it = static_cast<size_t>(iter_last - iter_first + 1);
-  const size_t nt = n_it * h->E * h->R * h->K, ns = n_it * h->E * h->R;
+  const bool gibbs = h->cfg.mode == HTM_MODE_BLOCKED_GIBBS;
+  // blocked Gibbs: trace [n_it][E+1][J] (row E = shared-parameter step), swaps [n_it]
+  const size_t nt = gibbs ? n_it * (static_cast<size_t>(h->E) + 1) * h->C : n_it * h->E * h->R * h->K;
+  const size_t ns = gibbs ? n_it : n_it * h->E * h->R;
   htm_step_trace* d_t = nullptr;
   htm_swap_trace* d_s = nullptr;
   if (trace) {
@@ -813,9 +981,46 @@ int32_t htm_fetch_samples(htm_handle h, int32_t rank, int32_t max_records, int32
   if (!h || !n_records) return fail(h, HTM_ERR_ARG, "null argument");
   *n_records = 0;
   if (rank < 0 || rank >= h->R) return fail(h, HTM_ERR_ARG, "rank out of range");
-  if (h->cfg.mode != HTM_MODE_FACTORISED) return fail(h, HTM_ERR_UNSUPPORTED, "samples: factorised mode only for now");
-  if (!h->d_samples) return HTM_OK;  // max_samples = 0: nothing is recorded
+  if (h->cfg.mode == HTM_MODE_REPLAY) return fail(h, HTM_ERR_UNSUPPORTED, "samples: not recorded in replay mode");
   HTM_CK(h, cudaSetDevice(h->cfg.device));
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
+    // records of the cold chains that sat on virtual rank `rank`, in loop order (iteration, chain)
+    if (!h->gl.hypo_rec) return HTM_OK;
+    int32_t rcg = pull_samples_gibbs(h);
+    if (rcg != HTM_OK) return rcg;
+    const int E = h->E, S = h->S, nc = h->n_cold_total;
+    int n = 0, rec = h->cur_samp[rank];
+    for (; rec < h->rec_pending; ++rec) {
+      const int it = (h->rec_origin + rec) * h->cfg.n_interval + 1;
+      if (it <= h->cfg.n_burn) continue;
+      int here = 0;
+      for (int sl = 0; sl < nc; ++sl)
+        if (h->host_rec_chain[static_cast<size_t>(rec) * nc + sl] / h->K == rank) ++here;
+      if (n + here > max_records) break;
+      for (int sl = 0; sl < nc; ++sl) {
+        const size_t o = static_cast<size_t>(rec) * nc + sl;
+        if (h->host_rec_chain[o] / h->K != rank) continue;
+        if (iter) iter[n] = it;
+        if (vs) vs[n] = h->host_rec_vs[o];
+        if (qs) qs[n] = h->host_rec_qs[o];
+        if (hypo)
+          for (int e = 0; e < E; ++e)
+            for (int cc = 0; cc < 3; ++cc) {
+              const size_t i = (o * E + e) * 4 + cc;
+              hypo[static_cast<size_t>(n) * 3 * E + 3 * e + cc] =
+                  h->rs == 8 ? reinterpret_cast<const double*>(h->host_hypo_rec.data())[i]
+                             : static_cast<double>(reinterpret_cast<const float*>(h->host_hypo_rec.data())[i]);
+            }
+        if (t_corr) std::memcpy(t_corr + static_cast<size_t>(n) * S, h->host_rec_tc.data() + o * S, S * sizeof(double));
+        if (a_corr) std::memcpy(a_corr + static_cast<size_t>(n) * S, h->host_rec_ac.data() + o * S, S * sizeof(double));
+        ++n;
+      }
+    }
+    h->cur_samp[rank] = rec;
+    *n_records = n;
+    return HTM_OK;
+  }
+  if (!h->d_samples) return HTM_OK;  // max_samples = 0: nothing is recorded
   int32_t rc = pull_samples(h);
   if (rc != HTM_OK) return rc;
   const int nc = h->cfg.n_cool, E = h->E, S = h->S;
@@ -846,9 +1051,33 @@ int32_t htm_fetch_likelihood(htm_handle h, int32_t rank, int32_t max_records, in
   if (!h || !n_records) return fail(h, HTM_ERR_ARG, "null argument");
   *n_records = 0;
   if (rank < 0 || rank >= h->R) return fail(h, HTM_ERR_ARG, "rank out of range");
-  if (h->cfg.mode != HTM_MODE_FACTORISED) return fail(h, HTM_ERR_UNSUPPORTED, "likelihood: factorised mode only for now");
-  if (!h->d_samples) return HTM_OK;
+  if (h->cfg.mode == HTM_MODE_REPLAY) return fail(h, HTM_ERR_UNSUPPORTED, "likelihood: not recorded in replay mode");
   HTM_CK(h, cudaSetDevice(h->cfg.device));
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
+    if (!h->gl.hypo_rec) return HTM_OK;
+    int32_t rcg = pull_samples_gibbs(h);
+    if (rcg != HTM_OK) return rcg;
+    const int nc = h->n_cold_total;
+    int n = 0, rec = h->cur_lik[rank];
+    for (; rec < h->rec_pending; ++rec) {
+      const int it = (h->rec_origin + rec) * h->cfg.n_interval + 1;
+      int here = 0;
+      for (int sl = 0; sl < nc; ++sl)
+        if (h->host_rec_chain[static_cast<size_t>(rec) * nc + sl] / h->K == rank) ++here;
+      if (n + here > max_records) break;
+      for (int sl = 0; sl < nc; ++sl) {
+        const size_t o = static_cast<size_t>(rec) * nc + sl;
+        if (h->host_rec_chain[o] / h->K != rank) continue;
+        if (iter) iter[n] = it;
+        if (log_likelihood) log_likelihood[n] = h->host_rec_L[o];
+        ++n;
+      }
+    }
+    h->cur_lik[rank] = rec;
+    *n_records = n;
+    return HTM_OK;
+  }
+  if (!h->d_samples) return HTM_OK;
   int32_t rc = pull_samples(h);
   if (rc != HTM_OK) return rc;
   const int nc = h->cfg.n_cool, E = h->E;

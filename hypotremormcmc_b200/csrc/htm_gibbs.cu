@@ -1,0 +1,668 @@
+// Mode C (blocked Gibbs): joint chains with the shared parameters solved.
+//
+// J = n_procs*n_chains joint chains, each = {vs, qs, t_corr(S), a_corr(S), T, all E hypocentres}.
+// One iteration (the CPU statement of this exact schedule lives with the test oracle):
+//   1. gibbs_sweep_kernel   every (chain, event) proposes one hypocentre coordinate and judges it on
+//                           the event's own log-likelihood with the chain's temperature
+//                           (src/cls_mcmc.f90:159-165,193-203; src/cls_forward.f90:307-362), then
+//                           evaluates the chain's pending shared-parameter proposal for that event and
+//                           writes per-tile partial sums of L (current and proposed).
+//   2. gibbs_decide_kernel  one CTA: adds the partial sums in a fixed order, judges the shared-parameter
+//                           proposal on the sum over ALL events (src/cls_forward.f90:268-303 is what the
+//                           reference recomputes for such a move), records the cold chains' shared
+//                           parameters, does the one swap attempt over all J chains
+//                           (src/cls_parallel.f90:220-240,285-302) and draws the next proposal.
+// A shared-parameter acceptance is committed lazily: the next sweep picks L_e := L_e(proposed).
+//
+// Mapping of the sweep: CTA = tile of 32 events x up to 8 chains; warp = chain, lane = event.  The
+// tile's observation rows are staged by 32 bulk-TMA copies (one per event) into padded shared-memory
+// rows, so the per-lane 16-byte reads are bank-conflict free; station table and the chains' station
+// terms are warp-broadcast reads.
+#include "htm_forward.cuh"
+#include "htm_kernels.hpp"
+
+namespace htm {
+
+constexpr int kTile = 32;   // events per CTA
+constexpr int kCW = 8;      // chains (warps) per CTA
+
+template <typename real>
+struct GibbsParams {
+  typedef typename M<real>::real4 real4;
+  const real4* sta4;
+  const real4* obs4;  // raw: no station terms folded
+  const real4* evc4;
+  const void* prior_xy;  // real2 [E]
+  real *hx, *hy, *hz, *hLe, *hLp;  // [J][E]
+  double *g_vs, *g_qs, *g_tc, *g_ac, *g_T, *g_L;  // [J], [J][S]
+  int* prop_which;
+  int* prop_idx;
+  double* prop_xnew;
+  double* prop_lpr;
+  int* a_prev;
+  int* slot_of;
+  double *part_cur, *part_prop;  // [J][n_tiles]
+  int E, S, J, K, n_tiles, n_cool_total;
+  int it, n_burn, n_interval;
+  PhiloxKeys rk;
+  uint32_t event_offset;
+  real prior_z, width_z, width_xy, step_xy, step_z;
+  unsigned long long* counts;
+  real4* hypo_rec;  // [cap][n_cool_total][E]
+  int rec_slot;     // ring slot of this iteration, or -1
+  htm_step_trace* trace;  // this iteration's [E+1][J] block, or null
+  htm_swap_trace* swap;   // this iteration's record, or null
+};
+
+template <typename real>
+__device__ __forceinline__ bool gibbs_is_cold(double T) {
+  return T < 1.0 + kEps64;
+}
+
+// one thread, sequential over stations; obs row and station terms in shared memory
+template <typename real>
+__device__ __forceinline__ real event_loglik_corr(const typename M<real>::real4* s_sta,
+                                                  const typename M<real>::real4* s_obs_row,
+                                                  const typename M<real>::real4 evc, int S, real px, real py,
+                                                  real pz, const Glob<real>& g, const real* s_tc, const real* s_ac,
+                                                  int ov_which, int ov_idx, real ov_val) {
+  typedef typename M<real>::real4 real4;
+  real ct = 0, ca = 0, S1t = 0, S1a = 0, S2 = 0;
+#pragma unroll 2
+  for (int j = 0; j < S; ++j) {
+    const real4 st = s_sta[j];
+    const real4 ob = s_obs_row[j];
+    real tc = s_tc[j], ac = s_ac[j];
+    if (j == ov_idx) {
+      if (ov_which == 2) tc = ov_val;
+      if (ov_which == 4) ac = ov_val;
+    }
+    real rt, ra;
+    station_resid(px, py, pz, g, st, ob, tc, ac, rt, ra);
+    if (j == 0) {
+      ct = rt;
+      ca = ra;
+    }
+    const real et = rt - ct, ea = ra - ca;
+    const real qt = ob.y * et, qa = ob.w * ea;
+    S1t += qt;
+    S1a += qa;
+    S2 += qt * et;
+    S2 += qa * ea;
+  }
+  return finish_loglik<real>(S1t, S2, S1a, static_cast<real>(0), evc);
+}
+
+template <typename real, bool TRACE>
+__global__ void __launch_bounds__(kCW * 32) gibbs_sweep_kernel(const GibbsParams<real> p) {
+  typedef typename M<real>::real4 real4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, J = p.J, E = p.E;
+  const int tile = blockIdx.x, e = tile * kTile + lane;
+  const int c = blockIdx.y * kCW + warp;
+  const int row = S + 1;  // padded row stride (in real4) -> conflict-free per-lane LDS.128
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // 16 bytes reserved
+  real4* s_obs = reinterpret_cast<real4*>(smem_raw + 16);     // [kTile][row]
+  real4* s_sta = s_obs + kTile * row;                          // [S]
+  real* s_tc = reinterpret_cast<real*>(s_sta + S);             // [kCW][S]
+  real* s_ac = s_tc + kCW * S;                                 // [kCW][S]
+  const int n_ev = min(kTile, E - tile * kTile);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t bytes = static_cast<uint32_t>(S * sizeof(real4));
+    if (lane == 0) mbar_expect_tx(bar, bytes * (n_ev + 1));
+    __syncwarp();
+    if (lane < n_ev) tma_load_1d(s_obs + lane * row, p.obs4 + static_cast<size_t>(tile * kTile + lane) * S, bytes, bar);
+    if (lane == 0) tma_load_1d(s_sta, p.sta4, bytes, bar);
+  }
+  // this chain's station terms (current values) -> shared memory
+  const bool chain_ok = c < J;
+  if (chain_ok) {
+    for (int j = lane; j < S; j += 32) {
+      s_tc[warp * S + j] = static_cast<real>(p.g_tc[static_cast<size_t>(c) * S + j]);
+      s_ac[warp * S + j] = static_cast<real>(p.g_ac[static_cast<size_t>(c) * S + j]);
+    }
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  if (!chain_ok) return;
+
+  const bool ev_ok = e < E;
+  const int ee = ev_ok ? e : E - 1;  // clamp: idle lanes clone the last event, never write
+  const size_t ci = static_cast<size_t>(c) * E + ee;
+  const double Td = p.g_T[c];
+  const real T = static_cast<real>(Td), iT = static_cast<real>(1) / T;
+  const bool cold = gibbs_is_cold<real>(Td);
+  const real vs = static_cast<real>(p.g_vs[c]), qs = static_cast<real>(p.g_qs[c]);
+  const Glob<real> g = make_glob<real>(vs, qs);
+  const int which = p.prop_which[c], pidx = p.prop_idx[c];
+  const real pval = static_cast<real>(p.prop_xnew[c]);
+  const real4 evc = p.evc4[ee];
+  const typename M<real>::real4* obs_row = s_obs + (ev_ok ? lane : n_ev - 1) * row;
+  const real* tc = s_tc + warp * S;
+  const real* ac = s_ac + warp * S;
+  real x = p.hx[ci], y = p.hy[ci], z = p.hz[ci];
+  real Le = p.a_prev[c] ? p.hLp[ci] : p.hLe[ci];  // lazy commit of the last shared-parameter acceptance
+
+  // ---- 1. hypocentre step (same rule as the factorised kernels) ----
+  const uint32_t gid = (static_cast<uint32_t>(ee) + p.event_offset) * static_cast<uint32_t>(J) + static_cast<uint32_t>(c);
+  const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(p.it), gid, PHX_STEP, 0u);
+  const int icmp = static_cast<int>(below(w.v[0], 3u));
+  const real gs = M<real>::gauss(w.v[1], w.v[2]);
+  const bool isz = icmp == 0;
+  const real mux = reinterpret_cast<const real*>(p.prior_xy)[2 * ee], muy = reinterpret_cast<const real*>(p.prior_xy)[2 * ee + 1];
+  const real x_old = isz ? z : (icmp == 1 ? y : x);
+  const real mu = isz ? p.prior_z : (icmp == 1 ? muy : mux);
+  const real sigma = isz ? p.width_z : p.width_xy;
+  const real step = isz ? p.step_z : p.step_xy;
+  const real x_new = x_old + gs * step;
+  const real dn = x_new - mu, dl = x_old - mu;
+  real lpr = -(dn * dn - dl * dl) / (static_cast<real>(2) * sigma * sigma);
+  bool ok = true;
+  if (isz) {
+    if (x_new <= mu)
+      ok = false;
+    else
+      lpr = lpr + M<real>::log(dn) - M<real>::log(dl);
+  }
+  const real nx = icmp == 2 ? x_new : x, ny = icmp == 1 ? x_new : y, nz = isz ? x_new : z;
+  const real Lnew = event_loglik_corr<real>(s_sta, obs_row, evc, S, nx, ny, nz, g, tc, ac, 0, -1, 0);
+  const real ratio = M<real>::div(Lnew - Le, T, iT) + lpr;
+  const real ru = M<real>::u_co(w.v[3]);
+  const bool acc = ok && (ru > static_cast<real>(0)) && (M<real>::log(ru) <= ratio);
+  if (acc) {
+    x = nx;
+    y = ny;
+    z = nz;
+    Le = Lnew;
+  }
+  if (TRACE) {
+    if (ev_ok && p.trace) {
+      htm_step_trace t;
+      t.proposal_type = 5 + icmp;
+      t.index = 3 * (e + 1) - icmp;
+      t.prior_ok = ok ? 1 : 0;
+      t.accepted = acc ? 1 : 0;
+      t.log_likelihood = static_cast<double>(Le);
+      p.trace[static_cast<size_t>(e) * J + c] = t;
+    }
+  }
+  // ---- 2. the chain's pending shared-parameter proposal, evaluated for this event ----
+  real Lp = Le;
+  if (which != 0) {
+    const Glob<real> gp = make_glob<real>(which == 1 ? pval : vs, which == 3 ? pval : qs);
+    Lp = event_loglik_corr<real>(s_sta, obs_row, evc, S, x, y, z, gp, tc, ac, which, (which == 2 || which == 4) ? pidx : -1,
+                                 pval);
+  }
+  if (ev_ok) {
+    p.hx[ci] = x;
+    p.hy[ci] = y;
+    p.hz[ci] = z;
+    p.hLe[ci] = Le;
+    p.hLp[ci] = Lp;
+    if (p.rec_slot >= 0 && p.slot_of[c] >= 0 && p.hypo_rec) {
+      real4 rec;
+      rec.x = x;
+      rec.y = y;
+      rec.z = z;
+      rec.w = Le;
+      p.hypo_rec[(static_cast<size_t>(p.rec_slot) * p.n_cool_total + p.slot_of[c]) * E + e] = rec;
+    }
+  }
+  // ---- partial sums over the tile (float64, butterfly = fixed order) and counters ----
+  const double s_cur = warp_sum<double>(ev_ok ? static_cast<double>(Le) : 0.0);
+  const double s_prop = warp_sum<double>(ev_ok ? static_cast<double>(Lp) : 0.0);
+  if (lane == 0) {
+    p.part_cur[static_cast<size_t>(c) * p.n_tiles + tile] = s_cur;
+    p.part_prop[static_cast<size_t>(c) * p.n_tiles + tile] = s_prop;
+  }
+  if (cold) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const uint32_t np = __popc(__ballot_sync(0xffffffffu, ev_ok && icmp == t));
+      const uint32_t na = __popc(__ballot_sync(0xffffffffu, ev_ok && icmp == t && acc));
+      if (lane == 0 && p.counts) {
+        if (np) atomicAdd(p.counts + 4 + t, static_cast<unsigned long long>(np));
+        if (na) atomicAdd(p.counts + 11 + t, static_cast<unsigned long long>(na));
+      }
+    }
+  }
+}
+
+// ---- chain-level bookkeeping -----------------------------------------------------------------------
+struct GibbsDecide {
+  double *g_vs, *g_qs, *g_tc, *g_ac, *g_T, *g_L;
+  int* prop_which;
+  int* prop_idx;
+  double* prop_xnew;
+  double* prop_lpr;
+  int* a_prev;
+  int* slot_of;
+  const double *part_cur, *part_prop;
+  int S, J, K, n_tiles, n_cool_total;
+  int it;       // iteration being decided; 0 = prepare only (no decision, no swap)
+  int it_next;  // iteration to propose for
+  PhiloxKeys rk;
+  int n_solved;
+  int solved[4];
+  double prior[4], width[4], step[4];  // indexed by type-1: vs, t_corr, qs, a_corr
+  unsigned long long* counts;
+  // shared-parameter records of the cold chains: [cap][n_cool_total]
+  int rec_slot;
+  int* rec_chain;
+  double *rec_vs, *rec_qs, *rec_L, *rec_tc, *rec_ac;
+  htm_step_trace* trace;  // [J] (row E of this iteration's block) or null
+  htm_swap_trace* swap;
+};
+
+__device__ __forceinline__ double gauss64(uint32_t wa, uint32_t wb) { return M<double>::gauss(wa, wb); }
+
+__global__ void __launch_bounds__(256) gibbs_decide_kernel(const GibbsDecide d) {
+  extern __shared__ double s_tot[];  // [2][J]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int J = d.J, S = d.S;
+  if (d.it > 0) {
+    // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly
+    for (int c = warp; c < J; c += nw) {
+      double a = 0.0, b = 0.0;
+      for (int t = lane; t < d.n_tiles; t += 32) {
+        a += d.part_cur[static_cast<size_t>(c) * d.n_tiles + t];
+        b += d.part_prop[static_cast<size_t>(c) * d.n_tiles + t];
+      }
+      a = warp_sum<double>(a);
+      b = warp_sum<double>(b);
+      if (lane == 0) {
+        s_tot[c] = a;
+        s_tot[J + c] = b;
+      }
+    }
+    __syncthreads();
+    // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----
+    for (int c = threadIdx.x; c < J; c += blockDim.x) {
+      const int which = d.prop_which[c];
+      const double T = d.g_T[c];
+      const bool cold = T < 1.0 + kEps64;
+      const double Lcur = s_tot[c], Lprop = s_tot[J + c];
+      bool acc = false;
+      if (which != 0) {
+        const u32x4 wb = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), static_cast<uint32_t>(c), PHX_GLOBAL, 1u);
+        const double ratio = (Lprop - Lcur) / T + d.prop_lpr[c];
+        const double r = M<double>::u_co(wb.v[0]);
+        if (r >= kEps64 && ::log(r) <= ratio) acc = true;
+        if (cold && d.counts) {
+          atomicAdd(d.counts + (which - 1), 1ull);
+          if (acc) atomicAdd(d.counts + 7 + (which - 1), 1ull);
+        }
+        if (acc) {
+          const double xn = d.prop_xnew[c];
+          const int idx = d.prop_idx[c];
+          if (which == 1) d.g_vs[c] = xn;
+          if (which == 2) d.g_tc[static_cast<size_t>(c) * S + idx] = xn;
+          if (which == 3) d.g_qs[c] = xn;
+          if (which == 4) d.g_ac[static_cast<size_t>(c) * S + idx] = xn;
+        }
+      }
+      d.a_prev[c] = acc ? 1 : 0;
+      d.g_L[c] = acc ? Lprop : Lcur;
+      if (d.trace) {
+        htm_step_trace t;
+        t.proposal_type = which;
+        t.index = which ? d.prop_idx[c] + 1 : 0;
+        t.prior_ok = 1;
+        t.accepted = acc ? 1 : 0;
+        t.log_likelihood = d.g_L[c];
+        d.trace[c] = t;
+      }
+    }
+    __syncthreads();
+    // ---- record the cold chains' shared parameters (src/hypo_tremor_mcmc.f90:270-280) ----
+    if (d.rec_slot >= 0 && d.rec_chain) {
+      for (int c = warp; c < J; c += nw) {
+        const int s = d.slot_of[c];
+        if (s < 0) continue;
+        const size_t o = static_cast<size_t>(d.rec_slot) * d.n_cool_total + s;
+        if (lane == 0) {
+          d.rec_chain[o] = c;
+          d.rec_vs[o] = d.g_vs[c];
+          d.rec_qs[o] = d.g_qs[c];
+          d.rec_L[o] = d.g_L[c];
+        }
+        for (int j = lane; j < S; j += 32) {
+          d.rec_tc[o * S + j] = d.g_tc[static_cast<size_t>(c) * S + j];
+          d.rec_ac[o * S + j] = d.g_ac[static_cast<size_t>(c) * S + j];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- one swap attempt over all J chains (src/cls_parallel.f90:220-240, 285-302) ----
+    if (threadIdx.x == 0 && J >= 2) {
+      const u32x4 w = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), 0u, PHX_SWAP, 1u);
+      const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(J)));
+      int i2 = i1 + 1 + static_cast<int>(below(w.v[1], static_cast<uint32_t>(J - 1)));
+      if (i2 >= J) i2 -= J;
+      const double T1 = d.g_T[i1], T2 = d.g_T[i2], L1 = d.g_L[i1], L2 = d.g_L[i2];
+      const double del_s = (L2 - L1) * (1.0 / T1 - 1.0 / T2);
+      const double r = M<double>::u_co(w.v[2]);
+      const bool sacc = r >= kEps64 && ::log(r) <= del_s;
+      if (sacc) {
+        d.g_T[i1] = T2;
+        d.g_T[i2] = T1;
+      }
+      if (d.swap) {
+        htm_swap_trace t;
+        t.rank1 = i1 / d.K;
+        t.chain1 = i1 % d.K + 1;
+        t.rank2 = i2 / d.K;
+        t.chain2 = i2 % d.K + 1;
+        t.accepted = sacc ? 1 : 0;
+        t.reserved = 0;
+        *d.swap = t;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- slots of the cold chains (in chain order) for the next iteration's records ----
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int c = 0; c < J; ++c) d.slot_of[c] = (d.g_T[c] < 1.0 + kEps64) ? s++ : -1;
+  }
+  // ---- next shared-parameter proposal (src/cls_mcmc.f90:134-157 restricted to the solved ones) ----
+  for (int c = threadIdx.x; c < J; c += blockDim.x) {
+    if (d.n_solved == 0) {
+      d.prop_which[c] = 0;
+      continue;
+    }
+    const u32x4 wa = philox4x32_10(d.rk, static_cast<uint32_t>(d.it_next), static_cast<uint32_t>(c), PHX_GLOBAL, 0u);
+    const int which = d.solved[below(wa.v[0], static_cast<uint32_t>(d.n_solved))];
+    const int idx = (which == 2 || which == 4) ? static_cast<int>(below(wa.v[1], static_cast<uint32_t>(S))) : 0;
+    const double gs = gauss64(wa.v[2], wa.v[3]);
+    double x_old;
+    if (which == 1) x_old = d.g_vs[c];
+    else if (which == 2) x_old = d.g_tc[static_cast<size_t>(c) * S + idx];
+    else if (which == 3) x_old = d.g_qs[c];
+    else x_old = d.g_ac[static_cast<size_t>(c) * S + idx];
+    const double mu = d.prior[which - 1], sg = d.width[which - 1];
+    const double x_new = __dadd_rn(x_old, __dmul_rn(gs, d.step[which - 1]));
+    const double dn = x_new - mu, dl = x_old - mu;
+    d.prop_which[c] = which;
+    d.prop_idx[c] = idx;
+    d.prop_xnew[c] = x_new;
+    d.prop_lpr[c] = -(__dmul_rn(dn, dn) - __dmul_rn(dl, dl)) / (2.0 * sg * sg);
+  }
+}
+
+// ---- chain set-up ---------------------------------------------------------------------------------
+struct GibbsInitChain {
+  double *g_vs, *g_qs, *g_tc, *g_ac, *g_T;
+  int S, J, K, n_cool, ladder, solve_tc, solve_ac;
+  double prior_vs, prior_qs, prior_tc, width_tc, prior_ac, width_ac, temp_high;
+  uint64_t seed;
+};
+__global__ void gibbs_init_chain_kernel(const GibbsInitChain a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.J) return;
+  const int k = c % a.K;
+  a.g_vs[c] = a.prior_vs;  // start at the prior mean, src/hypo_tremor_mcmc.f90:175-185
+  a.g_qs[c] = a.prior_qs;
+  for (int j = 0; j < a.S; ++j) {
+    const u32x4 w = philox4x32_10(a.seed, static_cast<uint32_t>(j), static_cast<uint32_t>(c), PHX_INIT, 1u);
+    a.g_tc[static_cast<size_t>(c) * a.S + j] = a.solve_tc ? a.prior_tc + gauss64(w.v[0], w.v[1]) * a.width_tc : a.prior_tc;
+    a.g_ac[static_cast<size_t>(c) * a.S + j] = a.solve_ac ? a.prior_ac + gauss64(w.v[2], w.v[3]) * a.width_ac : a.prior_ac;
+  }
+  double T = 1.0;
+  if (k >= a.n_cool) {
+    if (a.ladder == HTM_LADDER_GEOMETRIC) {
+      T = ::exp(::log(a.temp_high) * static_cast<double>(k - a.n_cool + 1) / static_cast<double>(a.K - a.n_cool));
+    } else {  // src/hypo_tremor_mcmc.f90:205-206
+      const u32x4 w = philox4x32_10(a.seed, 0u, static_cast<uint32_t>(c), PHX_TEMP, 1u);
+      T = ::exp((M<double>::u_co(w.v[0]) * (1.0 - kEps64) + kEps64) * ::log(a.temp_high));
+    }
+  }
+  a.g_T[c] = T;
+}
+
+// one thread per (chain, event): generate_model for the hypocentre + its log-likelihood
+template <typename real>
+__global__ void gibbs_init_hypo_kernel(const GibbsParams<real> p, uint64_t seed) {
+  typedef typename M<real>::real4 real4;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(p.J) * p.E) return;
+  const int c = static_cast<int>(i / p.E), e = static_cast<int>(i % p.E);
+  const uint32_t gid = (static_cast<uint32_t>(e) + p.event_offset) * static_cast<uint32_t>(p.J) + static_cast<uint32_t>(c);
+  const u32x4 a = philox4x32_10(seed, 0u, gid, PHX_INIT, 0u);
+  const u32x4 b = philox4x32_10(seed, 1u, gid, PHX_INIT, 0u);
+  const real mux = reinterpret_cast<const real*>(p.prior_xy)[2 * e], muy = reinterpret_cast<const real*>(p.prior_xy)[2 * e + 1];
+  const real x = mux + M<real>::gauss(a.v[0], a.v[1]) * p.width_xy;
+  const real y = muy + M<real>::gauss(a.v[2], a.v[3]) * p.width_xy;
+  const real z = p.prior_z + M<real>::sqrt(static_cast<real>(-2) * M<real>::log(M<real>::u_oo(b.v[0]))) * p.width_z;
+  const Glob<real> g = make_glob<real>(static_cast<real>(p.g_vs[c]), static_cast<real>(p.g_qs[c]));
+  // station terms straight from global memory (one-time cost)
+  real ct = 0, ca = 0, S1t = 0, S1a = 0, S2 = 0;
+  for (int j = 0; j < p.S; ++j) {
+    const real4 st = p.sta4[j];
+    const real4 ob = p.obs4[static_cast<size_t>(e) * p.S + j];
+    real rt, ra;
+    station_resid(x, y, z, g, st, ob, static_cast<real>(p.g_tc[static_cast<size_t>(c) * p.S + j]),
+                  static_cast<real>(p.g_ac[static_cast<size_t>(c) * p.S + j]), rt, ra);
+    if (j == 0) {
+      ct = rt;
+      ca = ra;
+    }
+    const real et = rt - ct, ea = ra - ca;
+    const real qt = ob.y * et, qa = ob.w * ea;
+    S1t += qt;
+    S1a += qa;
+    S2 += qt * et;
+    S2 += qa * ea;
+  }
+  p.hx[i] = x;
+  p.hy[i] = y;
+  p.hz[i] = z;
+  p.hLe[i] = finish_loglik<real>(S1t, S2, S1a, static_cast<real>(0), p.evc4[e]);
+  p.hLp[i] = p.hLe[i];
+}
+
+// g_L[c] = sum_e L_e (fixed order), one warp per chain
+template <typename real>
+__global__ void gibbs_total_kernel(const real* hLe, int E, int J, double* g_L) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= J) return;
+  double a = 0.0;
+  for (int e = lane; e < E; e += 32) a += static_cast<double>(hLe[static_cast<size_t>(c) * E + e]);
+  a = warp_sum<double>(a);
+  if (lane == 0) g_L[c] = a;
+}
+
+// ---- host launchers ---------------------------------------------------------------------------------
+template <typename real>
+static GibbsParams<real> make_gibbs_params(const GibbsLaunch& a) {
+  GibbsParams<real> p;
+  typedef typename M<real>::real4 real4;
+  p.sta4 = static_cast<const real4*>(a.tab.sta4);
+  p.obs4 = static_cast<const real4*>(a.tab.obs4_raw);
+  p.evc4 = static_cast<const real4*>(a.tab.evc4);
+  p.prior_xy = a.tab.prior_xy;
+  p.hx = static_cast<real*>(a.hx);
+  p.hy = static_cast<real*>(a.hy);
+  p.hz = static_cast<real*>(a.hz);
+  p.hLe = static_cast<real*>(a.hLe);
+  p.hLp = static_cast<real*>(a.hLp);
+  p.g_vs = a.g_vs;
+  p.g_qs = a.g_qs;
+  p.g_tc = a.g_tc;
+  p.g_ac = a.g_ac;
+  p.g_T = a.g_T;
+  p.g_L = a.g_L;
+  p.prop_which = a.prop_which;
+  p.prop_idx = a.prop_idx;
+  p.prop_xnew = a.prop_xnew;
+  p.prop_lpr = a.prop_lpr;
+  p.a_prev = a.a_prev;
+  p.slot_of = a.slot_of;
+  p.part_cur = a.part_cur;
+  p.part_prop = a.part_prop;
+  p.E = a.E;
+  p.S = a.S;
+  p.J = a.J;
+  p.K = a.K;
+  p.n_tiles = (a.E + kTile - 1) / kTile;
+  p.n_cool_total = a.n_cool_total;
+  p.it = 0;
+  p.n_burn = a.n_burn;
+  p.n_interval = a.n_interval;
+  p.rk = philox_keys(a.seed);
+  p.event_offset = a.event_offset;
+  p.prior_z = static_cast<real>(a.prior_z);
+  p.width_z = static_cast<real>(a.width_z);
+  p.width_xy = static_cast<real>(a.width_xy);
+  p.step_xy = static_cast<real>(a.step_xy);
+  p.step_z = static_cast<real>(a.step_z);
+  p.counts = a.counts;
+  p.hypo_rec = static_cast<real4*>(a.hypo_rec);
+  p.rec_slot = -1;
+  p.trace = nullptr;
+  p.swap = nullptr;
+  return p;
+}
+
+static GibbsDecide make_decide(const GibbsLaunch& a) {
+  GibbsDecide d;
+  d.g_vs = a.g_vs;
+  d.g_qs = a.g_qs;
+  d.g_tc = a.g_tc;
+  d.g_ac = a.g_ac;
+  d.g_T = a.g_T;
+  d.g_L = a.g_L;
+  d.prop_which = a.prop_which;
+  d.prop_idx = a.prop_idx;
+  d.prop_xnew = a.prop_xnew;
+  d.prop_lpr = a.prop_lpr;
+  d.a_prev = a.a_prev;
+  d.slot_of = a.slot_of;
+  d.part_cur = a.part_cur;
+  d.part_prop = a.part_prop;
+  d.S = a.S;
+  d.J = a.J;
+  d.K = a.K;
+  d.n_tiles = (a.E + kTile - 1) / kTile;
+  d.n_cool_total = a.n_cool_total;
+  d.it = 0;
+  d.it_next = 0;
+  d.rk = philox_keys(a.seed);
+  d.n_solved = 0;
+  for (int t = 0; t < 4; ++t) {
+    d.solved[t] = 0;
+    if (a.solve[t]) d.solved[d.n_solved++] = t + 1;
+    d.prior[t] = a.g_prior[t];
+    d.width[t] = a.g_width[t];
+    d.step[t] = a.g_step[t];
+  }
+  d.counts = a.counts;
+  d.rec_slot = -1;
+  d.rec_chain = a.rec_chain;
+  d.rec_vs = a.rec_vs;
+  d.rec_qs = a.rec_qs;
+  d.rec_L = a.rec_L;
+  d.rec_tc = a.rec_tc;
+  d.rec_ac = a.rec_ac;
+  d.trace = nullptr;
+  d.swap = nullptr;
+  return d;
+}
+
+template <typename real>
+static size_t sweep_smem(int S) {
+  typedef typename M<real>::real4 real4;
+  return static_cast<size_t>(kTile) * (S + 1) * sizeof(real4) + S * sizeof(real4) + 2 * kCW * S * sizeof(real) + 32;
+}
+
+template <typename real>
+static cudaError_t launch_gibbs_t(const GibbsLaunch& a, cudaStream_t stream, int* n_launches) {
+  GibbsParams<real> p = make_gibbs_params<real>(a);
+  GibbsDecide d = make_decide(a);
+  const size_t smem = sweep_smem<real>(a.S);
+  cudaError_t err;
+  const bool tracing = a.trace || a.swaps;
+  if (tracing)
+    err = cudaFuncSetAttribute(gibbs_sweep_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  else
+    err = cudaFuncSetAttribute(gibbs_sweep_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  const dim3 grid(p.n_tiles, (a.J + kCW - 1) / kCW);
+  const size_t dsm = 2 * static_cast<size_t>(a.J) * sizeof(double);
+  int nl = 0;
+  // prepare: cold slots + the proposal of the first iteration (a pure function of state and iteration)
+  d.it = 0;
+  d.it_next = a.iter_first;
+  gibbs_decide_kernel<<<1, 256, dsm, stream>>>(d);
+  ++nl;
+  const size_t per_it = static_cast<size_t>(a.E + 1) * a.J;
+  for (int it = a.iter_first; it <= a.iter_last; ++it) {
+    const bool rec = a.n_interval > 1 && (it % a.n_interval) == 1;
+    const int slot = rec ? (it - 1) / a.n_interval - a.rec_origin : -1;
+    p.it = it;
+    p.rec_slot = (slot >= 0 && slot < a.rec_cap) ? slot : -1;
+    p.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it : nullptr;
+    if (tracing)
+      gibbs_sweep_kernel<real, true><<<grid, kCW * 32, smem, stream>>>(p);
+    else
+      gibbs_sweep_kernel<real, false><<<grid, kCW * 32, smem, stream>>>(p);
+    d.it = it;
+    d.it_next = it + 1;
+    d.rec_slot = p.rec_slot;
+    d.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it + static_cast<size_t>(a.E) * a.J : nullptr;
+    d.swap = a.swaps ? a.swaps + (it - a.iter_first) : nullptr;
+    gibbs_decide_kernel<<<1, 256, dsm, stream>>>(d);
+    nl += 2;
+  }
+  if (n_launches) *n_launches = nl;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gibbs(const GibbsLaunch& a, cudaStream_t stream, int* n_launches) {
+  return a.precision == HTM_PRECISION_F64 ? launch_gibbs_t<double>(a, stream, n_launches)
+                                          : launch_gibbs_t<float>(a, stream, n_launches);
+}
+
+cudaError_t launch_gibbs_init(const GibbsLaunch& a, double temp_high, int ladder, int n_cool, cudaStream_t stream) {
+  GibbsInitChain ic;
+  ic.g_vs = a.g_vs;
+  ic.g_qs = a.g_qs;
+  ic.g_tc = a.g_tc;
+  ic.g_ac = a.g_ac;
+  ic.g_T = a.g_T;
+  ic.S = a.S;
+  ic.J = a.J;
+  ic.K = a.K;
+  ic.n_cool = n_cool;
+  ic.ladder = ladder;
+  ic.solve_tc = a.solve[1];
+  ic.solve_ac = a.solve[3];
+  ic.prior_vs = a.g_prior[0];
+  ic.prior_tc = a.g_prior[1];
+  ic.prior_qs = a.g_prior[2];
+  ic.prior_ac = a.g_prior[3];
+  ic.width_tc = a.g_width[1];
+  ic.width_ac = a.g_width[3];
+  ic.temp_high = temp_high;
+  ic.seed = a.seed;
+  gibbs_init_chain_kernel<<<(a.J + 63) / 64, 64, 0, stream>>>(ic);
+  const size_t n = static_cast<size_t>(a.J) * a.E;
+  const unsigned grid = static_cast<unsigned>((n + 127) / 128);
+  if (a.precision == HTM_PRECISION_F64) {
+    gibbs_init_hypo_kernel<double><<<grid, 128, 0, stream>>>(make_gibbs_params<double>(a), a.seed);
+    gibbs_total_kernel<double><<<(a.J + 3) / 4, 128, 0, stream>>>(static_cast<const double*>(a.hLe), a.E, a.J, a.g_L);
+  } else {
+    gibbs_init_hypo_kernel<float><<<grid, 128, 0, stream>>>(make_gibbs_params<float>(a), a.seed);
+    gibbs_total_kernel<float><<<(a.J + 3) / 4, 128, 0, stream>>>(static_cast<const float*>(a.hLe), a.E, a.J, a.g_L);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace htm

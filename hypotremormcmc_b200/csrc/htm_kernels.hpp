@@ -78,6 +78,34 @@ struct ReplayLaunch {
 };
 cudaError_t launch_replay(const ReplayLaunch& a, cudaStream_t stream);
 
+// mode C (blocked Gibbs): joint chains with solved shared parameters
+struct GibbsLaunch {
+  int precision = 32;
+  Tables tab;
+  void *hx = nullptr, *hy = nullptr, *hz = nullptr, *hLe = nullptr, *hLp = nullptr;  // real [J][E]
+  double *g_vs = nullptr, *g_qs = nullptr, *g_tc = nullptr, *g_ac = nullptr, *g_T = nullptr, *g_L = nullptr;
+  int *prop_which = nullptr, *prop_idx = nullptr, *a_prev = nullptr, *slot_of = nullptr;
+  double *prop_xnew = nullptr, *prop_lpr = nullptr;
+  double *part_cur = nullptr, *part_prop = nullptr;  // [J][ceil(E/32)]
+  int E = 0, S = 0, J = 0, K = 0, n_cool_total = 0;
+  int iter_first = 0, iter_last = 0, n_burn = 0, n_interval = 1;
+  uint64_t seed = 0;
+  uint32_t event_offset = 0;
+  double prior_z = 0, width_z = 0, width_xy = 0, step_xy = 0, step_z = 0;
+  int solve[4] = {0, 0, 0, 0};  // vs, t_corr, qs, a_corr
+  double g_prior[4] = {0, 0, 0, 0}, g_width[4] = {0, 0, 0, 0}, g_step[4] = {0, 0, 0, 0};
+  unsigned long long* counts = nullptr;
+  void* hypo_rec = nullptr;  // real4 [cap][n_cool_total][E]
+  int* rec_chain = nullptr;  // [cap][n_cool_total]
+  double *rec_vs = nullptr, *rec_qs = nullptr, *rec_L = nullptr;  // [cap][n_cool_total]
+  double *rec_tc = nullptr, *rec_ac = nullptr;                    // [cap][n_cool_total][S]
+  int rec_origin = 0, rec_cap = 0;
+  htm_step_trace* trace = nullptr;  // debug: [n_it][E+1][J]
+  htm_swap_trace* swaps = nullptr;  // debug: [n_it]
+};
+cudaError_t launch_gibbs(const GibbsLaunch& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_gibbs_init(const GibbsLaunch& a, double temp_high, int ladder, int n_cool, cudaStream_t stream);
+
 // FFMA / MUFU microbenchmark (roofline denominators)
 cudaError_t measure_fp32_peak(int device, double* tflops, double* mufu_gops);
 

@@ -111,6 +111,8 @@ void hto_init_chains(void* h) {
   Oracle* o = static_cast<Oracle*>(h);
   if (o->cfg.mode == HTM_MODE_FACTORISED)
     o->init_chains_factorised();
+  else if (o->cfg.mode == HTM_MODE_BLOCKED_GIBBS)
+    o->init_chains_gibbs();
   else
     o->init_chains_reference();
 }
@@ -133,6 +135,21 @@ void hto_get_chain_state(void* h, int32_t r, int32_t j, double* hypo, double* tc
     *qs = o->fixed_qs;
     *temp = o->bT[o->bidx(0, r, j)];
     *L = lsum;
+    return;
+  }
+  if (o->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
+    const Oracle::GibbsChain& g = o->gc[static_cast<size_t>(r) * o->n_chains + j];
+    for (int32_t e = 0; e < o->E; ++e) {
+      hypo[3 * e] = g.x[e];
+      hypo[3 * e + 1] = g.y[e];
+      hypo[3 * e + 2] = g.z[e];
+    }
+    if (tc) std::memcpy(tc, g.tc.data(), o->S * sizeof(double));
+    if (ac) std::memcpy(ac, g.ac.data(), o->S * sizeof(double));
+    *vs = g.vs;
+    *qs = g.qs;
+    *temp = g.temp;
+    *L = g.L;
     return;
   }
   const hto::Chain& c = o->chain(r, j);
@@ -161,6 +178,8 @@ void hto_run(void* h, int32_t iter_first, int32_t iter_last, htm_step_trace* tra
   Oracle* o = static_cast<Oracle*>(h);
   if (o->cfg.mode == HTM_MODE_FACTORISED)
     o->run_factorised(iter_first, iter_last, trace, swaps);
+  else if (o->cfg.mode == HTM_MODE_BLOCKED_GIBBS)
+    o->run_gibbs(iter_first, iter_last, trace, swaps);
   else
     o->run_reference(iter_first, iter_last, trace, swaps);
 }

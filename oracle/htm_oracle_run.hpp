@@ -279,7 +279,7 @@ struct Oracle {
   // parallel_output_proposal's reduction, src/cls_parallel.f90:259-268
   void counts(int64_t np[7], int64_t na[7]) const {
     for (int k = 0; k < 7; ++k) np[k] = na[k] = 0;
-    if (cfg.mode == HTM_MODE_FACTORISED) {
+    if (cfg.mode == HTM_MODE_FACTORISED || cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
       for (int k = 0; k < 7; ++k) {
         np[k] = b_propose[k];
         na[k] = b_accept[k];
@@ -469,6 +469,249 @@ struct Oracle {
       for (int32_t e = 0; e < E; ++e)
         for (int32_t r = 0; r < n_ranks; ++r)
           swap_factorised(e, r, it, swaps ? swaps + o * g_per_it + static_cast<size_t>(e) * n_ranks + r : nullptr);
+    }
+  }
+
+  // =========================================================================================
+  // Mode C (blocked Gibbs) on Philox draws: the schedule of the B200 joint-chain kernels.
+  // J = n_ranks*n_chains joint chains (c = r*n_chains + k), each with its own vs, qs, t_corr,
+  // a_corr, temperature and all E hypocentres.  One iteration of a chain:
+  //   1. every event proposes one hypocentre coordinate (mode B's step, judged with the CHAIN's
+  //      temperature on the event's own log-likelihood -- valid because the joint density
+  //      factorises over events given the shared parameters);
+  //   2. one shared parameter (uniformly among the solved ones; a random station for t_corr /
+  //      a_corr) is proposed and judged on the sum over all events (cls_mcmc.f90:193-203);
+  //   3. record (T = 1, mod(it, n_interval) == 1), 4. one swap attempt over all J chains
+  //      (cls_parallel.f90:220-240, 285-302).
+  // =========================================================================================
+  struct GibbsChain {
+    double vs, qs, temp, L;
+    std::vector<double> tc, ac, x, y, z, Le;
+  };
+  std::vector<GibbsChain> gc;
+  int32_t J() const { return n_ranks * n_chains; }
+  inline uint32_t gidC(int32_t e, int32_t c) const {
+    return static_cast<uint32_t>(e + event_offset) * static_cast<uint32_t>(J()) + static_cast<uint32_t>(c);
+  }
+  void solved_types(int32_t out[4], int32_t& n) const {
+    n = 0;
+    if (cfg.solve_vs) out[n++] = 1;      // order of cls_mcmc.f90:139-157
+    if (cfg.solve_t_corr) out[n++] = 2;
+    if (cfg.solve_qs) out[n++] = 3;
+    if (cfg.solve_a_corr) out[n++] = 4;
+  }
+  void init_chains_gibbs() {
+    gc.assign(J(), GibbsChain());
+    for (int32_t c = 0; c < J(); ++c) {
+      GibbsChain& g = gc[c];
+      const int32_t k = c % n_chains;
+      g.vs = cfg.prior_vs;  // start at the prior mean, hypo_tremor_mcmc.f90:175-185
+      g.qs = cfg.prior_qs;
+      g.tc.assign(S, cfg.prior_t_corr);
+      g.ac.assign(S, cfg.prior_a_corr);
+      for (int32_t j = 0; j < S; ++j) {
+        uint32_t w[4];
+        Philox::gen(cfg.seed, static_cast<uint32_t>(j), static_cast<uint32_t>(c), PHX_INIT, 1u, w);
+        if (cfg.solve_t_corr) g.tc[j] = cfg.prior_t_corr + gauss(w[0], w[1]) * cfg.prior_width_t_corr;
+        if (cfg.solve_a_corr) g.ac[j] = cfg.prior_a_corr + gauss(w[2], w[3]) * cfg.prior_width_a_corr;
+      }
+      if (k < cfg.n_cool) {
+        g.temp = 1.0;
+      } else if (cfg.ladder == HTM_LADDER_GEOMETRIC) {
+        g.temp = std::exp(std::log(cfg.temp_high) * static_cast<double>(k - cfg.n_cool + 1) /
+                          static_cast<double>(n_chains - cfg.n_cool));
+      } else {
+        uint32_t w[4];
+        Philox::gen(cfg.seed, 0u, static_cast<uint32_t>(c), PHX_TEMP, 1u, w);
+        g.temp = std::exp((Philox::u_co(w[0]) * (1.0 - kEps) + kEps) * std::log(cfg.temp_high));
+      }
+      g.x.resize(E);
+      g.y.resize(E);
+      g.z.resize(E);
+      g.Le.resize(E);
+      g.L = 0.0;
+      for (int32_t e = 0; e < E; ++e) {
+        uint32_t a[4], b[4];
+        Philox::gen(cfg.seed, 0u, gidC(e, c), PHX_INIT, 0u, a);
+        Philox::gen(cfg.seed, 1u, gidC(e, c), PHX_INIT, 0u, b);
+        g.x[e] = x_mu[e] + gauss(a[0], a[1]) * cfg.prior_width_xy;
+        g.y[e] = y_mu[e] + gauss(a[2], a[3]) * cfg.prior_width_xy;
+        g.z[e] = cfg.prior_z + std::sqrt(-2.0 * std::log(Philox::u_oo(b[0]))) * cfg.prior_width_z;
+        const double xyz[3] = {g.x[e], g.y[e], g.z[e]};
+        g.Le[e] = fwd.event_log_likelihood(e, xyz, g.tc.data(), g.vs, g.ac.data(), g.qs);
+      }
+      g.L = sum_events(g.Le);
+    }
+  }
+  // fixed-order pairwise sum (the device reduces 32-event tiles with a butterfly and adds the
+  // tile sums in order; any fixed order is fine at 1e-9, this one is simply left to right)
+  static double sum_events(const std::vector<double>& v) {
+    double s = 0.0;
+    for (double t : v) s += t;
+    return s;
+  }
+  void hypo_step_gibbs(int32_t c, int32_t e, int32_t it, htm_step_trace* tr) {
+    GibbsChain& g = gc[c];
+    uint32_t w[4];
+    Philox::gen(cfg.seed, static_cast<uint32_t>(it), gidC(e, c), PHX_STEP, 0u, w);
+    const int32_t icmp = static_cast<int32_t>(Philox::below(w[0], 3));
+    const int32_t comp = 2 - icmp;
+    const double gs = gauss(w[1], w[2]);
+    double xyz[3] = {g.x[e], g.y[e], g.z[e]};
+    const double x_old = xyz[comp];
+    const double mu = comp == 0 ? x_mu[e] : (comp == 1 ? y_mu[e] : cfg.prior_z);
+    const double sigma = comp == 2 ? cfg.prior_width_z : cfg.prior_width_xy;
+    const double step = comp == 2 ? cfg.step_size_z : cfg.step_size_xy;
+    const double x_new = x_old + gs * step;
+    double lpr = -((x_new - mu) * (x_new - mu) - (x_old - mu) * (x_old - mu)) / (2.0 * sigma * sigma);
+    bool prior_ok = true;
+    if (comp == 2) {
+      if (x_new <= mu)
+        prior_ok = false;
+      else
+        lpr = lpr + std::log(x_new - mu) - std::log(x_old - mu);
+    }
+    const int32_t type = 5 + icmp;
+    const bool cold = g.temp < 1.0 + kEps;
+    if (cold) b_propose[type - 1] += 1;
+    bool acc = false;
+    double ll_new = g.Le[e];
+    if (prior_ok) {
+      xyz[comp] = x_new;
+      ll_new = fwd.event_log_likelihood(e, xyz, g.tc.data(), g.vs, g.ac.data(), g.qs);
+      const double ratio = (ll_new - g.Le[e]) / g.temp + lpr;
+      const double rr = Philox::u_co(w[3]);
+      if (rr >= kEps && std::log(rr) <= ratio) acc = true;
+    }
+    if (acc) {
+      g.x[e] = xyz[0];
+      g.y[e] = xyz[1];
+      g.z[e] = xyz[2];
+      g.Le[e] = ll_new;
+      if (cold) b_accept[type - 1] += 1;
+    }
+    if (tr) {
+      tr->proposal_type = type;
+      tr->index = 3 * (e + 1) - icmp;
+      tr->prior_ok = prior_ok ? 1 : 0;
+      tr->accepted = acc ? 1 : 0;
+      tr->log_likelihood = g.Le[e];
+    }
+  }
+  void global_step_gibbs(int32_t c, int32_t it, htm_step_trace* tr) {
+    GibbsChain& g = gc[c];
+    g.L = sum_events(g.Le);
+    int32_t types[4], n_g;
+    solved_types(types, n_g);
+    if (n_g == 0) {
+      if (tr) {
+        tr->proposal_type = 0;
+        tr->index = 0;
+        tr->prior_ok = 1;
+        tr->accepted = 0;
+        tr->log_likelihood = g.L;
+      }
+      return;
+    }
+    uint32_t wa[4], wb[4];
+    Philox::gen(cfg.seed, static_cast<uint32_t>(it), static_cast<uint32_t>(c), PHX_GLOBAL, 0u, wa);
+    Philox::gen(cfg.seed, static_cast<uint32_t>(it), static_cast<uint32_t>(c), PHX_GLOBAL, 1u, wb);
+    const int32_t type = types[Philox::below(wa[0], static_cast<uint32_t>(n_g))];
+    const int32_t idx = (type == 2 || type == 4) ? static_cast<int32_t>(Philox::below(wa[1], static_cast<uint32_t>(S))) : 0;
+    const double gs = gauss(wa[2], wa[3]);
+    double* slot;
+    double mu, sigma, step;
+    if (type == 1) {
+      slot = &g.vs; mu = cfg.prior_vs; sigma = cfg.prior_width_vs; step = cfg.step_size_vs;
+    } else if (type == 2) {
+      slot = &g.tc[idx]; mu = cfg.prior_t_corr; sigma = cfg.prior_width_t_corr; step = cfg.step_size_t_corr;
+    } else if (type == 3) {
+      slot = &g.qs; mu = cfg.prior_qs; sigma = cfg.prior_width_qs; step = cfg.step_size_qs;
+    } else {
+      slot = &g.ac[idx]; mu = cfg.prior_a_corr; sigma = cfg.prior_width_a_corr; step = cfg.step_size_a_corr;
+    }
+    const double x_old = *slot;
+    const double x_new = x_old + gs * step;
+    const double lpr = -((x_new - mu) * (x_new - mu) - (x_old - mu) * (x_old - mu)) / (2.0 * sigma * sigma);
+    const bool cold = g.temp < 1.0 + kEps;
+    if (cold) b_propose[type - 1] += 1;
+    *slot = x_new;
+    std::vector<double> Lp(E);
+    for (int32_t e = 0; e < E; ++e) {
+      const double xyz[3] = {g.x[e], g.y[e], g.z[e]};
+      Lp[e] = fwd.event_log_likelihood(e, xyz, g.tc.data(), g.vs, g.ac.data(), g.qs);
+    }
+    const double L_new = sum_events(Lp);
+    const double ratio = (L_new - g.L) / g.temp + lpr;
+    const double rr = Philox::u_co(wb[0]);
+    bool acc = false;
+    if (rr >= kEps && std::log(rr) <= ratio) acc = true;
+    if (acc) {
+      g.Le = Lp;
+      g.L = L_new;
+      if (cold) b_accept[type - 1] += 1;
+    } else {
+      *slot = x_old;
+    }
+    if (tr) {
+      tr->proposal_type = type;
+      tr->index = idx + 1;
+      tr->prior_ok = 1;
+      tr->accepted = acc ? 1 : 0;
+      tr->log_likelihood = g.L;
+    }
+  }
+  void record_gibbs(int32_t it) {
+    if ((it % cfg.n_interval) != 1) return;
+    for (int32_t c = 0; c < J(); ++c) {
+      const GibbsChain& g = gc[c];
+      if (!(g.temp < 1.0 + kEps)) continue;
+      RankOutput& o = out[c / n_chains];
+      if (it > cfg.n_burn) {
+        o.iter.push_back(it);
+        o.vs.push_back(g.vs);
+        o.qs.push_back(g.qs);
+        for (int32_t e = 0; e < E; ++e) {
+          o.hypo.push_back(g.x[e]);
+          o.hypo.push_back(g.y[e]);
+          o.hypo.push_back(g.z[e]);
+        }
+        o.t_corr.insert(o.t_corr.end(), g.tc.begin(), g.tc.end());
+        o.a_corr.insert(o.a_corr.end(), g.ac.begin(), g.ac.end());
+      }
+      o.lik_iter.push_back(it);
+      o.lik.push_back(g.L);
+    }
+  }
+  void swap_gibbs(int32_t it, htm_swap_trace* tr) {
+    const int32_t n = J();
+    if (n < 2) return;
+    uint32_t w[4];
+    Philox::gen(cfg.seed, static_cast<uint32_t>(it), 0u, PHX_SWAP, 1u, w);
+    const int32_t i1 = static_cast<int32_t>(Philox::below(w[0], static_cast<uint32_t>(n)));
+    const int32_t i2 = (i1 + 1 + static_cast<int32_t>(Philox::below(w[1], static_cast<uint32_t>(n - 1)))) % n;
+    const bool acc = judge_swap_with(gc[i1].temp, gc[i2].temp, gc[i1].L, gc[i2].L, Philox::u_co(w[2]));
+    if (acc) std::swap(gc[i1].temp, gc[i2].temp);
+    if (tr) {
+      tr->rank1 = i1 / n_chains;
+      tr->chain1 = i1 % n_chains + 1;
+      tr->rank2 = i2 / n_chains;
+      tr->chain2 = i2 % n_chains + 1;
+      tr->accepted = acc ? 1 : 0;
+      tr->reserved = 0;
+    }
+  }
+  // trace: [iteration][E + 1][J] (row E = the shared-parameter step); swaps: [iteration]
+  void run_gibbs(int32_t iter_first, int32_t iter_last, htm_step_trace* trace, htm_swap_trace* swaps) {
+    const size_t per_it = static_cast<size_t>(E + 1) * J();
+    for (int32_t it = iter_first; it <= iter_last; ++it) {
+      htm_step_trace* t = trace ? trace + static_cast<size_t>(it - iter_first) * per_it : nullptr;
+      for (int32_t c = 0; c < J(); ++c) {
+        for (int32_t e = 0; e < E; ++e) hypo_step_gibbs(c, e, it, t ? t + static_cast<size_t>(e) * J() + c : nullptr);
+        global_step_gibbs(c, it, t ? t + static_cast<size_t>(E) * J() + c : nullptr);
+      }
+      record_gibbs(it);
+      swap_gibbs(it, swaps ? swaps + (it - iter_first) : nullptr);
     }
   }
 };

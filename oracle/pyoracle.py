@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 from hypotremormcmc_b200.config import (HtmConfig, copy_config, STEP_TRACE_DTYPE, SWAP_TRACE_DTYPE,
-                                        MODE_FACTORISED)
+                                        MODE_FACTORISED, MODE_BLOCKED_GIBBS)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -152,6 +152,10 @@ class Oracle:
         if self.cfg.mode == MODE_FACTORISED:
             tr = np.zeros((n_it, self.E, self.R, self.K), dtype=STEP_TRACE_DTYPE)
             sw = np.zeros((n_it, self.E, self.R), dtype=SWAP_TRACE_DTYPE)
+        elif self.cfg.mode == MODE_BLOCKED_GIBBS:
+            # row E of axis 1 is the shared-parameter step of each chain
+            tr = np.zeros((n_it, self.E + 1, self.R, self.K), dtype=STEP_TRACE_DTYPE)
+            sw = np.zeros(n_it, dtype=SWAP_TRACE_DTYPE)
         else:
             tr = np.zeros((n_it, self.R, self.K), dtype=STEP_TRACE_DTYPE)
             sw = np.zeros(n_it, dtype=SWAP_TRACE_DTYPE)

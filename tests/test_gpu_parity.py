@@ -412,3 +412,101 @@ def test_nccl_gather_of_histograms_and_counts():
         assert np.array_equal(counts.cpu().numpy(), np.concatenate([p, a]))
     finally:
         dist.destroy_process_group()
+
+
+# ---- mode C blocked Gibbs (shared parameters solved) ---------------------------------------------------------
+@pytest.mark.parametrize("E,S,R,K,solve", [(5, 9, 2, 3, (1, 1, 1, 1)), (40, 20, 3, 4, (1, 0, 1, 0)), (3, 33, 1, 2, (0, 1, 0, 1)),
+                                            (70, 12, 5, 2, (1, 1, 1, 1)), (4, 8, 2, 3, (0, 0, 0, 0))])
+def test_blocked_gibbs_float64_step_exact(E, S, R, K, solve):
+    syn = H.Synthetic(E, S, 40 + E)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=60, n_burn=12, n_interval=6,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=64, max_samples=16, solve_vs=solve[0],
+                           solve_t_corr=solve[1], solve_qs=solve[2], solve_a_corr=solve[3])
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    st_o = o.get_chain_state(R - 1, K - 1)
+    tr_o, sw_o = o.run(1, 60)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        st_g = g.get_chain_state(R - 1, K - 1)
+        tr_g, sw_g = g.run_traced(1, 60)
+        cg = g.get_counts()
+        smp = [g.fetch_samples(r) for r in range(R)]
+        lik = [g.fetch_likelihood(r) for r in range(R)]
+        fin = g.get_chain_state(0, 0)
+    assert np.allclose(st_g["hypo"], st_o["hypo"], rtol=1e-12, atol=1e-12) and st_g["temp"] == pytest.approx(st_o["temp"], rel=1e-13)
+    assert np.allclose(st_g["t_corr"], st_o["t_corr"], atol=1e-14) and rel(st_g["log_likelihood"], st_o["log_likelihood"]) < 1e-12
+    for f in FLAGS:
+        assert np.array_equal(tr_o[f], tr_g[f]), f
+    assert np.array_equal(sw_o, sw_g)
+    assert rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
+    co = o.get_counts()
+    assert np.array_equal(co[0], cg[0]) and np.array_equal(co[1], cg[1])
+    for r in range(R):
+        so = o.fetch_samples(r)
+        assert np.array_equal(so["iter"], smp[r]["iter"])
+        for k in ("hypo", "vs", "qs", "t_corr", "a_corr"):
+            assert np.allclose(so[k], smp[r][k], rtol=1e-10, atol=1e-10), k
+        lo = o.fetch_likelihood(r)
+        assert np.array_equal(lo[0], lik[r][0]) and np.allclose(lo[1], lik[r][1], rtol=1e-10)
+    fo = o.get_chain_state(0, 0)
+    assert np.allclose(fin["hypo"], fo["hypo"], rtol=1e-10, atol=1e-10) and abs(fin["vs"] - fo["vs"]) < 1e-12
+    assert rel(fin["log_likelihood"], fo["log_likelihood"]) < 1e-9
+
+
+def test_blocked_gibbs_chunked_runs_equal_one_run():
+    syn = H.Synthetic(100, 20, 3)
+    cfg = H.default_config(n_sta=20, n_events=100, n_procs=2, n_chains=4, n_iter=80, n_burn=0, n_interval=10,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=32)
+    with H.HypoTremorB200(cfg) as a, H.HypoTremorB200(cfg) as b:
+        for g in (a, b):
+            g.load(syn)
+            g.init_chains()
+        a.run(1, 80)
+        b.run(1, 33)
+        b.run(34, 80)
+        for r in range(2):
+            for k in range(4):
+                x, y = a.get_chain_state(r, k), b.get_chain_state(r, k)
+                assert np.array_equal(x["hypo"], y["hypo"]) and x["vs"] == y["vs"] and x["temp"] == y["temp"]
+                assert np.array_equal(x["t_corr"], y["t_corr"]) and x["log_likelihood"] == y["log_likelihood"]
+        assert np.array_equal(a.get_counts()[0], b.get_counts()[0])
+
+
+def test_blocked_gibbs_float32_posterior_matches_reference_schedule_oracle():
+    # correctness part (2) with the shared parameters solved (sample-file setting solve_* = T): marginals
+    # of x, y, depth, vs, qs, t_corr, a_corr from the B200 float32 blocked-Gibbs kernels vs the oracle's
+    # reference schedule (mode A).  Pass: KS p > 1e-3 on thinned samples, medians within 0.2 sigma.
+    syn = H.Synthetic(3, 8, 31)
+    base = dict(n_sta=8, n_events=3, n_procs=2, n_chains=4, n_cool=1)
+    cfgA = H.default_config(mode=H.MODE_REPLAY, precision=64, n_iter=6000000, n_interval=97, n_burn=300000, **base)
+    o = Oracle(cfgA, syn)
+    o.init_chains()
+    o.run(1, cfgA.n_iter, trace=False)
+    sa = [o.fetch_samples(r) for r in range(2)]
+    A = {k: np.concatenate([x[k] for x in sa]) for k in ("vs", "qs", "hypo", "t_corr", "a_corr")}
+    n_it, interval, burn = 300000, 7, 20000
+    cfgC = H.default_config(mode=H.MODE_BLOCKED_GIBBS, precision=32, n_iter=n_it, n_interval=interval, n_burn=burn,
+                            max_samples=4096, **base)
+    parts = []
+    with H.HypoTremorB200(cfgC) as g:
+        g.load(syn)
+        g.init_chains()
+        it0 = 1
+        while it0 <= n_it:                     # drained in chunks, like the Fortran driver does
+            it1 = min(n_it, it0 + 4000 * interval - 1)
+            g.run(it0, it1)
+            for r in range(2):
+                parts.append(g.fetch_samples(r))
+                g.fetch_likelihood(r)
+            it0 = it1 + 1
+    C = {k: np.concatenate([x[k] for x in parts]) for k in ("vs", "qs", "hypo", "t_corr", "a_corr")}
+    assert len(C["vs"]) == 2 * ((n_it - burn) // interval)
+    pick = [("vs", lambda d: d["vs"]), ("qs", lambda d: d["qs"]), ("z0", lambda d: d["hypo"][:, 2]),
+            ("x1", lambda d: d["hypo"][:, 3]), ("y2", lambda d: d["hypo"][:, 7]), ("tc0", lambda d: d["t_corr"][:, 0]),
+            ("ac3", lambda d: d["a_corr"][:, 3])]
+    for name, f in pick:
+        a, c = f(A), f(C)
+        assert stats.ks_2samp(a[::150], c[::150]).pvalue > 1e-3, name
+        assert abs(np.median(a) - np.median(c)) < 0.2 * np.std(a), name
