@@ -132,9 +132,30 @@ def perf():
                 out["perf_E%d_S%d_k%d_s%d" % (E, S, kernel, slots)] = str(ex)
 
 
+def perf_gibbs():
+    for (E, S, R, K, n_it) in ((1000, 20, 4, 5, 300), (10000, 50, 4, 5, 100), (100000, 50, 4, 5, 20)):
+        syn = H.Synthetic(E, S, 5)
+        cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=n_it, n_burn=0,
+                               n_interval=50, mode=H.MODE_BLOCKED_GIBBS, precision=32)
+        with H.HypoTremorB200(cfg) as g:
+            g.load(syn)
+            g.init_chains()
+            g.run(1, 20)
+            g.synchronize()
+            best = 1e30
+            for rep in range(2):
+                g.run(21 + rep * n_it, 20 + (rep + 1) * n_it)
+                ms, nl, npr = g.last_run_stats()
+                best = min(best, ms)
+            p, a = g.get_counts()
+        out["perf_gibbs_E%d_S%d_J%d" % (E, S, R * K)] = dict(ms=best, us_per_iter=best * 1e3 / n_it,
+                                                             proposals_per_s=npr / (best * 1e-3),
+                                                             accept=[float(x) for x in (a / np.maximum(1, p))])
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    for fn in (lambda: out.update(fp32_peak=measure_fp32_peak(0)), check_loglik, check_replay, check_factorised, perf):
+    for fn in (lambda: out.update(fp32_peak=measure_fp32_peak(0)), check_loglik, check_replay, check_factorised, perf, perf_gibbs):
         try:
             fn()
         except Exception as ex:  # keep going: this is a survey
