@@ -12,6 +12,7 @@ from .config import (HtmConfig, StepTrace, SwapTrace, default_config, copy_confi
                      KERNEL_WARP_PER_CHAIN, KERNEL_LANE_PER_CHAIN, PROPOSAL_LABELS,
                      STEP_TRACE_DTYPE, SWAP_TRACE_DTYPE)
 from .synth import Synthetic, shard_bounds  # noqa: F401
+from . import io  # noqa: F401
 from .api import HtmError, HypoTremorB200, load_library, library_path  # noqa: F401
 
 __version__ = "0.1.0"

@@ -165,7 +165,7 @@ contains
     integer(c_int32_t), allocatable :: it(:)
     double precision, allocatable :: vs(:), qs(:), hy(:,:), tc(:,:), ac(:,:), lk(:)
     integer :: cap, j
-    cap = (chunk_records + 1) * cfg%n_cool
+    cap = (chunk_records + 1) * cfg%n_cool * n_ranks   ! a rank can momentarily hold every cold chain
     allocate(it(cap), vs(cap), qs(cap), hy(3*n_events, cap), tc(n_sta, cap), ac(n_sta, cap), lk(cap))
     call htm_check(h, htm_fetch_samples(h, rank, cap, n, it, vs, qs, hy, tc, ac), "htm_fetch_samples")
     do j = 1, n

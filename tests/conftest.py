@@ -19,6 +19,7 @@ def _built():
     import subprocess
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libhtm_oracle.so"])
     subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "hypotremormcmc_b200", "csrc")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "drivers")])
 
 
 def have_gpu():

@@ -1,0 +1,119 @@
+"""The C++ twin of the drop-in driver: file formats in (parameter file, station file,
+selected_win.dat, opt_data.*.dat) and out (six .out families, proposal_count.txt)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import hypotremormcmc_b200 as H
+from hypotremormcmc_b200 import io as hio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "drivers", "hypo_tremor_mcmc_b200")
+NOSOLVE = dict(solve_vs=0, solve_t_corr=0, solve_qs=0, solve_a_corr=0)
+
+
+def run_driver(cwd, *args):
+    return subprocess.run([DRIVER, "hypo_tremor.in", *args], cwd=cwd, capture_output=True, text=True)
+
+
+def test_dry_run_parses_the_reference_formats(tmp_path):
+    syn = H.Synthetic(3, 5, 4)
+    cfg = H.default_config(n_sta=5, n_events=3, n_procs=2, n_chains=3, n_iter=100, n_burn=10, n_interval=5)
+    hio.write_dataset(str(tmp_path), syn, cfg)
+    # rewrite the parameter file the way a user would: comments, blanks everywhere, D exponents, .true.
+    lines = open(tmp_path / "hypo_tremor.in").read().splitlines()
+    messy = ["#  comment line", "   "]
+    for ln in lines:
+        if ln.startswith("temp_high"):
+            ln = "temp_high   =  2 0 0 . d 0   # blanks inside a value are removed too"
+        if ln.startswith("solve_vs"):
+            ln = "solve_vs=.true."
+        if ln.startswith("prior_qs"):
+            ln = "prior_qs = 250"
+        messy.append("  " + ln.replace("=", "  =  ") + "   # trailing comment")
+    messy.append("prior_t_corr = 1.5D-1")
+    messy.append("alpha = 0.5      # keys of the other programs are accepted")
+    open(tmp_path / "hypo_tremor.in", "w").write("\n".join(messy) + "\n")
+    r = run_driver(tmp_path, "--dry-run")
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout)
+    assert d["n_sta"] == 5 and d["n_events"] == 3 and d["n_procs"] == 2 and d["n_chains"] == 3
+    assert d["temp_high"] == 200.0 and d["prior_qs"] == 250.0 and d["prior_t_corr"] == 0.15
+    assert d["solve_vs"] == 1 and d["use_amp"] == 1 and d["mode"] == H.MODE_BLOCKED_GIBBS
+    assert d["x_mu0"] == pytest.approx(syn.x_mu[0], abs=1e-8) and d["y_mu0"] == pytest.approx(syn.y_mu[0], abs=1e-8)
+    assert d["t_obs00"] == syn.t_obs[0, 0] and d["a_stdv_last"] == syn.a_stdv[-1, -1]
+    assert d["sta_z_last"] == pytest.approx(syn.sta_z[-1], abs=1e-8)
+
+
+def test_missing_and_unknown_keys_are_fatal(tmp_path):
+    syn = H.Synthetic(2, 4, 1)
+    cfg = H.default_config(n_sta=4, n_events=2)
+    hio.write_dataset(str(tmp_path), syn, cfg)
+    text = open(tmp_path / "hypo_tremor.in").read()
+    open(tmp_path / "hypo_tremor.in", "w").write(text.replace("n_cool = 1\n", ""))
+    r = run_driver(tmp_path, "--dry-run")
+    assert r.returncode != 0 and "n_cool is not given" in r.stderr
+    open(tmp_path / "hypo_tremor.in", "w").write(text + "n_colo = 1\n")
+    r = run_driver(tmp_path, "--dry-run")
+    assert r.returncode != 0 and "Invalid parameter name" in r.stderr
+    r = subprocess.run([DRIVER], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "USAGE: hypo_tremor_mcmc [parameter file]" in r.stderr
+
+
+def test_stream_reader_and_quantiles(tmp_path):
+    rec = np.dtype([("i", ">i4"), ("v", ">f8", (3,))])
+    a = np.zeros(5, dtype=rec)
+    a["i"] = [1, 11, 21, 31, 41]
+    a["v"] = np.arange(15).reshape(5, 3)
+    a.tofile(tmp_path / "x.out")
+    it, v = hio.read_stream(str(tmp_path / "x.out"), 3)
+    assert list(it) == [1, 11, 21, 31, 41] and np.array_equal(v, np.arange(15.0).reshape(5, 3))
+    with pytest.raises(ValueError):
+        hio.read_stream(str(tmp_path / "x.out"), 4)
+    s = np.arange(1, 1001, dtype=float)[::-1]
+    med, lo, hi = hio.quantile_summary(s)
+    assert (med, lo, hi) == (500.0, 25.0, 975.0)      # elements int(0.5 n), int(0.025 n), int(0.975 n), 1-based
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solve", [0, 1])
+def test_driver_end_to_end(tmp_path, solve):
+    E, S, R, K = 6, 10, 2, 4
+    syn = H.Synthetic(E, S, 20231002)
+    kw = NOSOLVE if not solve else {}
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=2000, n_burn=500, n_interval=10,
+                           **kw)
+    hio.write_dataset(str(tmp_path), syn, cfg)
+    r = run_driver(tmp_path, "--chunk", "37")
+    assert r.returncode == 0, r.stderr
+    out = hio.read_outputs(str(tmp_path), R, E, S)
+    n_mod = (cfg.n_iter - cfg.n_burn) * R * cfg.n_cool // cfg.n_interval     # src/cls_statistics.f90:65
+    for k in ("hypo", "t_corr", "vs", "a_corr", "qs"):
+        assert out[k].shape[0] == n_mod, k
+        assert np.all(out["iter"][k] % 10 == 1) and out["iter"][k].min() > 500
+    assert out["lik"].shape[0] == cfg.n_iter * R * cfg.n_cool // cfg.n_interval and out["iter"]["lik"].min() == 1
+    assert np.all(np.isfinite(out["hypo"])) and np.all(out["hypo"][:, 2::3] > cfg.prior_z)
+    if not solve:
+        assert np.all(out["vs"] == cfg.prior_vs) and np.all(out["t_corr"] == 0.0)
+    else:
+        assert out["vs"].std() > 0 and out["t_corr"].std() > 0
+    rows = hio.read_proposal_count(str(tmp_path / "proposal_count.txt"))
+    assert [r_[0] for r_ in rows] == H.PROPOSAL_LABELS
+    assert all(a <= p for _, p, a in rows) and sum(p for _, p, _ in rows[4:]) == cfg.n_iter * E * R
+    # the same run through the Python mirror of the ABI gives byte-identical samples
+    c2 = H.copy_config(cfg, mode=H.MODE_BLOCKED_GIBBS if solve else H.MODE_FACTORISED, precision=32, max_samples=256)
+    with H.HypoTremorB200(c2) as g:
+        g.load(syn)
+        g.init_chains()
+        g.run(1, cfg.n_iter)
+        s = [g.fetch_samples(rank) for rank in range(R)]
+    assert np.array_equal(np.concatenate([x["hypo"] for x in s]), out["hypo"])
+    assert np.array_equal(np.concatenate([x["vs"] for x in s]), out["vs"][:, 0])
+    # little-endian switch
+    r = run_driver(tmp_path, "--chunk", "64", "--little-endian")
+    assert r.returncode == 0
+    out_le = hio.read_outputs(str(tmp_path), R, E, S, big_endian=False)
+    assert np.array_equal(out_le["hypo"], out["hypo"])
