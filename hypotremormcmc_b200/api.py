@@ -34,7 +34,8 @@ class HtmError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "csrc", "libhtm_b200.so")
+    # HTM_B200_LIB: load another build of the same library (kernel-tuning experiments)
+    return os.environ.get("HTM_B200_LIB") or os.path.join(_HERE, "csrc", "libhtm_b200.so")
 
 
 def load_library():

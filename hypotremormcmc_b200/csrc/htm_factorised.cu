@@ -142,9 +142,15 @@ __device__ __forceinline__ void hist_add(const FactParams<real>& p, int e, real 
 // Per-chain registers: x, y, z, L, T, 1/T, ln(z - prior_z).  Every warp is independent (own
 // shared-memory slice, own mbarrier, no block barrier), so the CTA size (1, 2 or 4 warps) is
 // chosen by the launcher only to balance warps over the 148 SMs.
-template <typename real, int NSLOT, bool TRACE, bool PACKED>
-__global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p) {
-  static_assert(!PACKED || (sizeof(real) == 4 && NSLOT % 2 == 0), "packed math: float32, even slot count");
+#ifndef HTM_LANE_MINB
+#define HTM_LANE_MINB 1
+#endif
+#ifndef HTM_NP_UNROLL
+#define HTM_NP_UNROLL 8
+#endif
+constexpr int kScalarUnroll = HTM_NP_UNROLL;
+template <typename real, int NSLOT, bool TRACE>
+__global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const FactParams<real> p) {
   typedef typename M<real>::real4 real4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -158,7 +164,10 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
   const int e = static_cast<int>(gw / wpe), we = static_cast<int>(gw % wpe);
 
   // --- stage this event's tables with 1-D bulk TMA into the warp's slice of shared memory ---
-  constexpr int kF4PerSta = PACKED ? 6 : 2;  // packed: 2 staged + 4 expanded float4 per station
+  // float32: 2 staged + 2 expanded float4 per station (pairs of stations, 4 float4 per pair);
+  // float64 reads the staged tables directly
+  constexpr bool kF32 = sizeof(real) == 4;
+  constexpr int kF4PerSta = kF32 ? 4 : 2;
   real4* s_sta = reinterpret_cast<real4*>(smem_raw) + static_cast<size_t>(warp) * kF4PerSta * S;
   real4* s_obs = s_sta + S;
   uint64_t* bar =
@@ -217,16 +226,21 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
   if (p.n_interval == 1) rec_left = -1;  // mod(it, 1) == 1 never holds (reference quirk Q6)
 
   mbar_wait(bar, 0);
-  if constexpr (PACKED) {
-    // expand the staged tables into the duplicated, sign-folded layout of forward_packed()
-    float4* s_pk = reinterpret_cast<float4*>(s_obs + S);
-    for (int j = lane; j < S; j += 32) {
-      const float4 st = reinterpret_cast<const float4*>(s_sta)[j];
-      const float4 ob = reinterpret_cast<const float4*>(s_obs)[j];
-      s_pk[4 * j] = make_float4(-st.x, -st.x, -st.y, -st.y);
-      s_pk[4 * j + 1] = make_float4(-st.z, -st.z, -ob.x, -ob.x);
-      s_pk[4 * j + 2] = make_float4(ob.y, ob.y, -ob.z, -ob.z);
-      s_pk[4 * j + 3] = make_float4(ob.w, ob.w, 0.f, 0.f);
+  if constexpr (kF32) {
+    // expand the staged tables into the packed station-pair records of htm_forward.cuh (once per launch)
+    float4* s_x = reinterpret_cast<float4*>(s_obs + S);
+    const float4* st = reinterpret_cast<const float4*>(s_sta);
+    const float4* ob = reinterpret_cast<const float4*>(s_obs);
+    for (int m = lane; m < n_station_pairs(S); m += 32) {
+      const int j0 = 1 + 2 * m, j1 = j0 + 1;
+      const StaRecF a = expand_station(st[j0], ob[j0], pxy.x, pxy.y);
+      StaRecF b = a;
+      if (j1 < S) {
+        b = expand_station(st[j1], ob[j1], pxy.x, pxy.y);
+      } else {  // odd tail: zero-weight copy
+        b.B = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      store_station_pair(s_x + 4 * m, a, b);
     }
     __syncwarp();
   }
@@ -265,8 +279,18 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
     }
     // ---- forward: one pass over the stations serves all NSLOT chains of this thread ----
     real S1t[NSLOT], S1a[NSLOT], S2[NSLOT];
-    if constexpr (PACKED) {
-      forward_packed<NSLOT>(reinterpret_cast<const float4*>(s_obs + S), S, nx, ny, nz, g, S1t, S1a, S2);
+    if constexpr (kF32) {
+      const float4* s_x = reinterpret_cast<const float4*>(s_obs + S);
+      const float4 st0 = reinterpret_cast<const float4*>(s_sta)[0], ob0 = reinterpret_cast<const float4*>(s_obs)[0];
+      const StaRecF r0 = expand_station(st0, ob0, pxy.x, pxy.y);
+      float hx[NSLOT], hy[NSLOT], hz[NSLOT];
+#pragma unroll
+      for (int q = 0; q < NSLOT; ++q) {
+        hx[q] = nx[q] - pxy.x;
+        hy[q] = ny[q] - pxy.y;
+        hz[q] = nz[q];
+      }
+      forward_pairs<NSLOT>(s_x, n_station_pairs(S), r0.A, ob0.x, ob0.z, hx, hy, hz, g, S1t, S1a, S2);
     } else {
       real nct[NSLOT], nca[NSLOT];
       const real4 st = s_sta[0];
@@ -281,7 +305,7 @@ __global__ void __launch_bounds__(128) fact_lane_kernel(const FactParams<real> p
         S1a[q] = 0;
         S2[q] = 0;
       }
-#pragma unroll 4
+#pragma unroll kScalarUnroll
       for (int j = 1; j < S; ++j) {
         const real4 stj = s_sta[j];
         const real4 obj = s_obs[j];
@@ -686,8 +710,8 @@ static FactParams<real> make_params(const FactLaunch& a) {
   return p;
 }
 
-template <typename real, int NSLOT, bool PACKED>
-static cudaError_t launch_lane_p(const FactLaunch& a, cudaStream_t stream) {
+template <typename real, int NSLOT>
+static cudaError_t launch_lane(const FactLaunch& a, cudaStream_t stream) {
   typedef typename M<real>::real4 real4;
   const FactParams<real> p = make_params<real>(a);
   const int gpw = a.R < 32 / a.K ? a.R : 32 / a.K;
@@ -698,30 +722,21 @@ static cudaError_t launch_lane_p(const FactLaunch& a, cudaStream_t stream) {
   // 1-warp CTAs while everything is resident at once (<= 32 CTAs/SM), else 2 or 4
   const int wpb = n_warps <= 148L * 32 ? 1 : (n_warps <= 148L * 64 ? 2 : 4);
   const unsigned grid = static_cast<unsigned>((n_warps + wpb - 1) / wpb);
-  const size_t smem = static_cast<size_t>(wpb) * ((PACKED ? 6 : 2) * a.S * sizeof(real4) + sizeof(uint64_t));
+  const size_t smem = static_cast<size_t>(wpb) * ((sizeof(real) == 4 ? 4 : 2) * a.S * sizeof(real4) + sizeof(uint64_t));
   const bool trace = a.trace || a.swaps;
   cudaError_t err;
   if (trace) {
-    err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, true, PACKED>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    fact_lane_kernel<real, NSLOT, true, PACKED><<<grid, wpb * 32, smem, stream>>>(p);
+    fact_lane_kernel<real, NSLOT, true><<<grid, wpb * 32, smem, stream>>>(p);
   } else {
-    err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, false, PACKED>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    err = cudaFuncSetAttribute(fact_lane_kernel<real, NSLOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    fact_lane_kernel<real, NSLOT, false, PACKED><<<grid, wpb * 32, smem, stream>>>(p);
+    fact_lane_kernel<real, NSLOT, false><<<grid, wpb * 32, smem, stream>>>(p);
   }
   return cudaGetLastError();
-}
-// float32 with an even slot count runs the packed (FFMA2) forward unless HTM_NO_PACK is set
-template <typename real, int NSLOT>
-static cudaError_t launch_lane(const FactLaunch& a, cudaStream_t stream) {
-  if constexpr (sizeof(real) == 4 && NSLOT % 2 == 0) {
-    static const bool no_pack = std::getenv("HTM_NO_PACK") != nullptr;
-    if (!no_pack) return launch_lane_p<real, NSLOT, true>(a, stream);
-  }
-  return launch_lane_p<real, NSLOT, false>(a, stream);
 }
 
 template <typename real, int SPL>
@@ -769,20 +784,14 @@ static cudaError_t launch_factorised_t(const FactLaunch& a, cudaStream_t stream,
     *why = "warp-per-chain kernel supports n_sta <= 128; use the lane-per-chain kernel";
     return cudaErrorInvalidValue;
   }
-  const size_t smem_need = static_cast<size_t>(4) * (6 * a.S * sizeof(typename M<real>::real4) + 8);
+  const size_t smem_need = static_cast<size_t>(4) * (4 * a.S * sizeof(typename M<real>::real4) + 8);
   if (smem_need > 200 * 1024) {
     *why = "n_sta too large for the shared-memory staging of the lane-per-chain kernel";
     return cudaErrorInvalidValue;
   }
-  int slots = a.slots;
-  if (slots == 0) {
-    // one slot keeps the most warps in flight; more slots amortise the table reads.  Use
-    // more slots only when there are enough chains to keep every SM busy anyway.
-    const int gpw = a.R < 32 / a.K ? a.R : 32 / a.K;
-    const long warps1 = static_cast<long>(a.E) * ((a.R + gpw - 1) / gpw);
-    slots = 1;
-    if (a.R >= 2 * gpw && warps1 >= 2L * 148 * 16) slots = 2;
-  }
+  // one chain per lane keeps the most warps in flight and measured fastest at every size; 2 or 4
+  // chains per lane (fewer, fatter warps) stay available on request
+  const int slots = a.slots == 0 ? 1 : a.slots;
   switch (slots) {
     case 1: return launch_lane<real, 1>(a, stream);
     case 2: return launch_lane<real, 2>(a, stream);

@@ -96,72 +96,113 @@ __device__ __forceinline__ void station_accum(double px, double py, double pz, c
   S2 += qa * ea;
 }
 
-// ---- packed float32 (FFMA2 / FADD2 / FMUL2): two chains of one thread per instruction -------
-// Shared-memory record per station, 16 floats, every value duplicated so that one 64-bit
-// register pair feeds both chains:  {-X,-X,-Y,-Y} {-Z,-Z,-t,-t} {w_t,w_t,-a,-a} {w_a,w_a,0,0}
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ void packed_geometry(const float2 px, const float2 py, const float2 pz, const float4 r0,
-                                                const float4 r1, float2& d, float2& l2) {
-  const float2 dx = __fadd2_rn(px, f2(r0.x, r0.y));
-  const float2 dy = __fadd2_rn(py, f2(r0.z, r0.w));
-  const float2 dz = __fadd2_rn(pz, f2(r1.x, r1.y));
-  const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-  d = __fmul2_rn(d2, f2(mufu_rsq(d2.x), mufu_rsq(d2.y)));
-  l2 = f2(mufu_lg2(d2.x), mufu_lg2(d2.y));
+// ---- float32 throughput formulation (lane-per-chain kernels) --------------------------------------
+// The staged tables are expanded once per launch, in shared memory, into a record that needs only
+// 14 FMA-pipe operations + 2 MUFU per chain-station:
+//   A = {cx, cy, cz, c0}     cx = -2(X - x0), cy = -2(Y - y0), cz = -2 Z, c0 = (X-x0)^2 + (Y-y0)^2 + Z^2
+//   B = {sw_t, -sw_t*t_obs, sw_a, -sw_a*a_obs}        sw = sqrt(w) = 1/sigma
+// with (x0, y0) the event's prior centre.  For a hypocentre h (centred the same way, hh = |h|^2):
+//   d^2 = c0 + hh + h.c                       (expansion around the centre: 1 add + 3 FMA instead of 6 ops;
+//                                              centring keeps the cancellation harmless)
+//   u_t = sw_t (d/vs - c_t - t_obs)           = fma(sw_t, fma(d, 1/vs, -c_t), -sw_t t_obs)
+//   u_a = sw_a (-B d - ln d - c_a - a_obs)
+//   S2 += u_t^2 + u_a^2 ;  S1t += sw_t u_t ;  S1a += sw_a u_a       (so S1 = sum w e, S2 = sum w e^2)
+struct StaRecF {
+  float4 A, B;
+};
+__device__ __forceinline__ StaRecF expand_station(const float4 st, const float4 ob, float x0, float y0) {
+  StaRecF r;
+  const float X = st.x - x0, Y = st.y - y0, Z = st.z;
+  r.A = make_float4(-2.f * X, -2.f * Y, -2.f * Z, fmaf(X, X, fmaf(Y, Y, Z * Z)));
+  const float swt = sqrtf(ob.y), swa = sqrtf(ob.w);
+  r.B = make_float4(swt, -swt * ob.x, swa, -swa * ob.z);
+  return r;
 }
+__device__ __forceinline__ void station_accum_x(float hx, float hy, float hz, float hh, const Glob<float>& g,
+                                                float nct, float nca, const float4 A, const float4 B, float& S1t,
+                                                float& S1a, float& S2) {
+  const float d2 = fmaf(hx, A.x, fmaf(hy, A.y, fmaf(hz, A.z, A.w + hh)));
+  const float d = d2 * mufu_rsq(d2);
+  const float l2 = mufu_lg2(d2);
+  const float ut = fmaf(B.x, fmaf(d, g.ivs, nct), B.y);
+  const float ua = fmaf(B.z, fmaf(-0.34657359027997264f, l2, fmaf(-g.B, d, nca)), B.w);
+  S2 = fmaf(ut, ut, S2);
+  S1t = fmaf(B.x, ut, S1t);
+  S2 = fmaf(ua, ua, S2);
+  S1a = fmaf(B.z, ua, S1a);
+}
+
+// Packed form (FFMA2 / FADD2 / FMUL2, sm_100a): TWO STATIONS of one chain per instruction, so the
+// 14 operations per station become 7 issue slots while every lane still owns one chain.  Stations
+// 1..S-1 are stored as pairs (station 0 is the shift station and is handled apart); an odd tail is
+// padded with a zero-weight copy.  Shared-memory record per pair, 4 x float4:
+//   {cx0,cx1,cy0,cy1} {cz0,cz1,c0_0,c0_1} {sw_t0,sw_t1,-sw_t t_0,-sw_t t_1} {sw_a0,sw_a1,-sw_a a_0,-sw_a a_1}
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ int n_station_pairs(int S) { return S / 2; }  // ceil((S-1)/2)
+__device__ __forceinline__ void store_station_pair(float4* dst, const StaRecF a, const StaRecF b) {
+  dst[0] = make_float4(a.A.x, b.A.x, a.A.y, b.A.y);
+  dst[1] = make_float4(a.A.z, b.A.z, a.A.w, b.A.w);
+  dst[2] = make_float4(a.B.x, b.B.x, a.B.y, b.B.y);
+  dst[3] = make_float4(a.B.z, b.B.z, a.B.w, b.B.w);
+}
+#ifndef HTM_PK_UNROLL
+#define HTM_PK_UNROLL 2
+#endif
+constexpr int kPackedUnroll = HTM_PK_UNROLL;
+// hx/hy/hz: hypocentres centred on the event's prior centre; A0: expanded geometry of station 0;
+// t0/a0: raw {t_obs, a_obs} of station 0.  Returns S1t, S1a, S2 per slot.
 template <int NSLOT>
-__device__ __forceinline__ void forward_packed(const float4* __restrict__ s_pk, const int S, const float (&nx)[NSLOT],
-                                               const float (&ny)[NSLOT], const float (&nz)[NSLOT],
-                                               const Glob<float>& g, float (&S1t)[NSLOT], float (&S1a)[NSLOT],
-                                               float (&S2)[NSLOT]) {
-  constexpr int NP = NSLOT / 2;
+__device__ __forceinline__ void forward_pairs(const float4* __restrict__ s_pk, const int n_pairs, const float4 A0,
+                                              const float t0, const float a0, const float (&hx)[NSLOT],
+                                              const float (&hy)[NSLOT], const float (&hz)[NSLOT],
+                                              const Glob<float>& g, float (&S1t)[NSLOT], float (&S1a)[NSLOT],
+                                              float (&S2)[NSLOT]) {
   const float2 ivs2 = f2(g.ivs, g.ivs), nB2 = f2(-g.B, -g.B);
   const float2 nc2 = f2(-0.34657359027997264f, -0.34657359027997264f);
-  float2 px[NP], py[NP], pz[NP], nct[NP], nca[NP], a1t[NP], a1a[NP], a2[NP];
-  {
-    const float4 r0 = s_pk[0], r1 = s_pk[1], r2 = s_pk[2];
+  float2 px[NSLOT], py[NSLOT], pz[NSLOT], hh[NSLOT], nct[NSLOT], nca[NSLOT], a1t[NSLOT], a1a[NSLOT], a2[NSLOT];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      px[p] = f2(nx[2 * p], nx[2 * p + 1]);
-      py[p] = f2(ny[2 * p], ny[2 * p + 1]);
-      pz[p] = f2(nz[2 * p], nz[2 * p + 1]);
-      float2 d, l2;
-      packed_geometry(px[p], py[p], pz[p], r0, r1, d, l2);
-      // shift = raw residual of station 0; keep its negative
-      const float2 rt = __ffma2_rn(d, ivs2, f2(r1.z, r1.w));
-      const float2 ra = __ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, f2(r2.z, r2.w)));
-      nct[p] = f2(-rt.x, -rt.y);
-      nca[p] = f2(-ra.x, -ra.y);
-      a1t[p] = f2(0.f, 0.f);
-      a1a[p] = f2(0.f, 0.f);
-      a2[p] = f2(0.f, 0.f);
+  for (int q = 0; q < NSLOT; ++q) {
+    const float h2 = fmaf(hz[q], hz[q], fmaf(hy[q], hy[q], hx[q] * hx[q]));
+    // shift station: raw residuals of station 0 (negated)
+    const float d2 = fmaf(hx[q], A0.x, fmaf(hy[q], A0.y, fmaf(hz[q], A0.z, A0.w + h2)));
+    const float d = d2 * mufu_rsq(d2);
+    const float l2 = mufu_lg2(d2);
+    const float ct = -fmaf(d, g.ivs, -t0);
+    const float ca = -fmaf(-0.34657359027997264f, l2, fmaf(-g.B, d, -a0));
+    px[q] = f2(hx[q], hx[q]);
+    py[q] = f2(hy[q], hy[q]);
+    pz[q] = f2(hz[q], hz[q]);
+    hh[q] = f2(h2, h2);
+    nct[q] = f2(ct, ct);
+    nca[q] = f2(ca, ca);
+    a1t[q] = f2(0.f, 0.f);
+    a1a[q] = f2(0.f, 0.f);
+    a2[q] = f2(0.f, 0.f);
+  }
+#pragma unroll kPackedUnroll
+  for (int m = 0; m < n_pairs; ++m) {
+    const float4 r0 = s_pk[4 * m], r1 = s_pk[4 * m + 1], r2 = s_pk[4 * m + 2], r3 = s_pk[4 * m + 3];
+    const float2 swt = f2(r2.x, r2.y), swa = f2(r3.x, r3.y);
+#pragma unroll
+    for (int q = 0; q < NSLOT; ++q) {
+      const float2 d2 = __ffma2_rn(px[q], f2(r0.x, r0.y),
+                                   __ffma2_rn(py[q], f2(r0.z, r0.w),
+                                              __ffma2_rn(pz[q], f2(r1.x, r1.y), __fadd2_rn(f2(r1.z, r1.w), hh[q]))));
+      const float2 d = __fmul2_rn(d2, f2(mufu_rsq(d2.x), mufu_rsq(d2.y)));
+      const float2 l2 = f2(mufu_lg2(d2.x), mufu_lg2(d2.y));
+      const float2 ut = __ffma2_rn(swt, __ffma2_rn(d, ivs2, nct[q]), f2(r2.z, r2.w));
+      const float2 ua = __ffma2_rn(swa, __ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, nca[q])), f2(r3.z, r3.w));
+      a2[q] = __ffma2_rn(ut, ut, a2[q]);
+      a1t[q] = __ffma2_rn(swt, ut, a1t[q]);
+      a2[q] = __ffma2_rn(ua, ua, a2[q]);
+      a1a[q] = __ffma2_rn(swa, ua, a1a[q]);
     }
   }
-#pragma unroll 2
-  for (int j = 1; j < S; ++j) {
-    const float4 r0 = s_pk[4 * j], r1 = s_pk[4 * j + 1], r2 = s_pk[4 * j + 2];
-    const float2 wa = *reinterpret_cast<const float2*>(s_pk + 4 * j + 3);
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      float2 d, l2;
-      packed_geometry(px[p], py[p], pz[p], r0, r1, d, l2);
-      const float2 et = __fadd2_rn(__ffma2_rn(d, ivs2, nct[p]), f2(r1.z, r1.w));
-      const float2 ea = __fadd2_rn(__ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, nca[p])), f2(r2.z, r2.w));
-      const float2 qt = __fmul2_rn(f2(r2.x, r2.y), et), qa = __fmul2_rn(wa, ea);
-      a1t[p] = __fadd2_rn(a1t[p], qt);
-      a1a[p] = __fadd2_rn(a1a[p], qa);
-      a2[p] = __ffma2_rn(qt, et, a2[p]);
-      a2[p] = __ffma2_rn(qa, ea, a2[p]);
-    }
-  }
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    S1t[2 * p] = a1t[p].x;
-    S1t[2 * p + 1] = a1t[p].y;
-    S1a[2 * p] = a1a[p].x;
-    S1a[2 * p + 1] = a1a[p].y;
-    S2[2 * p] = a2[p].x;
-    S2[2 * p + 1] = a2[p].y;
+  for (int q = 0; q < NSLOT; ++q) {
+    S1t[q] = a1t[q].x + a1t[q].y;
+    S1a[q] = a1a[q].x + a1a[q].y;
+    S2[q] = a2[q].x + a2[q].y;
   }
 }
 

@@ -243,6 +243,33 @@ def test_factorised_fixed_globals_are_folded_exactly():
     assert rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
 
 
+@pytest.mark.parametrize("kernel,slots", [(2, 1), (2, 2), (2, 4), (1, 0)])
+@pytest.mark.parametrize("S", [20, 50])
+def test_factorised_float32_kernel_likelihood_accuracy(kernel, slots, S):
+    # the float32 throughput kernels' own log-likelihood (carried in registers across steps) against a
+    # float64 evaluation of the SAME float32 states by the oracle: isolates the kernels' arithmetic
+    # (distance by expansion, sqrt-weight folding, MUFU approximations).  Bound per event:
+    # 2e-3 + 5e-5 |L|  (measured: <= 1.5e-3 for |L| < 500, <= 2.5e-5 |L| for far-from-converged hot chains).
+    E, R, K = 24, 4, 8
+    syn = H.Synthetic(E, S, 17)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=40, n_burn=0, n_interval=10,
+                           mode=H.MODE_FACTORISED, precision=32, kernel=kernel, lane_slots=slots, **NOSOLVE)
+    o = Oracle(cfg, syn)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        tr, _ = g.run_traced(1, 40)
+        worst = 0.0
+        for r in range(R):
+            for k in range(K):
+                st = g.get_chain_state(r, k)
+                _, pe = o.loglik(st["hypo"][None, :], np.zeros((1, S)), np.zeros((1, S)), [cfg.prior_vs],
+                                 [cfg.prior_qs], per_event=True)
+                err = np.abs(pe[0] - tr["log_likelihood"][-1, :, r, k])
+                worst = max(worst, np.max(err / (2e-3 + 5e-5 * np.abs(pe[0]))))
+    assert worst <= 1.0, worst
+
+
 # ---- size-independent properties at BASELINE sizes ------------------------------------------------------
 def fact_cfg(E, S, R, K, **kw):
     base = dict(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=400, n_burn=0, n_interval=50,
