@@ -123,9 +123,16 @@ class HypoTremorB200:
             self._h = ctypes.c_void_p()
             raise HtmError(rc, buf.value.decode())
         from .synth import shard_bounds
-        lo, hi = shard_bounds(cfg.n_events, cfg.shard_rank, cfg.shard_count)
-        self.event_offset, self.n_events = lo, hi - lo
         self.n_sta, self.n_procs, self.n_chains = cfg.n_sta, cfg.n_procs, cfg.n_chains
+        self.rank_offset = 0
+        if cfg.mode == MODE_BLOCKED_GIBBS:
+            # joint chains: the shards split the virtual ranks and every shard holds all events
+            lo, hi = shard_bounds(cfg.n_procs, cfg.shard_rank, cfg.shard_count)
+            self.event_offset, self.n_events = 0, cfg.n_events
+            self.rank_offset, self.n_procs = lo, hi - lo
+        else:
+            lo, hi = shard_bounds(cfg.n_events, cfg.shard_rank, cfg.shard_count)
+            self.event_offset, self.n_events = lo, hi - lo
 
     # -- plumbing ------------------------------------------------------------------------
     def _ck(self, rc):
@@ -249,7 +256,7 @@ class HypoTremorB200:
         E, S = self.n_events, self.n_sta
         n = ctypes.c_int32()
         # bounded by the ring capacity (in blocked-Gibbs mode a rank can momentarily hold every cold chain)
-        cap = min(max_records, max(1, self.cfg.max_samples) * self.cfg.n_cool * self.cfg.n_procs)
+        cap = min(max_records, max(1, self.cfg.max_samples) * self.cfg.n_cool * self.n_procs)
         it = np.empty(cap, dtype=np.int32)
         vs, qs = np.empty(cap), np.empty(cap)
         hypo = np.empty((cap, 3 * E))

@@ -18,7 +18,7 @@ thread_local std::string g_create_error;
 struct htm_handle_s {
   htm_config cfg;
   std::string err;
-  int E = 0, E_total = 0, ev_off = 0, S = 0, R = 0, K = 0, C = 0;
+  int E = 0, E_total = 0, ev_off = 0, rank_off = 0, S = 0, R = 0, K = 0, C = 0;
   size_t rs = 4;  // sizeof(real)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -315,6 +315,9 @@ void gibbs_launch_of(htm_handle h) {
   g.n_interval = h->cfg.n_interval;
   g.seed = h->cfg.seed;
   g.event_offset = static_cast<uint32_t>(h->ev_off);
+  g.chain_offset = static_cast<uint32_t>(h->rank_off) * h->K;
+  g.J_total = static_cast<uint32_t>(h->cfg.n_procs) * h->K;
+  g.swap_stream = static_cast<uint32_t>(h->cfg.shard_rank);
   g.prior_z = h->cfg.prior_z;
   g.width_z = h->cfg.prior_width_z;
   g.width_xy = h->cfg.prior_width_xy;
@@ -461,10 +464,8 @@ int32_t htm_create(htm_handle* out, const htm_config* cfg) {
   if (cfg->mode != HTM_MODE_REPLAY && cfg->mode != HTM_MODE_FACTORISED && cfg->mode != HTM_MODE_BLOCKED_GIBBS)
     return fail(nullptr, HTM_ERR_ARG, "unknown mode");
   if (cfg->hist_bins < 0 || cfg->max_samples < 0) return fail(nullptr, HTM_ERR_ARG, "negative hist_bins/max_samples");
-  if (cfg->mode == HTM_MODE_BLOCKED_GIBBS && cfg->shard_count != 1)
-    return fail(nullptr, HTM_ERR_UNSUPPORTED,
-                "blocked-Gibbs mode on sharded events needs an all-reduce of the per-chain sums per "
-                "iteration; not built yet (single GPU only)");
+  if (cfg->mode == HTM_MODE_BLOCKED_GIBBS && cfg->shard_count > cfg->n_procs)
+    return fail(nullptr, HTM_ERR_ARG, "blocked-Gibbs mode shards the virtual ranks: shard_count must be <= n_procs");
 
   int n_dev = 0;
   cudaError_t ce = cudaGetDeviceCount(&n_dev);
@@ -480,11 +481,22 @@ int32_t htm_create(htm_handle* out, const htm_config* cfg) {
   h->cfg = *cfg;
   h->E_total = cfg->n_events;
   int lo, hi;
-  shard_bounds(cfg->n_events, cfg->shard_rank, cfg->shard_count, &lo, &hi);
-  h->ev_off = lo;
-  h->E = hi - lo;
+  if (cfg->mode == HTM_MODE_BLOCKED_GIBBS) {
+    // joint chains couple all events, so this mode shards the VIRTUAL RANKS instead (the reference's own
+    // decomposition, src/hypo_tremor_mcmc.f90:114-118): every shard holds all events and an independent
+    // ensemble of its ranks' chains; swaps stay inside the shard; no collective.
+    shard_bounds(cfg->n_procs, cfg->shard_rank, cfg->shard_count, &lo, &hi);
+    h->rank_off = lo;
+    h->ev_off = 0;
+    h->E = cfg->n_events;
+    h->R = hi - lo;
+  } else {
+    shard_bounds(cfg->n_events, cfg->shard_rank, cfg->shard_count, &lo, &hi);
+    h->ev_off = lo;
+    h->E = hi - lo;
+    h->R = cfg->n_procs;
+  }
   h->S = cfg->n_sta;
-  h->R = cfg->n_procs;
   h->K = cfg->n_chains;
   h->C = h->R * h->K;
   h->rs = cfg->precision == HTM_PRECISION_F64 ? 8 : 4;
@@ -492,9 +504,9 @@ int32_t htm_create(htm_handle* out, const htm_config* cfg) {
   h->g_qs = cfg->prior_qs;
   h->g_tc.assign(h->S, cfg->prior_t_corr);
   h->g_ac.assign(h->S, cfg->prior_a_corr);
-  if (h->E < 1) {
+  if (h->E < 1 || h->R < 1) {
     delete h;
-    return fail(nullptr, HTM_ERR_ARG, "this shard holds no events");
+    return fail(nullptr, HTM_ERR_ARG, "this shard holds no events / no virtual ranks");
   }
   ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev0);

@@ -46,6 +46,7 @@ struct GibbsParams {
   int it, n_burn, n_interval;
   PhiloxKeys rk;
   uint32_t event_offset;
+  uint32_t chain_offset, J_total;  // Philox ids are global: shards of virtual ranks draw distinct streams
   real prior_z, width_z, width_xy, step_xy, step_z;
   unsigned long long* counts;
   real4* hypo_rec;  // [cap][n_cool_total][E]
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kCW * 32) gibbs_sweep_kernel(const GibbsParams
   real Le = p.a_prev[c] ? p.hLp[ci] : p.hLe[ci];  // lazy commit of the last shared-parameter acceptance
 
   // ---- 1. hypocentre step (same rule as the factorised kernels) ----
-  const uint32_t gid = (static_cast<uint32_t>(ee) + p.event_offset) * static_cast<uint32_t>(J) + static_cast<uint32_t>(c);
+  const uint32_t gid = (static_cast<uint32_t>(ee) + p.event_offset) * p.J_total + p.chain_offset + static_cast<uint32_t>(c);
   const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(p.it), gid, PHX_STEP, 0u);
   const int icmp = static_cast<int>(below(w.v[0], 3u));
   const real gs = M<real>::gauss(w.v[1], w.v[2]);
@@ -249,6 +250,7 @@ struct GibbsDecide {
   int it;       // iteration being decided; 0 = prepare only (no decision, no swap)
   int it_next;  // iteration to propose for
   PhiloxKeys rk;
+  uint32_t chain_offset, swap_stream;
   int n_solved;
   int solved[4];
   double prior[4], width[4], step[4];  // indexed by type-1: vs, t_corr, qs, a_corr
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(256) gibbs_decide_kernel(const GibbsDecide d) 
       const double Lcur = s_tot[c], Lprop = s_tot[J + c];
       bool acc = false;
       if (which != 0) {
-        const u32x4 wb = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), static_cast<uint32_t>(c), PHX_GLOBAL, 1u);
+        const u32x4 wb = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 1u);
         const double ratio = (Lprop - Lcur) / T + d.prop_lpr[c];
         const double r = M<double>::u_co(wb.v[0]);
         if (r >= kEps64 && ::log(r) <= ratio) acc = true;
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(256) gibbs_decide_kernel(const GibbsDecide d) 
     __syncthreads();
     // ---- one swap attempt over all J chains (src/cls_parallel.f90:220-240, 285-302) ----
     if (threadIdx.x == 0 && J >= 2) {
-      const u32x4 w = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), 0u, PHX_SWAP, 1u);
+      const u32x4 w = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), d.swap_stream, PHX_SWAP, 1u);
       const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(J)));
       int i2 = i1 + 1 + static_cast<int>(below(w.v[1], static_cast<uint32_t>(J - 1)));
       if (i2 >= J) i2 -= J;
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(256) gibbs_decide_kernel(const GibbsDecide d) 
       d.prop_which[c] = 0;
       continue;
     }
-    const u32x4 wa = philox4x32_10(d.rk, static_cast<uint32_t>(d.it_next), static_cast<uint32_t>(c), PHX_GLOBAL, 0u);
+    const u32x4 wa = philox4x32_10(d.rk, static_cast<uint32_t>(d.it_next), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 0u);
     const int which = d.solved[below(wa.v[0], static_cast<uint32_t>(d.n_solved))];
     const int idx = (which == 2 || which == 4) ? static_cast<int>(below(wa.v[1], static_cast<uint32_t>(S))) : 0;
     const double gs = gauss64(wa.v[2], wa.v[3]);
@@ -403,6 +405,7 @@ struct GibbsInitChain {
   int S, J, K, n_cool, ladder, solve_tc, solve_ac;
   double prior_vs, prior_qs, prior_tc, width_tc, prior_ac, width_ac, temp_high;
   uint64_t seed;
+  uint32_t chain_offset;
 };
 __global__ void gibbs_init_chain_kernel(const GibbsInitChain a) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -411,7 +414,7 @@ __global__ void gibbs_init_chain_kernel(const GibbsInitChain a) {
   a.g_vs[c] = a.prior_vs;  // start at the prior mean, src/hypo_tremor_mcmc.f90:175-185
   a.g_qs[c] = a.prior_qs;
   for (int j = 0; j < a.S; ++j) {
-    const u32x4 w = philox4x32_10(a.seed, static_cast<uint32_t>(j), static_cast<uint32_t>(c), PHX_INIT, 1u);
+    const u32x4 w = philox4x32_10(a.seed, static_cast<uint32_t>(j), a.chain_offset + static_cast<uint32_t>(c), PHX_INIT, 1u);
     a.g_tc[static_cast<size_t>(c) * a.S + j] = a.solve_tc ? a.prior_tc + gauss64(w.v[0], w.v[1]) * a.width_tc : a.prior_tc;
     a.g_ac[static_cast<size_t>(c) * a.S + j] = a.solve_ac ? a.prior_ac + gauss64(w.v[2], w.v[3]) * a.width_ac : a.prior_ac;
   }
@@ -420,7 +423,7 @@ __global__ void gibbs_init_chain_kernel(const GibbsInitChain a) {
     if (a.ladder == HTM_LADDER_GEOMETRIC) {
       T = ::exp(::log(a.temp_high) * static_cast<double>(k - a.n_cool + 1) / static_cast<double>(a.K - a.n_cool));
     } else {  // src/hypo_tremor_mcmc.f90:205-206
-      const u32x4 w = philox4x32_10(a.seed, 0u, static_cast<uint32_t>(c), PHX_TEMP, 1u);
+      const u32x4 w = philox4x32_10(a.seed, 0u, a.chain_offset + static_cast<uint32_t>(c), PHX_TEMP, 1u);
       T = ::exp((M<double>::u_co(w.v[0]) * (1.0 - kEps64) + kEps64) * ::log(a.temp_high));
     }
   }
@@ -434,7 +437,7 @@ __global__ void gibbs_init_hypo_kernel(const GibbsParams<real> p, uint64_t seed)
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(p.J) * p.E) return;
   const int c = static_cast<int>(i / p.E), e = static_cast<int>(i % p.E);
-  const uint32_t gid = (static_cast<uint32_t>(e) + p.event_offset) * static_cast<uint32_t>(p.J) + static_cast<uint32_t>(c);
+  const uint32_t gid = (static_cast<uint32_t>(e) + p.event_offset) * p.J_total + p.chain_offset + static_cast<uint32_t>(c);
   const u32x4 a = philox4x32_10(seed, 0u, gid, PHX_INIT, 0u);
   const u32x4 b = philox4x32_10(seed, 1u, gid, PHX_INIT, 0u);
   const real mux = reinterpret_cast<const real*>(p.prior_xy)[2 * e], muy = reinterpret_cast<const real*>(p.prior_xy)[2 * e + 1];
@@ -518,6 +521,8 @@ static GibbsParams<real> make_gibbs_params(const GibbsLaunch& a) {
   p.n_interval = a.n_interval;
   p.rk = philox_keys(a.seed);
   p.event_offset = a.event_offset;
+  p.chain_offset = a.chain_offset;
+  p.J_total = a.J_total;
   p.prior_z = static_cast<real>(a.prior_z);
   p.width_z = static_cast<real>(a.width_z);
   p.width_xy = static_cast<real>(a.width_xy);
@@ -555,6 +560,8 @@ static GibbsDecide make_decide(const GibbsLaunch& a) {
   d.it = 0;
   d.it_next = 0;
   d.rk = philox_keys(a.seed);
+  d.chain_offset = a.chain_offset;
+  d.swap_stream = a.swap_stream;
   d.n_solved = 0;
   for (int t = 0; t < 4; ++t) {
     d.solved[t] = 0;
@@ -652,6 +659,7 @@ cudaError_t launch_gibbs_init(const GibbsLaunch& a, double temp_high, int ladder
   ic.width_ac = a.g_width[3];
   ic.temp_high = temp_high;
   ic.seed = a.seed;
+  ic.chain_offset = a.chain_offset;
   gibbs_init_chain_kernel<<<(a.J + 63) / 64, 64, 0, stream>>>(ic);
   const size_t n = static_cast<size_t>(a.J) * a.E;
   const unsigned grid = static_cast<unsigned>((n + 127) / 128);

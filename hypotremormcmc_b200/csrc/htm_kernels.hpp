@@ -91,6 +91,7 @@ struct GibbsLaunch {
   int iter_first = 0, iter_last = 0, n_burn = 0, n_interval = 1;
   uint64_t seed = 0;
   uint32_t event_offset = 0;
+  uint32_t chain_offset = 0, J_total = 0, swap_stream = 0;  // shards of virtual ranks (global Philox ids)
   double prior_z = 0, width_z = 0, width_xy = 0, step_xy = 0, step_z = 0;
   int solve[4] = {0, 0, 0, 0};  // vs, t_corr, qs, a_corr
   double g_prior[4] = {0, 0, 0, 0}, g_width[4] = {0, 0, 0, 0}, g_step[4] = {0, 0, 0, 0};

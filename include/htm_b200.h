@@ -109,8 +109,11 @@ typedef struct htm_config {
   int32_t ladder;           /* HTM_LADDER_*                                             */
   int32_t kernel;           /* HTM_KERNEL_*                                             */
   int32_t device;           /* CUDA device ordinal                                      */
-  int32_t shard_rank;       /* this process's index among shard_count event shards      */
-  int32_t shard_count;      /* events are split in contiguous blocks over the shards    */
+  int32_t shard_rank;       /* this process's index among shard_count shards            */
+  int32_t shard_count;      /* modes A/B: EVENTS are split in contiguous blocks over the
+                               shards.  Mode C (joint chains): the VIRTUAL RANKS are split
+                               instead (every shard holds all events and runs an independent
+                               ensemble of its ranks; `rank` arguments are then shard-local) */
   int32_t hist_bins;        /* bins per coordinate histogram; 0 = no histograms         */
   int32_t max_samples;      /* capacity (in recorded iterations) of the sample ring     */
   int32_t lane_slots;       /* lane-per-chain kernel: chains per thread (1, 2, 4); 0 = auto */

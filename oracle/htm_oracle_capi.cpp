@@ -67,6 +67,13 @@ void hto_destroy(void* h) { delete static_cast<Oracle*>(h); }
 
 void hto_set_event_offset(void* h, int32_t off) { static_cast<Oracle*>(h)->event_offset = off; }
 
+void hto_set_rank_shard(void* h, uint32_t chain_offset, uint32_t j_total, uint32_t swap_stream) {
+  Oracle* o = static_cast<Oracle*>(h);
+  o->chain_offset = chain_offset;
+  o->J_total = j_total;
+  o->swap_stream = swap_stream;
+}
+
 void hto_set_globals(void* h, double vs, double qs, const double* tc, const double* ac) {
   Oracle* o = static_cast<Oracle*>(h);
   o->fixed_vs = vs;

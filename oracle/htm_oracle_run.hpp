@@ -489,9 +489,12 @@ struct Oracle {
     std::vector<double> tc, ac, x, y, z, Le;
   };
   std::vector<GibbsChain> gc;
+  // shards of virtual ranks: Philox ids stay global so every shard draws its own streams
+  uint32_t chain_offset = 0, J_total = 0, swap_stream = 0;
   int32_t J() const { return n_ranks * n_chains; }
+  uint32_t Jt() const { return J_total ? J_total : static_cast<uint32_t>(J()); }
   inline uint32_t gidC(int32_t e, int32_t c) const {
-    return static_cast<uint32_t>(e + event_offset) * static_cast<uint32_t>(J()) + static_cast<uint32_t>(c);
+    return static_cast<uint32_t>(e + event_offset) * Jt() + chain_offset + static_cast<uint32_t>(c);
   }
   void solved_types(int32_t out[4], int32_t& n) const {
     n = 0;
@@ -511,7 +514,7 @@ struct Oracle {
       g.ac.assign(S, cfg.prior_a_corr);
       for (int32_t j = 0; j < S; ++j) {
         uint32_t w[4];
-        Philox::gen(cfg.seed, static_cast<uint32_t>(j), static_cast<uint32_t>(c), PHX_INIT, 1u, w);
+        Philox::gen(cfg.seed, static_cast<uint32_t>(j), chain_offset + static_cast<uint32_t>(c), PHX_INIT, 1u, w);
         if (cfg.solve_t_corr) g.tc[j] = cfg.prior_t_corr + gauss(w[0], w[1]) * cfg.prior_width_t_corr;
         if (cfg.solve_a_corr) g.ac[j] = cfg.prior_a_corr + gauss(w[2], w[3]) * cfg.prior_width_a_corr;
       }
@@ -522,7 +525,7 @@ struct Oracle {
                           static_cast<double>(n_chains - cfg.n_cool));
       } else {
         uint32_t w[4];
-        Philox::gen(cfg.seed, 0u, static_cast<uint32_t>(c), PHX_TEMP, 1u, w);
+        Philox::gen(cfg.seed, 0u, chain_offset + static_cast<uint32_t>(c), PHX_TEMP, 1u, w);
         g.temp = std::exp((Philox::u_co(w[0]) * (1.0 - kEps) + kEps) * std::log(cfg.temp_high));
       }
       g.x.resize(E);
@@ -614,8 +617,8 @@ struct Oracle {
       return;
     }
     uint32_t wa[4], wb[4];
-    Philox::gen(cfg.seed, static_cast<uint32_t>(it), static_cast<uint32_t>(c), PHX_GLOBAL, 0u, wa);
-    Philox::gen(cfg.seed, static_cast<uint32_t>(it), static_cast<uint32_t>(c), PHX_GLOBAL, 1u, wb);
+    Philox::gen(cfg.seed, static_cast<uint32_t>(it), chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 0u, wa);
+    Philox::gen(cfg.seed, static_cast<uint32_t>(it), chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 1u, wb);
     const int32_t type = types[Philox::below(wa[0], static_cast<uint32_t>(n_g))];
     const int32_t idx = (type == 2 || type == 4) ? static_cast<int32_t>(Philox::below(wa[1], static_cast<uint32_t>(S))) : 0;
     const double gs = gauss(wa[2], wa[3]);
@@ -687,7 +690,7 @@ struct Oracle {
     const int32_t n = J();
     if (n < 2) return;
     uint32_t w[4];
-    Philox::gen(cfg.seed, static_cast<uint32_t>(it), 0u, PHX_SWAP, 1u, w);
+    Philox::gen(cfg.seed, static_cast<uint32_t>(it), swap_stream, PHX_SWAP, 1u, w);
     const int32_t i1 = static_cast<int32_t>(Philox::below(w[0], static_cast<uint32_t>(n)));
     const int32_t i2 = (i1 + 1 + static_cast<int32_t>(Philox::below(w[1], static_cast<uint32_t>(n - 1)))) % n;
     const bool acc = judge_swap_with(gc[i1].temp, gc[i2].temp, gc[i1].L, gc[i2].L, Philox::u_co(w[2]));

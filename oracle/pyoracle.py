@@ -98,6 +98,11 @@ class Oracle:
         except Exception:
             pass
 
+    def set_rank_shard(self, chain_offset, j_total, swap_stream):
+        """blocked-Gibbs mode: this oracle holds the virtual ranks of one shard (global Philox ids)"""
+        self.L.hto_set_rank_shard(self.h, ctypes.c_uint32(chain_offset), ctypes.c_uint32(j_total),
+                                  ctypes.c_uint32(swap_stream))
+
     def set_globals(self, vs, qs, t_corr, a_corr):
         tc = np.ascontiguousarray(t_corr, dtype=np.float64)
         ac = np.ascontiguousarray(a_corr, dtype=np.float64)

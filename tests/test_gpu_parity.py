@@ -539,3 +539,31 @@ def test_blocked_gibbs_float32_posterior_matches_reference_schedule_oracle():
         a, c = f(A), f(C)
         assert stats.ks_2samp(a[::150], c[::150]).pvalue > 1e-3, name
         assert abs(np.median(a) - np.median(c)) < 0.2 * np.std(a), name
+
+
+def test_blocked_gibbs_rank_shards_are_independent_ensembles():
+    # mode C shards the virtual ranks (the reference's own decomposition): shard 1 of 2 reproduces the oracle's
+    # statement with the same global Philox ids, and the two shards draw different streams
+    E, S, R, K = 6, 9, 4, 3
+    syn = H.Synthetic(E, S, 61)
+    base = dict(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=40, n_burn=0, n_interval=5,
+                mode=H.MODE_BLOCKED_GIBBS, precision=64, shard_count=2)
+    finals = []
+    for shard in (0, 1):
+        cfg = H.default_config(shard_rank=shard, **base)
+        ocfg = H.copy_config(cfg, n_procs=R // 2, shard_count=1, shard_rank=0)
+        o = Oracle(ocfg, syn)
+        o.set_rank_shard(shard * (R // 2) * K, R * K, shard)
+        o.init_chains()
+        tr_o, sw_o = o.run(1, 40)
+        with H.HypoTremorB200(cfg) as g:
+            assert g.n_procs == R // 2 and g.n_events == E
+            g.load(syn)
+            g.init_chains()
+            tr_g, sw_g = g.run_traced(1, 40)
+            finals.append(g.get_chain_state(0, 0)["hypo"])
+        for f in FLAGS:
+            assert np.array_equal(tr_o[f], tr_g[f]), f
+        assert np.array_equal(sw_o, sw_g)
+        assert rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
+    assert not np.allclose(finals[0], finals[1])
