@@ -29,6 +29,7 @@ struct htm_handle_s {
   // device tables
   void *d_sta4 = nullptr, *d_obs4 = nullptr, *d_obs4_raw = nullptr, *d_evc4 = nullptr, *d_prior_xy = nullptr;
   double* d_prior_xy64 = nullptr;
+  void* d_obsx = nullptr;
   // mode B state
   void *d_x = nullptr, *d_y = nullptr, *d_z = nullptr, *d_L = nullptr, *d_T = nullptr;
   unsigned long long* d_counts = nullptr;
@@ -163,11 +164,23 @@ int32_t build_tables_t(htm_handle h) {
   return HTM_OK;
 }
 
+Tables tables_of(htm_handle h);
+
 int32_t ensure_tables(htm_handle h) {
   if (h->tables_ok) return HTM_OK;
   if (!h->have_sta) return fail(h, HTM_ERR_STATE, "stations not set (htm_set_stations)");
   if (!h->have_obs) return fail(h, HTM_ERR_STATE, "observations not set (htm_set_observations)");
-  return h->cfg.precision == HTM_PRECISION_F64 ? build_tables_t<double>(h) : build_tables_t<float>(h);
+  const int32_t rc = h->cfg.precision == HTM_PRECISION_F64 ? build_tables_t<double>(h) : build_tables_t<float>(h);
+  if (rc != HTM_OK) return rc;
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS && h->cfg.precision == HTM_PRECISION_F32) {
+    // expanded station-pair rows for the float32 joint-chain sweep (layout: htm_forward.cuh)
+    const int xrow = 2 + 4 * (h->S / 2);
+    if (!h->d_obsx) HTM_CK(h, cudaMalloc(&h->d_obsx, static_cast<size_t>(h->E) * xrow * 16));
+    HTM_CK(h, launch_expand_obs(tables_of(h), h->E, h->S, h->d_obsx, h->stream));
+    h->gl.obsx = h->d_obsx;
+    h->gl.xrow = xrow;
+  }
+  return HTM_OK;
 }
 
 Tables tables_of(htm_handle h) {
@@ -284,6 +297,7 @@ int32_t alloc_state(htm_handle h) {
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.prop_lpr), J * 8));
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.part_cur), J * nt * 8));
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.part_prop), J * nt * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.done_counter), 8));
     if (h->cfg.max_samples > 0) {
       h->rec_cap = h->cfg.max_samples;
       const size_t n = static_cast<size_t>(h->rec_cap) * h->n_cold_total;
@@ -539,6 +553,7 @@ int32_t htm_destroy(htm_handle h) {
                   static_cast<void*>(h->d_status)})
     free_dev(p);
   for (void* p : h->gibbs_bufs) free_dev(p);
+  free_dev(h->d_obsx);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);

@@ -33,6 +33,8 @@ struct GibbsParams {
   const real4* obs4;  // raw: no station terms folded
   const real4* evc4;
   const void* prior_xy;  // real2 [E]
+  const float4* obsx;    // float32 only: expanded station-pair rows [E][xrow] (htm_forward.cuh)
+  int xrow;
   real *hx, *hy, *hz, *hLe, *hLp;  // [J][E]
   double *g_vs, *g_qs, *g_tc, *g_ac, *g_T, *g_L;  // [J], [J][S]
   int* prop_which;
@@ -94,20 +96,289 @@ __device__ __forceinline__ real event_loglik_corr(const typename M<real>::real4*
   return finish_loglik<real>(S1t, S2, S1a, static_cast<real>(0), evc);
 }
 
+// ---- chain-level bookkeeping -----------------------------------------------------------------------
+struct GibbsDecide {
+  double *g_vs, *g_qs, *g_tc, *g_ac, *g_T, *g_L;
+  int* prop_which;
+  int* prop_idx;
+  double* prop_xnew;
+  double* prop_lpr;
+  int* a_prev;
+  int* slot_of;
+  const double *part_cur, *part_prop;
+  int S, J, K, n_tiles, n_cool_total;
+  int it;       // iteration being decided; 0 = prepare only (no decision, no swap)
+  int it_next;  // iteration to propose for
+  PhiloxKeys rk;
+  uint32_t chain_offset, swap_stream;
+  int n_solved;
+  int solved[4];
+  double prior[4], width[4], step[4];  // indexed by type-1: vs, t_corr, qs, a_corr
+  unsigned long long* counts;
+  // shared-parameter records of the cold chains: [cap][n_cool_total]
+  int rec_slot;
+  int* rec_chain;
+  double *rec_vs, *rec_qs, *rec_L, *rec_tc, *rec_ac;
+  htm_step_trace* trace;  // [J] (row E of this iteration's block) or null
+  htm_swap_trace* swap;
+};
+
+__device__ __forceinline__ double gauss64(uint32_t wa, uint32_t wb) { return M<double>::gauss(wa, wb); }
+
+// runs on one CTA (any size >= 32 threads); s_tot: shared scratch of 4*J doubles.
+// Chain-level values are staged in shared memory so the serial parts (swap, cold-slot numbering)
+// never wait on global-memory round trips.
+__device__ void gibbs_decide(const GibbsDecide& d, double* s_tot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int J = d.J, S = d.S;
+  double* s_T = s_tot + 2 * J;   // [J]
+  double* s_L = s_tot + 3 * J;   // [J]
+  for (int c = threadIdx.x; c < J; c += blockDim.x) {
+    s_T[c] = d.g_T[c];
+    s_L[c] = d.g_L[c];
+  }
+  if (d.it > 0) {
+    // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly
+    for (int c = warp; c < J; c += nw) {
+      double a = 0.0, b = 0.0;
+      for (int t = lane; t < d.n_tiles; t += 32) {
+        a += __ldcg(d.part_cur + static_cast<size_t>(c) * d.n_tiles + t);
+        b += __ldcg(d.part_prop + static_cast<size_t>(c) * d.n_tiles + t);
+      }
+      a = warp_sum<double>(a);
+      b = warp_sum<double>(b);
+      if (lane == 0) {
+        s_tot[c] = a;
+        s_tot[J + c] = b;
+      }
+    }
+    __syncthreads();
+    // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----
+    for (int c = threadIdx.x; c < J; c += blockDim.x) {
+      const int which = d.prop_which[c];
+      const double T = s_T[c];
+      const bool cold = T < 1.0 + kEps64;
+      const double Lcur = s_tot[c], Lprop = s_tot[J + c];
+      bool acc = false;
+      if (which != 0) {
+        const u32x4 wb = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 1u);
+        const double ratio = (Lprop - Lcur) / T + d.prop_lpr[c];
+        const double r = M<double>::u_co(wb.v[0]);
+        if (r >= kEps64 && ::log(r) <= ratio) acc = true;
+        if (cold && d.counts) {
+          atomicAdd(d.counts + (which - 1), 1ull);
+          if (acc) atomicAdd(d.counts + 7 + (which - 1), 1ull);
+        }
+        if (acc) {
+          const double xn = d.prop_xnew[c];
+          const int idx = d.prop_idx[c];
+          if (which == 1) d.g_vs[c] = xn;
+          if (which == 2) d.g_tc[static_cast<size_t>(c) * S + idx] = xn;
+          if (which == 3) d.g_qs[c] = xn;
+          if (which == 4) d.g_ac[static_cast<size_t>(c) * S + idx] = xn;
+        }
+      }
+      d.a_prev[c] = acc ? 1 : 0;
+      s_L[c] = acc ? Lprop : Lcur;
+      d.g_L[c] = s_L[c];
+      if (d.trace) {
+        htm_step_trace t;
+        t.proposal_type = which;
+        t.index = which ? d.prop_idx[c] + 1 : 0;
+        t.prior_ok = 1;
+        t.accepted = acc ? 1 : 0;
+        t.log_likelihood = s_L[c];
+        d.trace[c] = t;
+      }
+    }
+    __syncthreads();
+    // ---- record the cold chains' shared parameters (src/hypo_tremor_mcmc.f90:270-280) ----
+    if (d.rec_slot >= 0 && d.rec_chain) {
+      for (int c = warp; c < J; c += nw) {
+        const int s = d.slot_of[c];
+        if (s < 0) continue;
+        const size_t o = static_cast<size_t>(d.rec_slot) * d.n_cool_total + s;
+        if (lane == 0) {
+          d.rec_chain[o] = c;
+          d.rec_vs[o] = d.g_vs[c];
+          d.rec_qs[o] = d.g_qs[c];
+          d.rec_L[o] = s_L[c];
+        }
+        for (int j = lane; j < S; j += 32) {
+          d.rec_tc[o * S + j] = d.g_tc[static_cast<size_t>(c) * S + j];
+          d.rec_ac[o * S + j] = d.g_ac[static_cast<size_t>(c) * S + j];
+        }
+      }
+      __syncthreads();
+    }
+    // ---- one swap attempt over all J chains (src/cls_parallel.f90:220-240, 285-302) ----
+    if (threadIdx.x == 0 && J >= 2) {
+      const u32x4 w = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), d.swap_stream, PHX_SWAP, 1u);
+      const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(J)));
+      int i2 = i1 + 1 + static_cast<int>(below(w.v[1], static_cast<uint32_t>(J - 1)));
+      if (i2 >= J) i2 -= J;
+      const double T1 = s_T[i1], T2 = s_T[i2], L1 = s_L[i1], L2 = s_L[i2];
+      const double del_s = (L2 - L1) * (1.0 / T1 - 1.0 / T2);
+      const double r = M<double>::u_co(w.v[2]);
+      const bool sacc = r >= kEps64 && ::log(r) <= del_s;
+      if (sacc) {
+        s_T[i1] = T2;
+        s_T[i2] = T1;
+        d.g_T[i1] = T2;
+        d.g_T[i2] = T1;
+      }
+      if (d.swap) {
+        htm_swap_trace t;
+        t.rank1 = i1 / d.K;
+        t.chain1 = i1 % d.K + 1;
+        t.rank2 = i2 / d.K;
+        t.chain2 = i2 % d.K + 1;
+        t.accepted = sacc ? 1 : 0;
+        t.reserved = 0;
+        *d.swap = t;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- slots of the cold chains (in chain order) for the next iteration's records ----
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int c = 0; c < J; ++c) d.slot_of[c] = (s_T[c] < 1.0 + kEps64) ? s++ : -1;
+  }
+  // ---- next shared-parameter proposal (src/cls_mcmc.f90:134-157 restricted to the solved ones) ----
+  for (int c = threadIdx.x; c < J; c += blockDim.x) {
+    if (d.n_solved == 0) {
+      d.prop_which[c] = 0;
+      continue;
+    }
+    const u32x4 wa = philox4x32_10(d.rk, static_cast<uint32_t>(d.it_next), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 0u);
+    const int which = d.solved[below(wa.v[0], static_cast<uint32_t>(d.n_solved))];
+    const int idx = (which == 2 || which == 4) ? static_cast<int>(below(wa.v[1], static_cast<uint32_t>(S))) : 0;
+    const double gs = gauss64(wa.v[2], wa.v[3]);
+    double x_old;
+    if (which == 1) x_old = d.g_vs[c];
+    else if (which == 2) x_old = d.g_tc[static_cast<size_t>(c) * S + idx];
+    else if (which == 3) x_old = d.g_qs[c];
+    else x_old = d.g_ac[static_cast<size_t>(c) * S + idx];
+    const double mu = d.prior[which - 1], sg = d.width[which - 1];
+    const double x_new = __dadd_rn(x_old, __dmul_rn(gs, d.step[which - 1]));
+    const double dn = x_new - mu, dl = x_old - mu;
+    d.prop_which[c] = which;
+    d.prop_idx[c] = idx;
+    d.prop_xnew[c] = x_new;
+    d.prop_lpr[c] = -(__dmul_rn(dn, dn) - __dmul_rn(dl, dl)) / (2.0 * sg * sg);
+  }
+}
+
+__global__ void __launch_bounds__(256) gibbs_decide_kernel(const GibbsDecide d) {
+  extern __shared__ double s_tot_dyn[];  // [2][J]
+  gibbs_decide(d, s_tot_dyn);
+}
+
+// ---- float32 packed evaluation (lane = event, warp = chain) --------------------------------------------
+// Row of one event in the expanded table: [0] = A of station 0, [1] = {t_obs0, a_obs0, 0, 0}, then 4 float4
+// per station pair (htm_forward.cuh: store_station_pair).  cp[m] = {-tc_j0, -tc_j1, -ac_j0, -ac_j1} are the
+// chain's station terms of pair m (warp-broadcast), ntc0/nac0 those of station 0.
+__device__ __forceinline__ int gibbs_xrow(int S) { return 2 + 4 * (S / 2); }
+__device__ __forceinline__ float eval_pairs_f32(const float4* __restrict__ row, const int n_pairs, const float hx,
+                                                const float hy, const float hz, const Glob<float>& g,
+                                                const float4* __restrict__ cp, const float ntc0, const float nac0,
+                                                const float4 evc) {
+  const float kC = 0.34657359027997264f;
+  const float4 A0 = row[0], h1 = row[1];
+  const float h2 = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
+  float2 nct, nca;
+  {
+    const float d2 = fmaf(hx, A0.x, fmaf(hy, A0.y, fmaf(hz, A0.z, A0.w + h2)));
+    const float d = d2 * mufu_rsq(d2);
+    const float l2 = mufu_lg2(d2);
+    const float ct = -(fmaf(d, g.ivs, ntc0) - h1.x);
+    const float ca = -(fmaf(-kC, l2, fmaf(-g.B, d, nac0)) - h1.y);
+    nct = f2(ct, ct);
+    nca = f2(ca, ca);
+  }
+  const float2 px = f2(hx, hx), py = f2(hy, hy), pz = f2(hz, hz), hh = f2(h2, h2);
+  const float2 ivs2 = f2(g.ivs, g.ivs), nB2 = f2(-g.B, -g.B), nc2 = f2(-kC, -kC);
+  float2 a1t = f2(0.f, 0.f), a1a = f2(0.f, 0.f), a2 = f2(0.f, 0.f);
+  const float4* r = row + 2;
+#pragma unroll 2
+  for (int m = 0; m < n_pairs; ++m) {
+    const float4 r0 = r[4 * m], r1 = r[4 * m + 1], r2 = r[4 * m + 2], r3 = r[4 * m + 3];
+    const float4 c4 = cp[m];
+    const float2 swt = f2(r2.x, r2.y), swa = f2(r3.x, r3.y);
+    const float2 d2 = __ffma2_rn(px, f2(r0.x, r0.y),
+                                 __ffma2_rn(py, f2(r0.z, r0.w), __ffma2_rn(pz, f2(r1.x, r1.y), __fadd2_rn(f2(r1.z, r1.w), hh))));
+    const float2 d = __fmul2_rn(d2, f2(mufu_rsq(d2.x), mufu_rsq(d2.y)));
+    const float2 l2 = f2(mufu_lg2(d2.x), mufu_lg2(d2.y));
+    const float2 at = __fadd2_rn(__ffma2_rn(d, ivs2, nct), f2(c4.x, c4.y));
+    const float2 ut = __ffma2_rn(swt, at, f2(r2.z, r2.w));
+    const float2 aa = __fadd2_rn(__ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, nca)), f2(c4.z, c4.w));
+    const float2 ua = __ffma2_rn(swa, aa, f2(r3.z, r3.w));
+    a2 = __ffma2_rn(ut, ut, a2);
+    a1t = __ffma2_rn(swt, ut, a1t);
+    a2 = __ffma2_rn(ua, ua, a2);
+    a1a = __ffma2_rn(swa, ua, a1a);
+  }
+  return finish_loglik<float>(a1t.x + a1t.y, a2.x + a2.y, a1a.x + a1a.y, 0.f, evc);
+}
+
+// builds the expanded rows once per table upload: one thread per (event, pair) and one per event header
+__global__ void expand_obs_kernel(const float4* __restrict__ sta4, const float4* __restrict__ obs4,
+                                  const float2* __restrict__ prior_xy, int E, int S, float4* __restrict__ obsx) {
+  const int n_pairs = S / 2, per_ev = n_pairs + 1, xrow = 2 + 4 * n_pairs;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(E) * per_ev) return;
+  const int e = static_cast<int>(i / per_ev), m = static_cast<int>(i % per_ev) - 1;
+  const float2 c = prior_xy[e];
+  const float4* ob = obs4 + static_cast<size_t>(e) * S;
+  float4* row = obsx + static_cast<size_t>(e) * xrow;
+  if (m < 0) {
+    const StaRecF r0 = expand_station(sta4[0], ob[0], c.x, c.y);
+    row[0] = r0.A;
+    row[1] = make_float4(ob[0].x, ob[0].z, 0.f, 0.f);
+    return;
+  }
+  const int j0 = 1 + 2 * m, j1 = j0 + 1;
+  const StaRecF a = expand_station(sta4[j0], ob[j0], c.x, c.y);
+  StaRecF b = a;
+  if (j1 < S)
+    b = expand_station(sta4[j1], ob[j1], c.x, c.y);
+  else
+    b.B = make_float4(0.f, 0.f, 0.f, 0.f);
+  store_station_pair(row + 2 + 4 * m, a, b);
+}
+
+cudaError_t launch_expand_obs(const Tables& tab, int E, int S, void* obsx, cudaStream_t stream) {
+  const size_t n = static_cast<size_t>(E) * (S / 2 + 1);
+  expand_obs_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(
+      static_cast<const float4*>(tab.sta4), static_cast<const float4*>(tab.obs4_raw),
+      static_cast<const float2*>(tab.prior_xy), E, S, static_cast<float4*>(obsx));
+  return cudaGetLastError();
+}
+
 template <typename real, bool TRACE>
-__global__ void __launch_bounds__(kCW * 32) gibbs_sweep_kernel(const GibbsParams<real> p) {
+__global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsParams<real> p, const GibbsDecide dec,
+                                                               unsigned int* done_counter) {
   typedef typename M<real>::real4 real4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S, J = p.J, E = p.E;
   const int tile = blockIdx.x, e = tile * kTile + lane;
   const int c = blockIdx.y * kCW + warp;
-  const int row = S + 1;  // padded row stride (in real4) -> conflict-free per-lane LDS.128
+  constexpr bool kF32 = sizeof(real) == 4;
+  const int n_pairs = S / 2;
+  // float32: rows of the expanded table (xrow float4 + 1 pad: odd stride -> conflict-free per-lane LDS.128);
+  // float64: rows of the raw table (S real4 + 1 pad) + the station table
+  const int row = kF32 ? p.xrow + 1 : S + 1;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // 16 bytes reserved
   real4* s_obs = reinterpret_cast<real4*>(smem_raw + 16);     // [kTile][row]
-  real4* s_sta = s_obs + kTile * row;                          // [S]
-  real* s_tc = reinterpret_cast<real*>(s_sta + S);             // [kCW][S]
-  real* s_ac = s_tc + kCW * S;                                 // [kCW][S]
+  real4* s_sta = s_obs + kTile * row;                          // f64: [S]
+  real* s_tc = reinterpret_cast<real*>(s_sta + S);             // f64: [kCW][S]
+  real* s_ac = s_tc + kCW * S;                                 // f64: [kCW][S]
+  // f32: station terms per pair, current and proposed, and those of station 0
+  float4* s_cp = reinterpret_cast<float4*>(s_obs + kTile * row);   // [kCW][n_pairs]
+  float4* s_cpP = s_cp + kCW * n_pairs;                            // [kCW][n_pairs]
+  float4* s_c0 = s_cpP + kCW * n_pairs;                            // [kCW] {-tc0, -ac0, -tc0', -ac0'}
   const int n_ev = min(kTile, E - tile * kTile);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
@@ -116,23 +387,59 @@ __global__ void __launch_bounds__(kCW * 32) gibbs_sweep_kernel(const GibbsParams
   }
   __syncthreads();
   if (warp == 0) {
-    const uint32_t bytes = static_cast<uint32_t>(S * sizeof(real4));
-    if (lane == 0) mbar_expect_tx(bar, bytes * (n_ev + 1));
-    __syncwarp();
-    if (lane < n_ev) tma_load_1d(s_obs + lane * row, p.obs4 + static_cast<size_t>(tile * kTile + lane) * S, bytes, bar);
-    if (lane == 0) tma_load_1d(s_sta, p.sta4, bytes, bar);
+    if constexpr (kF32) {
+      const uint32_t bytes = static_cast<uint32_t>(p.xrow * sizeof(float4));
+      if (lane == 0) mbar_expect_tx(bar, bytes * n_ev);
+      __syncwarp();
+      if (lane < n_ev)
+        tma_load_1d(s_obs + lane * row, p.obsx + static_cast<size_t>(tile * kTile + lane) * p.xrow, bytes, bar);
+    } else {
+      const uint32_t bytes = static_cast<uint32_t>(S * sizeof(real4));
+      if (lane == 0) mbar_expect_tx(bar, bytes * (n_ev + 1));
+      __syncwarp();
+      if (lane < n_ev) tma_load_1d(s_obs + lane * row, p.obs4 + static_cast<size_t>(tile * kTile + lane) * S, bytes, bar);
+      if (lane == 0) tma_load_1d(s_sta, p.sta4, bytes, bar);
+    }
   }
-  // this chain's station terms (current values) -> shared memory
+  // this chain's station terms -> shared memory
   const bool chain_ok = c < J;
   if (chain_ok) {
-    for (int j = lane; j < S; j += 32) {
-      s_tc[warp * S + j] = static_cast<real>(p.g_tc[static_cast<size_t>(c) * S + j]);
-      s_ac[warp * S + j] = static_cast<real>(p.g_ac[static_cast<size_t>(c) * S + j]);
+    if constexpr (kF32) {
+      const double* gtc = p.g_tc + static_cast<size_t>(c) * S;
+      const double* gac = p.g_ac + static_cast<size_t>(c) * S;
+      const int wh = p.prop_which[c], pi = p.prop_idx[c];
+      const float pv = static_cast<float>(p.prop_xnew[c]);
+      for (int m = lane; m < n_pairs; m += 32) {
+        const int j0 = 1 + 2 * m, j1 = j0 + 1;
+        float4 cur = make_float4(-static_cast<float>(gtc[j0]), 0.f, -static_cast<float>(gac[j0]), 0.f);
+        if (j1 < S) {
+          cur.y = -static_cast<float>(gtc[j1]);
+          cur.w = -static_cast<float>(gac[j1]);
+        }
+        float4 prp = cur;
+        if (wh == 2 && pi == j0) prp.x = -pv;
+        if (wh == 2 && pi == j1) prp.y = -pv;
+        if (wh == 4 && pi == j0) prp.z = -pv;
+        if (wh == 4 && pi == j1) prp.w = -pv;
+        s_cp[warp * n_pairs + m] = cur;
+        s_cpP[warp * n_pairs + m] = prp;
+      }
+      if (lane == 0) {
+        float4 c0 = make_float4(-static_cast<float>(gtc[0]), -static_cast<float>(gac[0]), 0.f, 0.f);
+        c0.z = (wh == 2 && pi == 0) ? -pv : c0.x;
+        c0.w = (wh == 4 && pi == 0) ? -pv : c0.y;
+        s_c0[warp] = c0;
+      }
+    } else {
+      for (int j = lane; j < S; j += 32) {
+        s_tc[warp * S + j] = static_cast<real>(p.g_tc[static_cast<size_t>(c) * S + j]);
+        s_ac[warp * S + j] = static_cast<real>(p.g_ac[static_cast<size_t>(c) * S + j]);
+      }
     }
   }
   __syncthreads();
   mbar_wait(bar, 0);
-  if (!chain_ok) return;
+  if (chain_ok) {
 
   const bool ev_ok = e < E;
   const int ee = ev_ok ? e : E - 1;  // clamp: idle lanes clone the last event, never write
@@ -173,7 +480,13 @@ __global__ void __launch_bounds__(kCW * 32) gibbs_sweep_kernel(const GibbsParams
       lpr = lpr + M<real>::log(dn) - M<real>::log(dl);
   }
   const real nx = icmp == 2 ? x_new : x, ny = icmp == 1 ? x_new : y, nz = isz ? x_new : z;
-  const real Lnew = event_loglik_corr<real>(s_sta, obs_row, evc, S, nx, ny, nz, g, tc, ac, 0, -1, 0);
+  real Lnew;
+  if constexpr (kF32) {
+    Lnew = eval_pairs_f32(reinterpret_cast<const float4*>(obs_row), n_pairs, nx - mux, ny - muy, nz, g,
+                          s_cp + warp * n_pairs, s_c0[warp].x, s_c0[warp].y, evc);
+  } else {
+    Lnew = event_loglik_corr<real>(s_sta, obs_row, evc, S, nx, ny, nz, g, tc, ac, 0, -1, 0);
+  }
   const real ratio = M<real>::div(Lnew - Le, T, iT) + lpr;
   const real ru = M<real>::u_co(w.v[3]);
   const bool acc = ok && (ru > static_cast<real>(0)) && (M<real>::log(ru) <= ratio);
@@ -198,8 +511,13 @@ __global__ void __launch_bounds__(kCW * 32) gibbs_sweep_kernel(const GibbsParams
   real Lp = Le;
   if (which != 0) {
     const Glob<real> gp = make_glob<real>(which == 1 ? pval : vs, which == 3 ? pval : qs);
-    Lp = event_loglik_corr<real>(s_sta, obs_row, evc, S, x, y, z, gp, tc, ac, which, (which == 2 || which == 4) ? pidx : -1,
-                                 pval);
+    if constexpr (kF32) {
+      Lp = eval_pairs_f32(reinterpret_cast<const float4*>(obs_row), n_pairs, x - mux, y - muy, z, gp,
+                          s_cpP + warp * n_pairs, s_c0[warp].z, s_c0[warp].w, evc);
+    } else {
+      Lp = event_loglik_corr<real>(s_sta, obs_row, evc, S, x, y, z, gp, tc, ac, which,
+                                   (which == 2 || which == 4) ? pidx : -1, pval);
+    }
   }
   if (ev_ok) {
     p.hx[ci] = x;
@@ -234,168 +552,21 @@ __global__ void __launch_bounds__(kCW * 32) gibbs_sweep_kernel(const GibbsParams
       }
     }
   }
-}
+  }  // chain_ok
 
-// ---- chain-level bookkeeping -----------------------------------------------------------------------
-struct GibbsDecide {
-  double *g_vs, *g_qs, *g_tc, *g_ac, *g_T, *g_L;
-  int* prop_which;
-  int* prop_idx;
-  double* prop_xnew;
-  double* prop_lpr;
-  int* a_prev;
-  int* slot_of;
-  const double *part_cur, *part_prop;
-  int S, J, K, n_tiles, n_cool_total;
-  int it;       // iteration being decided; 0 = prepare only (no decision, no swap)
-  int it_next;  // iteration to propose for
-  PhiloxKeys rk;
-  uint32_t chain_offset, swap_stream;
-  int n_solved;
-  int solved[4];
-  double prior[4], width[4], step[4];  // indexed by type-1: vs, t_corr, qs, a_corr
-  unsigned long long* counts;
-  // shared-parameter records of the cold chains: [cap][n_cool_total]
-  int rec_slot;
-  int* rec_chain;
-  double *rec_vs, *rec_qs, *rec_L, *rec_tc, *rec_ac;
-  htm_step_trace* trace;  // [J] (row E of this iteration's block) or null
-  htm_swap_trace* swap;
-};
-
-__device__ __forceinline__ double gauss64(uint32_t wa, uint32_t wb) { return M<double>::gauss(wa, wb); }
-
-__global__ void __launch_bounds__(256) gibbs_decide_kernel(const GibbsDecide d) {
-  extern __shared__ double s_tot[];  // [2][J]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int J = d.J, S = d.S;
-  if (d.it > 0) {
-    // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly
-    for (int c = warp; c < J; c += nw) {
-      double a = 0.0, b = 0.0;
-      for (int t = lane; t < d.n_tiles; t += 32) {
-        a += d.part_cur[static_cast<size_t>(c) * d.n_tiles + t];
-        b += d.part_prop[static_cast<size_t>(c) * d.n_tiles + t];
-      }
-      a = warp_sum<double>(a);
-      b = warp_sum<double>(b);
-      if (lane == 0) {
-        s_tot[c] = a;
-        s_tot[J + c] = b;
-      }
-    }
-    __syncthreads();
-    // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----
-    for (int c = threadIdx.x; c < J; c += blockDim.x) {
-      const int which = d.prop_which[c];
-      const double T = d.g_T[c];
-      const bool cold = T < 1.0 + kEps64;
-      const double Lcur = s_tot[c], Lprop = s_tot[J + c];
-      bool acc = false;
-      if (which != 0) {
-        const u32x4 wb = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 1u);
-        const double ratio = (Lprop - Lcur) / T + d.prop_lpr[c];
-        const double r = M<double>::u_co(wb.v[0]);
-        if (r >= kEps64 && ::log(r) <= ratio) acc = true;
-        if (cold && d.counts) {
-          atomicAdd(d.counts + (which - 1), 1ull);
-          if (acc) atomicAdd(d.counts + 7 + (which - 1), 1ull);
-        }
-        if (acc) {
-          const double xn = d.prop_xnew[c];
-          const int idx = d.prop_idx[c];
-          if (which == 1) d.g_vs[c] = xn;
-          if (which == 2) d.g_tc[static_cast<size_t>(c) * S + idx] = xn;
-          if (which == 3) d.g_qs[c] = xn;
-          if (which == 4) d.g_ac[static_cast<size_t>(c) * S + idx] = xn;
-        }
-      }
-      d.a_prev[c] = acc ? 1 : 0;
-      d.g_L[c] = acc ? Lprop : Lcur;
-      if (d.trace) {
-        htm_step_trace t;
-        t.proposal_type = which;
-        t.index = which ? d.prop_idx[c] + 1 : 0;
-        t.prior_ok = 1;
-        t.accepted = acc ? 1 : 0;
-        t.log_likelihood = d.g_L[c];
-        d.trace[c] = t;
-      }
-    }
-    __syncthreads();
-    // ---- record the cold chains' shared parameters (src/hypo_tremor_mcmc.f90:270-280) ----
-    if (d.rec_slot >= 0 && d.rec_chain) {
-      for (int c = warp; c < J; c += nw) {
-        const int s = d.slot_of[c];
-        if (s < 0) continue;
-        const size_t o = static_cast<size_t>(d.rec_slot) * d.n_cool_total + s;
-        if (lane == 0) {
-          d.rec_chain[o] = c;
-          d.rec_vs[o] = d.g_vs[c];
-          d.rec_qs[o] = d.g_qs[c];
-          d.rec_L[o] = d.g_L[c];
-        }
-        for (int j = lane; j < S; j += 32) {
-          d.rec_tc[o * S + j] = d.g_tc[static_cast<size_t>(c) * S + j];
-          d.rec_ac[o * S + j] = d.g_ac[static_cast<size_t>(c) * S + j];
-        }
-      }
-    }
-    __syncthreads();
-    // ---- one swap attempt over all J chains (src/cls_parallel.f90:220-240, 285-302) ----
-    if (threadIdx.x == 0 && J >= 2) {
-      const u32x4 w = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), d.swap_stream, PHX_SWAP, 1u);
-      const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(J)));
-      int i2 = i1 + 1 + static_cast<int>(below(w.v[1], static_cast<uint32_t>(J - 1)));
-      if (i2 >= J) i2 -= J;
-      const double T1 = d.g_T[i1], T2 = d.g_T[i2], L1 = d.g_L[i1], L2 = d.g_L[i2];
-      const double del_s = (L2 - L1) * (1.0 / T1 - 1.0 / T2);
-      const double r = M<double>::u_co(w.v[2]);
-      const bool sacc = r >= kEps64 && ::log(r) <= del_s;
-      if (sacc) {
-        d.g_T[i1] = T2;
-        d.g_T[i2] = T1;
-      }
-      if (d.swap) {
-        htm_swap_trace t;
-        t.rank1 = i1 / d.K;
-        t.chain1 = i1 % d.K + 1;
-        t.rank2 = i2 / d.K;
-        t.chain2 = i2 % d.K + 1;
-        t.accepted = sacc ? 1 : 0;
-        t.reserved = 0;
-        *d.swap = t;
-      }
-    }
-    __syncthreads();
-  }
-  // ---- slots of the cold chains (in chain order) for the next iteration's records ----
+  // ---- the last CTA to finish judges the shared-parameter proposals (fixed-order sums: deterministic) ----
+  __shared__ int s_last;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    int s = 0;
-    for (int c = 0; c < J; ++c) d.slot_of[c] = (d.g_T[c] < 1.0 + kEps64) ? s++ : -1;
+    __threadfence();  // the CTA's partial sums (ordered before by the barrier) become visible device-wide
+    const unsigned int ticket = atomicAdd(done_counter, 1u);
+    s_last = ticket == gridDim.x * gridDim.y - 1 ? 1 : 0;
   }
-  // ---- next shared-parameter proposal (src/cls_mcmc.f90:134-157 restricted to the solved ones) ----
-  for (int c = threadIdx.x; c < J; c += blockDim.x) {
-    if (d.n_solved == 0) {
-      d.prop_which[c] = 0;
-      continue;
-    }
-    const u32x4 wa = philox4x32_10(d.rk, static_cast<uint32_t>(d.it_next), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 0u);
-    const int which = d.solved[below(wa.v[0], static_cast<uint32_t>(d.n_solved))];
-    const int idx = (which == 2 || which == 4) ? static_cast<int>(below(wa.v[1], static_cast<uint32_t>(S))) : 0;
-    const double gs = gauss64(wa.v[2], wa.v[3]);
-    double x_old;
-    if (which == 1) x_old = d.g_vs[c];
-    else if (which == 2) x_old = d.g_tc[static_cast<size_t>(c) * S + idx];
-    else if (which == 3) x_old = d.g_qs[c];
-    else x_old = d.g_ac[static_cast<size_t>(c) * S + idx];
-    const double mu = d.prior[which - 1], sg = d.width[which - 1];
-    const double x_new = __dadd_rn(x_old, __dmul_rn(gs, d.step[which - 1]));
-    const double dn = x_new - mu, dl = x_old - mu;
-    d.prop_which[c] = which;
-    d.prop_idx[c] = idx;
-    d.prop_xnew[c] = x_new;
-    d.prop_lpr[c] = -(__dmul_rn(dn, dn) - __dmul_rn(dl, dl)) / (2.0 * sg * sg);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    gibbs_decide(dec, reinterpret_cast<double*>(smem_raw));
+    if (threadIdx.x == 0) *done_counter = 0u;
   }
 }
 
@@ -491,6 +662,8 @@ static GibbsParams<real> make_gibbs_params(const GibbsLaunch& a) {
   p.obs4 = static_cast<const real4*>(a.tab.obs4_raw);
   p.evc4 = static_cast<const real4*>(a.tab.evc4);
   p.prior_xy = a.tab.prior_xy;
+  p.obsx = static_cast<const float4*>(a.obsx);
+  p.xrow = a.xrow;
   p.hx = static_cast<real*>(a.hx);
   p.hy = static_cast<real*>(a.hy);
   p.hz = static_cast<real*>(a.hz);
@@ -586,6 +759,10 @@ static GibbsDecide make_decide(const GibbsLaunch& a) {
 template <typename real>
 static size_t sweep_smem(int S) {
   typedef typename M<real>::real4 real4;
+  if (sizeof(real) == 4) {
+    const int n_pairs = S / 2, xrow = 2 + 4 * n_pairs;
+    return 16 + static_cast<size_t>(kTile) * (xrow + 1) * sizeof(float4) + (2 * kCW * n_pairs + kCW) * sizeof(float4);
+  }
   return static_cast<size_t>(kTile) * (S + 1) * sizeof(real4) + S * sizeof(real4) + 2 * kCW * S * sizeof(real) + 32;
 }
 
@@ -593,7 +770,8 @@ template <typename real>
 static cudaError_t launch_gibbs_t(const GibbsLaunch& a, cudaStream_t stream, int* n_launches) {
   GibbsParams<real> p = make_gibbs_params<real>(a);
   GibbsDecide d = make_decide(a);
-  const size_t smem = sweep_smem<real>(a.S);
+  size_t smem = sweep_smem<real>(a.S);
+  if (smem < 4 * static_cast<size_t>(a.J) * sizeof(double)) smem = 4 * static_cast<size_t>(a.J) * sizeof(double);
   cudaError_t err;
   const bool tracing = a.trace || a.swaps;
   if (tracing)
@@ -602,7 +780,7 @@ static cudaError_t launch_gibbs_t(const GibbsLaunch& a, cudaStream_t stream, int
     err = cudaFuncSetAttribute(gibbs_sweep_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
   const dim3 grid(p.n_tiles, (a.J + kCW - 1) / kCW);
-  const size_t dsm = 2 * static_cast<size_t>(a.J) * sizeof(double);
+  const size_t dsm = 4 * static_cast<size_t>(a.J) * sizeof(double);
   int nl = 0;
   // prepare: cold slots + the proposal of the first iteration (a pure function of state and iteration)
   d.it = 0;
@@ -610,23 +788,23 @@ static cudaError_t launch_gibbs_t(const GibbsLaunch& a, cudaStream_t stream, int
   gibbs_decide_kernel<<<1, 256, dsm, stream>>>(d);
   ++nl;
   const size_t per_it = static_cast<size_t>(a.E + 1) * a.J;
+  // one launch per iteration: the sweep, and in its last CTA the chain-level decide step
   for (int it = a.iter_first; it <= a.iter_last; ++it) {
     const bool rec = a.n_interval > 1 && (it % a.n_interval) == 1;
     const int slot = rec ? (it - 1) / a.n_interval - a.rec_origin : -1;
     p.it = it;
     p.rec_slot = (slot >= 0 && slot < a.rec_cap) ? slot : -1;
     p.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it : nullptr;
-    if (tracing)
-      gibbs_sweep_kernel<real, true><<<grid, kCW * 32, smem, stream>>>(p);
-    else
-      gibbs_sweep_kernel<real, false><<<grid, kCW * 32, smem, stream>>>(p);
     d.it = it;
     d.it_next = it + 1;
     d.rec_slot = p.rec_slot;
     d.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it + static_cast<size_t>(a.E) * a.J : nullptr;
     d.swap = a.swaps ? a.swaps + (it - a.iter_first) : nullptr;
-    gibbs_decide_kernel<<<1, 256, dsm, stream>>>(d);
-    nl += 2;
+    if (tracing)
+      gibbs_sweep_kernel<real, true><<<grid, kCW * 32, smem, stream>>>(p, d, a.done_counter);
+    else
+      gibbs_sweep_kernel<real, false><<<grid, kCW * 32, smem, stream>>>(p, d, a.done_counter);
+    ++nl;
   }
   if (n_launches) *n_launches = nl;
   return cudaGetLastError();

@@ -87,6 +87,9 @@ struct GibbsLaunch {
   int *prop_which = nullptr, *prop_idx = nullptr, *a_prev = nullptr, *slot_of = nullptr;
   double *prop_xnew = nullptr, *prop_lpr = nullptr;
   double *part_cur = nullptr, *part_prop = nullptr;  // [J][ceil(E/32)]
+  unsigned int* done_counter = nullptr;              // CTAs finished in the current sweep
+  const void* obsx = nullptr;                        // float32: expanded station-pair rows [E][xrow] float4
+  int xrow = 0;
   int E = 0, S = 0, J = 0, K = 0, n_cool_total = 0;
   int iter_first = 0, iter_last = 0, n_burn = 0, n_interval = 1;
   uint64_t seed = 0;
@@ -105,6 +108,8 @@ struct GibbsLaunch {
   htm_swap_trace* swaps = nullptr;  // debug: [n_it]
 };
 cudaError_t launch_gibbs(const GibbsLaunch& a, cudaStream_t stream, int* n_launches);
+// float32: build the expanded rows from the raw tables (once per table upload)
+cudaError_t launch_expand_obs(const Tables& tab, int E, int S, void* obsx, cudaStream_t stream);
 cudaError_t launch_gibbs_init(const GibbsLaunch& a, double temp_high, int ladder, int n_cool, cudaStream_t stream);
 
 // FFMA / MUFU microbenchmark (roofline denominators)
