@@ -652,6 +652,10 @@ __global__ void fact_init_kernel(const FactParams<real> p, const real temp_high,
       T = M<real>::exp((u * (static_cast<real>(1) - static_cast<real>(kEps64)) + static_cast<real>(kEps64)) *
                        M<real>::log(temp_high));
     }
+    // The reference keeps a hot chain off T = 1 by mixing in eps(1.d0) (src/hypo_tremor_mcmc.f90:205); in
+    // float32 that margin rounds away (u = 0 gave T == 1.0f and one extra "cold" chain in a 6.4 M-chain
+    // run), so the smallest float above 1 is enforced instead.
+    if (sizeof(real) == 4 && !(T > static_cast<real>(1))) T = static_cast<real>(1.00000012f);
   }
   const Glob<real> g = make_glob<real>(p.vs, p.qs);
   const real L = lane_event_loglik<real>(p.sta4, p.obs4 + static_cast<size_t>(e) * p.S, p.evc4[e], p.S, x, y, z, g);
