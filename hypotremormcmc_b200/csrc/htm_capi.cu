@@ -823,7 +823,13 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
     h->gl.swaps = d_swaps;
     int nlg = 0;
     HTM_CK(h, cudaEventRecord(h->ev0, h->stream));
-    HTM_CK(h, launch_gibbs(h->gl, h->stream, &nlg));
+    {
+      const cudaError_t eg = launch_gibbs(h->gl, h->stream, &nlg);
+      if (eg == cudaErrorInvalidConfiguration)
+        return fail(h, HTM_ERR_UNSUPPORTED,
+                    "blocked-Gibbs mode stages 32 event rows per CTA in shared memory: n_sta is too large (limit about 200)");
+      HTM_CK(h, eg);
+    }
     HTM_CK(h, cudaEventRecord(h->ev1, h->stream));
     h->timed = true;
     h->last_launches = nlg;

@@ -724,9 +724,11 @@ static cudaError_t launch_lane(const FactLaunch& a, cudaStream_t stream) {
   const long n_warps = static_cast<long>(a.E) * wpe;
   // warps are independent, so the CTA size only sets how evenly they spread over the SMs:
   // 1-warp CTAs while everything is resident at once (<= 32 CTAs/SM), else 2 or 4
-  const int wpb = n_warps <= 148L * 32 ? 1 : (n_warps <= 148L * 64 ? 2 : 4);
+  int wpb = n_warps <= 148L * 32 ? 1 : (n_warps <= 148L * 64 ? 2 : 4);
+  const size_t per_warp = (sizeof(real) == 4 ? 4 : 2) * a.S * sizeof(real4) + sizeof(uint64_t);
+  while (wpb > 1 && wpb * per_warp > 200 * 1024) wpb >>= 1;  // very large station counts: fewer warps per CTA
   const unsigned grid = static_cast<unsigned>((n_warps + wpb - 1) / wpb);
-  const size_t smem = static_cast<size_t>(wpb) * ((sizeof(real) == 4 ? 4 : 2) * a.S * sizeof(real4) + sizeof(uint64_t));
+  const size_t smem = static_cast<size_t>(wpb) * per_warp;
   const bool trace = a.trace || a.swaps;
   cudaError_t err;
   if (trace) {
@@ -788,7 +790,7 @@ static cudaError_t launch_factorised_t(const FactLaunch& a, cudaStream_t stream,
     *why = "warp-per-chain kernel supports n_sta <= 128; use the lane-per-chain kernel";
     return cudaErrorInvalidValue;
   }
-  const size_t smem_need = static_cast<size_t>(4) * (4 * a.S * sizeof(typename M<real>::real4) + 8);
+  const size_t smem_need = (sizeof(real) == 4 ? 4 : 2) * a.S * sizeof(typename M<real>::real4) + 8;
   if (smem_need > 200 * 1024) {
     *why = "n_sta too large for the shared-memory staging of the lane-per-chain kernel";
     return cudaErrorInvalidValue;

@@ -771,6 +771,7 @@ static cudaError_t launch_gibbs_t(const GibbsLaunch& a, cudaStream_t stream, int
   GibbsParams<real> p = make_gibbs_params<real>(a);
   GibbsDecide d = make_decide(a);
   size_t smem = sweep_smem<real>(a.S);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // reported as "n_sta too large" by the caller
   if (smem < 4 * static_cast<size_t>(a.J) * sizeof(double)) smem = 4 * static_cast<size_t>(a.J) * sizeof(double);
   cudaError_t err;
   const bool tracing = a.trace || a.swaps;

@@ -78,6 +78,23 @@ def test_stream_reader_and_quantiles(tmp_path):
     assert (med, lo, hi) == (500.0, 25.0, 975.0)      # elements int(0.5 n), int(0.025 n), int(0.975 n), 1-based
 
 
+def test_stat_files_layout(tmp_path):
+    # (I9,9F13.6) / (A12,6F13.6) / (6F13.6) records of src/cls_statistics.f90:245-252,379-385,420-425
+    rng = np.random.default_rng(0)
+    out = dict(hypo=rng.normal(0, 1, (400, 6)), t_corr=rng.normal(0, 1, (400, 3)), a_corr=rng.normal(0, 1, (400, 3)),
+               vs=rng.normal(3, 0.1, (400, 1)), qs=rng.normal(250, 10, (400, 1)))
+    hio.write_stat_files(str(tmp_path), out, [7, 12], ["AAA", "BB", "C"])
+    lines = open(tmp_path / "hypo.stat").read().splitlines()
+    assert lines[0].startswith("# window ID") and len(lines) == 3 and len(lines[1]) == 9 + 9 * 13
+    v = [float(lines[2][9 + 13 * k: 22 + 13 * k]) for k in range(9)]
+    s = np.sort(out["hypo"][:, 3])
+    assert abs(v[0] - s[199]) < 1e-6 and abs(v[1] - s[9]) < 1e-6 and abs(v[2] - s[389]) < 1e-6   # 1-based 200, 10, 390
+    lines = open(tmp_path / "station_corrections.stat").read().splitlines()
+    assert len(lines) == 4 and len(lines[1]) == 12 + 6 * 13 and lines[3][:12].strip() == "C"
+    lines = open(tmp_path / "uniform_structure.stat").read().splitlines()
+    assert len(lines) == 2 and len(lines[1]) == 6 * 13 and abs(float(lines[1][:13]) - 3.0) < 0.05
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("solve", [0, 1])
 def test_driver_end_to_end(tmp_path, solve):
@@ -112,6 +129,13 @@ def test_driver_end_to_end(tmp_path, solve):
         s = [g.fetch_samples(rank) for rank in range(R)]
     assert np.array_equal(np.concatenate([x["hypo"] for x in s]), out["hypo"])
     assert np.array_equal(np.concatenate([x["vs"] for x in s]), out["vs"][:, 0])
+    # the statistics stage's tables from these files: medians bracketed by the 2.5 / 97.5 % bounds
+    hio.write_stat_files(str(tmp_path), out, list(range(1, E + 1)), ["ST%02d" % j for j in range(S)])
+    rows = [ln for ln in open(tmp_path / "hypo.stat").read().splitlines()[1:]]
+    assert len(rows) == E
+    for ln in rows:
+        v = [float(ln[9 + 13 * k: 22 + 13 * k]) for k in range(9)]
+        assert v[1] <= v[0] <= v[2] and v[4] <= v[3] <= v[5] and v[7] <= v[6] <= v[8]
     # little-endian switch
     r = run_driver(tmp_path, "--chunk", "64", "--little-endian")
     assert r.returncode == 0
