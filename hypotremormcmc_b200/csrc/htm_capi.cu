@@ -295,8 +295,8 @@ int32_t alloc_state(htm_handle h) {
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.slot_of), J * 4));
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.prop_xnew), J * 8));
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.prop_lpr), J * 8));
-    HTM_CK(h, grab(reinterpret_cast<void**>(&g.part_cur), J * nt * 8));
-    HTM_CK(h, grab(reinterpret_cast<void**>(&g.part_prop), J * nt * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.part_cur), 4 * J * nt * 8));  // [2 buffers][cur, prop][J][tiles]
+    g.part_prop = g.part_cur + J * nt;
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.done_counter), 8));
     if (h->cfg.max_samples > 0) {
       h->rec_cap = h->cfg.max_samples;
@@ -827,7 +827,10 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
       const cudaError_t eg = launch_gibbs(h->gl, h->stream, &nlg);
       if (eg == cudaErrorInvalidConfiguration)
         return fail(h, HTM_ERR_UNSUPPORTED,
-                    "blocked-Gibbs mode stages 32 event rows per CTA in shared memory: n_sta is too large (limit about 200)");
+                    "blocked-Gibbs mode stages 32 event rows and the chain-level state in shared memory: "
+                    "n_sta (limit about 200) or n_procs*n_chains*n_sta is too large");
+      if (eg == cudaErrorCooperativeLaunchTooLarge)
+        return fail(h, HTM_ERR_UNSUPPORTED, "HTM_GIBBS_PERSIST=1 but the grid does not fit on the device at once");
       HTM_CK(h, eg);
     }
     HTM_CK(h, cudaEventRecord(h->ev1, h->stream));

@@ -18,8 +18,14 @@
 // tile's observation rows are staged by 32 bulk-TMA copies (one per event) into padded shared-memory
 // rows, so the per-lane 16-byte reads are bank-conflict free; station table and the chains' station
 // terms are warp-broadcast reads.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "htm_forward.cuh"
 #include "htm_kernels.hpp"
+
+namespace cg = cooperative_groups;
 
 namespace htm {
 
@@ -125,109 +131,167 @@ struct GibbsDecide {
 
 __device__ __forceinline__ double gauss64(uint32_t wa, uint32_t wb) { return M<double>::gauss(wa, wb); }
 
-// runs on one CTA (any size >= 32 threads); s_tot: shared scratch of 4*J doubles.
-// Chain-level values are staged in shared memory so the serial parts (swap, cold-slot numbering)
-// never wait on global-memory round trips.
-__device__ void gibbs_decide(const GibbsDecide& d, double* s_tot) {
+// Chain-level state staged in shared memory: the serial parts of the decide step (swap, cold-slot numbering)
+// never wait on global memory, and the persistent kernel keeps it there for the whole launch.
+struct ChainSm {
+  double *T, *L, *vs, *qs, *xnew, *lpr, *tot, *tc, *ac;  // tot: [2][J]; tc, ac: [J][S]
+  int *which, *idx, *aprev, *slot;
+};
+__host__ __device__ inline size_t chain_sm_bytes(int J, int S) {
+  return static_cast<size_t>(J) * (2 * S + 8) * sizeof(double) + static_cast<size_t>(J) * 4 * sizeof(int);
+}
+__device__ __forceinline__ ChainSm carve_chain_sm(unsigned char* base, int J, int S) {
+  ChainSm c;
+  double* d = reinterpret_cast<double*>(base);
+  c.T = d; d += J;
+  c.L = d; d += J;
+  c.vs = d; d += J;
+  c.qs = d; d += J;
+  c.xnew = d; d += J;
+  c.lpr = d; d += J;
+  c.tot = d; d += 2 * J;
+  c.tc = d; d += static_cast<size_t>(J) * S;
+  c.ac = d; d += static_cast<size_t>(J) * S;
+  int* i = reinterpret_cast<int*>(d);
+  c.which = i; i += J;
+  c.idx = i; i += J;
+  c.aprev = i; i += J;
+  c.slot = i;
+  return c;
+}
+__device__ void chain_load(const GibbsDecide& d, const ChainSm& cs) {
+  for (int c = threadIdx.x; c < d.J; c += blockDim.x) {
+    cs.T[c] = d.g_T[c];
+    cs.L[c] = d.g_L[c];
+    cs.vs[c] = d.g_vs[c];
+    cs.qs[c] = d.g_qs[c];
+    cs.xnew[c] = d.prop_xnew[c];
+    cs.lpr[c] = d.prop_lpr[c];
+    cs.which[c] = d.prop_which[c];
+    cs.idx[c] = d.prop_idx[c];
+    cs.aprev[c] = d.a_prev[c];
+    cs.slot[c] = d.slot_of[c];
+  }
+  for (int i = threadIdx.x; i < d.J * d.S; i += blockDim.x) {
+    cs.tc[i] = d.g_tc[i];
+    cs.ac[i] = d.g_ac[i];
+  }
+}
+__device__ void chain_store(const GibbsDecide& d, const ChainSm& cs) {
+  for (int c = threadIdx.x; c < d.J; c += blockDim.x) {
+    d.g_T[c] = cs.T[c];
+    d.g_L[c] = cs.L[c];
+    d.g_vs[c] = cs.vs[c];
+    d.g_qs[c] = cs.qs[c];
+    d.prop_xnew[c] = cs.xnew[c];
+    d.prop_lpr[c] = cs.lpr[c];
+    d.prop_which[c] = cs.which[c];
+    d.prop_idx[c] = cs.idx[c];
+    d.a_prev[c] = cs.aprev[c];
+    d.slot_of[c] = cs.slot[c];
+  }
+  for (int i = threadIdx.x; i < d.J * d.S; i += blockDim.x) {
+    d.g_tc[i] = cs.tc[i];
+    d.g_ac[i] = cs.ac[i];
+  }
+}
+
+// The decide step on the staged state.  Every thread of the CTA takes part; a CTA that is not the
+// `writer` computes exactly the same values but leaves counters, records and traces alone (the
+// persistent kernel runs this redundantly on every CTA so that one grid barrier per iteration suffices).
+// Ends with a block barrier.
+__device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int it, const int it_next,
+                            const double* part_cur, const double* part_prop, const int rec_slot,
+                            htm_step_trace* trace, htm_swap_trace* swap, const bool writer) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int J = d.J, S = d.S;
-  double* s_T = s_tot + 2 * J;   // [J]
-  double* s_L = s_tot + 3 * J;   // [J]
-  for (int c = threadIdx.x; c < J; c += blockDim.x) {
-    s_T[c] = d.g_T[c];
-    s_L[c] = d.g_L[c];
-  }
-  if (d.it > 0) {
+  if (it > 0) {
     // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly
     for (int c = warp; c < J; c += nw) {
       double a = 0.0, b = 0.0;
       for (int t = lane; t < d.n_tiles; t += 32) {
-        a += __ldcg(d.part_cur + static_cast<size_t>(c) * d.n_tiles + t);
-        b += __ldcg(d.part_prop + static_cast<size_t>(c) * d.n_tiles + t);
+        a += __ldcg(part_cur + static_cast<size_t>(c) * d.n_tiles + t);
+        b += __ldcg(part_prop + static_cast<size_t>(c) * d.n_tiles + t);
       }
       a = warp_sum<double>(a);
       b = warp_sum<double>(b);
       if (lane == 0) {
-        s_tot[c] = a;
-        s_tot[J + c] = b;
+        cs.tot[c] = a;
+        cs.tot[J + c] = b;
       }
     }
     __syncthreads();
     // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----
     for (int c = threadIdx.x; c < J; c += blockDim.x) {
-      const int which = d.prop_which[c];
-      const double T = s_T[c];
+      const int which = cs.which[c];
+      const double T = cs.T[c];
       const bool cold = T < 1.0 + kEps64;
-      const double Lcur = s_tot[c], Lprop = s_tot[J + c];
+      const double Lcur = cs.tot[c], Lprop = cs.tot[J + c];
       bool acc = false;
       if (which != 0) {
-        const u32x4 wb = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 1u);
-        const double ratio = (Lprop - Lcur) / T + d.prop_lpr[c];
+        const u32x4 wb = philox4x32_10(d.rk, static_cast<uint32_t>(it), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 1u);
+        const double ratio = (Lprop - Lcur) / T + cs.lpr[c];
         const double r = M<double>::u_co(wb.v[0]);
         if (r >= kEps64 && ::log(r) <= ratio) acc = true;
-        if (cold && d.counts) {
+        if (writer && cold && d.counts) {
           atomicAdd(d.counts + (which - 1), 1ull);
           if (acc) atomicAdd(d.counts + 7 + (which - 1), 1ull);
         }
         if (acc) {
-          const double xn = d.prop_xnew[c];
-          const int idx = d.prop_idx[c];
-          if (which == 1) d.g_vs[c] = xn;
-          if (which == 2) d.g_tc[static_cast<size_t>(c) * S + idx] = xn;
-          if (which == 3) d.g_qs[c] = xn;
-          if (which == 4) d.g_ac[static_cast<size_t>(c) * S + idx] = xn;
+          const double xn = cs.xnew[c];
+          const int idx = cs.idx[c];
+          if (which == 1) cs.vs[c] = xn;
+          if (which == 2) cs.tc[static_cast<size_t>(c) * S + idx] = xn;
+          if (which == 3) cs.qs[c] = xn;
+          if (which == 4) cs.ac[static_cast<size_t>(c) * S + idx] = xn;
         }
       }
-      d.a_prev[c] = acc ? 1 : 0;
-      s_L[c] = acc ? Lprop : Lcur;
-      d.g_L[c] = s_L[c];
-      if (d.trace) {
+      cs.aprev[c] = acc ? 1 : 0;
+      cs.L[c] = acc ? Lprop : Lcur;
+      if (writer && trace) {
         htm_step_trace t;
         t.proposal_type = which;
-        t.index = which ? d.prop_idx[c] + 1 : 0;
+        t.index = which ? cs.idx[c] + 1 : 0;
         t.prior_ok = 1;
         t.accepted = acc ? 1 : 0;
-        t.log_likelihood = s_L[c];
-        d.trace[c] = t;
+        t.log_likelihood = cs.L[c];
+        trace[c] = t;
       }
     }
     __syncthreads();
     // ---- record the cold chains' shared parameters (src/hypo_tremor_mcmc.f90:270-280) ----
-    if (d.rec_slot >= 0 && d.rec_chain) {
+    if (writer && rec_slot >= 0 && d.rec_chain) {
       for (int c = warp; c < J; c += nw) {
-        const int s = d.slot_of[c];
-        if (s < 0) continue;
-        const size_t o = static_cast<size_t>(d.rec_slot) * d.n_cool_total + s;
+        const int sl = cs.slot[c];
+        if (sl < 0) continue;
+        const size_t o = static_cast<size_t>(rec_slot) * d.n_cool_total + sl;
         if (lane == 0) {
           d.rec_chain[o] = c;
-          d.rec_vs[o] = d.g_vs[c];
-          d.rec_qs[o] = d.g_qs[c];
-          d.rec_L[o] = s_L[c];
+          d.rec_vs[o] = cs.vs[c];
+          d.rec_qs[o] = cs.qs[c];
+          d.rec_L[o] = cs.L[c];
         }
         for (int j = lane; j < S; j += 32) {
-          d.rec_tc[o * S + j] = d.g_tc[static_cast<size_t>(c) * S + j];
-          d.rec_ac[o * S + j] = d.g_ac[static_cast<size_t>(c) * S + j];
+          d.rec_tc[o * S + j] = cs.tc[static_cast<size_t>(c) * S + j];
+          d.rec_ac[o * S + j] = cs.ac[static_cast<size_t>(c) * S + j];
         }
       }
-      __syncthreads();
     }
     // ---- one swap attempt over all J chains (src/cls_parallel.f90:220-240, 285-302) ----
     if (threadIdx.x == 0 && J >= 2) {
-      const u32x4 w = philox4x32_10(d.rk, static_cast<uint32_t>(d.it), d.swap_stream, PHX_SWAP, 1u);
+      const u32x4 w = philox4x32_10(d.rk, static_cast<uint32_t>(it), d.swap_stream, PHX_SWAP, 1u);
       const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(J)));
       int i2 = i1 + 1 + static_cast<int>(below(w.v[1], static_cast<uint32_t>(J - 1)));
       if (i2 >= J) i2 -= J;
-      const double T1 = s_T[i1], T2 = s_T[i2], L1 = s_L[i1], L2 = s_L[i2];
+      const double T1 = cs.T[i1], T2 = cs.T[i2], L1 = cs.L[i1], L2 = cs.L[i2];
       const double del_s = (L2 - L1) * (1.0 / T1 - 1.0 / T2);
       const double r = M<double>::u_co(w.v[2]);
       const bool sacc = r >= kEps64 && ::log(r) <= del_s;
       if (sacc) {
-        s_T[i1] = T2;
-        s_T[i2] = T1;
-        d.g_T[i1] = T2;
-        d.g_T[i2] = T1;
+        cs.T[i1] = T2;
+        cs.T[i2] = T1;
       }
-      if (d.swap) {
+      if (writer && swap) {
         htm_swap_trace t;
         t.rank1 = i1 / d.K;
         t.chain1 = i1 % d.K + 1;
@@ -235,44 +299,54 @@ __device__ void gibbs_decide(const GibbsDecide& d, double* s_tot) {
         t.chain2 = i2 % d.K + 1;
         t.accepted = sacc ? 1 : 0;
         t.reserved = 0;
-        *d.swap = t;
+        *swap = t;
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   // ---- slots of the cold chains (in chain order) for the next iteration's records ----
   if (threadIdx.x == 0) {
-    int s = 0;
-    for (int c = 0; c < J; ++c) d.slot_of[c] = (s_T[c] < 1.0 + kEps64) ? s++ : -1;
+    int sl = 0;
+    for (int c = 0; c < J; ++c) cs.slot[c] = (cs.T[c] < 1.0 + kEps64) ? sl++ : -1;
   }
   // ---- next shared-parameter proposal (src/cls_mcmc.f90:134-157 restricted to the solved ones) ----
   for (int c = threadIdx.x; c < J; c += blockDim.x) {
     if (d.n_solved == 0) {
-      d.prop_which[c] = 0;
+      cs.which[c] = 0;
       continue;
     }
-    const u32x4 wa = philox4x32_10(d.rk, static_cast<uint32_t>(d.it_next), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 0u);
+    const u32x4 wa = philox4x32_10(d.rk, static_cast<uint32_t>(it_next), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 0u);
     const int which = d.solved[below(wa.v[0], static_cast<uint32_t>(d.n_solved))];
     const int idx = (which == 2 || which == 4) ? static_cast<int>(below(wa.v[1], static_cast<uint32_t>(S))) : 0;
     const double gs = gauss64(wa.v[2], wa.v[3]);
     double x_old;
-    if (which == 1) x_old = d.g_vs[c];
-    else if (which == 2) x_old = d.g_tc[static_cast<size_t>(c) * S + idx];
-    else if (which == 3) x_old = d.g_qs[c];
-    else x_old = d.g_ac[static_cast<size_t>(c) * S + idx];
+    if (which == 1) x_old = cs.vs[c];
+    else if (which == 2) x_old = cs.tc[static_cast<size_t>(c) * S + idx];
+    else if (which == 3) x_old = cs.qs[c];
+    else x_old = cs.ac[static_cast<size_t>(c) * S + idx];
     const double mu = d.prior[which - 1], sg = d.width[which - 1];
     const double x_new = __dadd_rn(x_old, __dmul_rn(gs, d.step[which - 1]));
     const double dn = x_new - mu, dl = x_old - mu;
-    d.prop_which[c] = which;
-    d.prop_idx[c] = idx;
-    d.prop_xnew[c] = x_new;
-    d.prop_lpr[c] = -(__dmul_rn(dn, dn) - __dmul_rn(dl, dl)) / (2.0 * sg * sg);
+    cs.which[c] = which;
+    cs.idx[c] = idx;
+    cs.xnew[c] = x_new;
+    cs.lpr[c] = -(__dmul_rn(dn, dn) - __dmul_rn(dl, dl)) / (2.0 * sg * sg);
   }
+  __syncthreads();
+}
+
+// one CTA: global -> shared, decide, shared -> global.  smem: chain_sm_bytes(J, S)
+__device__ void gibbs_decide(const GibbsDecide& d, unsigned char* smem) {
+  const ChainSm cs = carve_chain_sm(smem, d.J, d.S);
+  chain_load(d, cs);
+  __syncthreads();
+  decide_core(d, cs, d.it, d.it_next, d.part_cur, d.part_prop, d.rec_slot, d.trace, d.swap, true);
+  chain_store(d, cs);
 }
 
 __global__ void __launch_bounds__(256) gibbs_decide_kernel(const GibbsDecide d) {
-  extern __shared__ double s_tot_dyn[];  // [2][J]
-  gibbs_decide(d, s_tot_dyn);
+  extern __shared__ __align__(16) unsigned char s_decide_dyn[];
+  gibbs_decide(d, s_decide_dyn);
 }
 
 // ---- float32 packed evaluation (lane = event, warp = chain) --------------------------------------------
@@ -356,115 +430,39 @@ cudaError_t launch_expand_obs(const Tables& tab, int E, int S, void* obsx, cudaS
   return cudaGetLastError();
 }
 
+// ---- per-thread step shared by the per-iteration sweep and the persistent kernel ---------------------
+template <typename real>
+struct StepIn {
+  real T, iT, vs, qs, pval;
+  bool cold;
+  int which, pidx;
+  int S, n_pairs;
+  const typename M<real>::real4* obs_row;  // this lane's event row in shared memory
+  // float32 operands (station terms per pair: current / proposed; station 0: {-tc0, -ac0, -tc0', -ac0'})
+  const float4* cp;
+  const float4* cpP;
+  float4 c0;
+  // float64 operands
+  const typename M<real>::real4* s_sta;
+  const real* tc;
+  const real* ac;
+};
+
+// 1. one hypocentre coordinate proposed and judged on the event's own log-likelihood with the chain's
+//    temperature; 2. the chain's pending shared-parameter proposal evaluated for this event (-> Lp).
 template <typename real, bool TRACE>
-__global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsParams<real> p, const GibbsDecide dec,
-                                                               unsigned int* done_counter) {
-  typedef typename M<real>::real4 real4;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = p.S, J = p.J, E = p.E;
-  const int tile = blockIdx.x, e = tile * kTile + lane;
-  const int c = blockIdx.y * kCW + warp;
+__device__ __forceinline__ void gibbs_thread_step(const GibbsParams<real>& p, const int it, const StepIn<real>& in,
+                                                  const int c, const int e, const int ee, const bool ev_ok,
+                                                  const typename M<real>::real4 evc, const real mux, const real muy,
+                                                  real& x, real& y, real& z, real& Le, real& Lp, int& icmp, bool& acc,
+                                                  htm_step_trace* trace) {
   constexpr bool kF32 = sizeof(real) == 4;
-  const int n_pairs = S / 2;
-  // float32: rows of the expanded table (xrow float4 + 1 pad: odd stride -> conflict-free per-lane LDS.128);
-  // float64: rows of the raw table (S real4 + 1 pad) + the station table
-  const int row = kF32 ? p.xrow + 1 : S + 1;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // 16 bytes reserved
-  real4* s_obs = reinterpret_cast<real4*>(smem_raw + 16);     // [kTile][row]
-  real4* s_sta = s_obs + kTile * row;                          // f64: [S]
-  real* s_tc = reinterpret_cast<real*>(s_sta + S);             // f64: [kCW][S]
-  real* s_ac = s_tc + kCW * S;                                 // f64: [kCW][S]
-  // f32: station terms per pair, current and proposed, and those of station 0
-  float4* s_cp = reinterpret_cast<float4*>(s_obs + kTile * row);   // [kCW][n_pairs]
-  float4* s_cpP = s_cp + kCW * n_pairs;                            // [kCW][n_pairs]
-  float4* s_c0 = s_cpP + kCW * n_pairs;                            // [kCW] {-tc0, -ac0, -tc0', -ac0'}
-  const int n_ev = min(kTile, E - tile * kTile);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-    fence_proxy_async();
-  }
-  __syncthreads();
-  if (warp == 0) {
-    if constexpr (kF32) {
-      const uint32_t bytes = static_cast<uint32_t>(p.xrow * sizeof(float4));
-      if (lane == 0) mbar_expect_tx(bar, bytes * n_ev);
-      __syncwarp();
-      if (lane < n_ev)
-        tma_load_1d(s_obs + lane * row, p.obsx + static_cast<size_t>(tile * kTile + lane) * p.xrow, bytes, bar);
-    } else {
-      const uint32_t bytes = static_cast<uint32_t>(S * sizeof(real4));
-      if (lane == 0) mbar_expect_tx(bar, bytes * (n_ev + 1));
-      __syncwarp();
-      if (lane < n_ev) tma_load_1d(s_obs + lane * row, p.obs4 + static_cast<size_t>(tile * kTile + lane) * S, bytes, bar);
-      if (lane == 0) tma_load_1d(s_sta, p.sta4, bytes, bar);
-    }
-  }
-  // this chain's station terms -> shared memory
-  const bool chain_ok = c < J;
-  if (chain_ok) {
-    if constexpr (kF32) {
-      const double* gtc = p.g_tc + static_cast<size_t>(c) * S;
-      const double* gac = p.g_ac + static_cast<size_t>(c) * S;
-      const int wh = p.prop_which[c], pi = p.prop_idx[c];
-      const float pv = static_cast<float>(p.prop_xnew[c]);
-      for (int m = lane; m < n_pairs; m += 32) {
-        const int j0 = 1 + 2 * m, j1 = j0 + 1;
-        float4 cur = make_float4(-static_cast<float>(gtc[j0]), 0.f, -static_cast<float>(gac[j0]), 0.f);
-        if (j1 < S) {
-          cur.y = -static_cast<float>(gtc[j1]);
-          cur.w = -static_cast<float>(gac[j1]);
-        }
-        float4 prp = cur;
-        if (wh == 2 && pi == j0) prp.x = -pv;
-        if (wh == 2 && pi == j1) prp.y = -pv;
-        if (wh == 4 && pi == j0) prp.z = -pv;
-        if (wh == 4 && pi == j1) prp.w = -pv;
-        s_cp[warp * n_pairs + m] = cur;
-        s_cpP[warp * n_pairs + m] = prp;
-      }
-      if (lane == 0) {
-        float4 c0 = make_float4(-static_cast<float>(gtc[0]), -static_cast<float>(gac[0]), 0.f, 0.f);
-        c0.z = (wh == 2 && pi == 0) ? -pv : c0.x;
-        c0.w = (wh == 4 && pi == 0) ? -pv : c0.y;
-        s_c0[warp] = c0;
-      }
-    } else {
-      for (int j = lane; j < S; j += 32) {
-        s_tc[warp * S + j] = static_cast<real>(p.g_tc[static_cast<size_t>(c) * S + j]);
-        s_ac[warp * S + j] = static_cast<real>(p.g_ac[static_cast<size_t>(c) * S + j]);
-      }
-    }
-  }
-  __syncthreads();
-  mbar_wait(bar, 0);
-  if (chain_ok) {
-
-  const bool ev_ok = e < E;
-  const int ee = ev_ok ? e : E - 1;  // clamp: idle lanes clone the last event, never write
-  const size_t ci = static_cast<size_t>(c) * E + ee;
-  const double Td = p.g_T[c];
-  const real T = static_cast<real>(Td), iT = static_cast<real>(1) / T;
-  const bool cold = gibbs_is_cold<real>(Td);
-  const real vs = static_cast<real>(p.g_vs[c]), qs = static_cast<real>(p.g_qs[c]);
-  const Glob<real> g = make_glob<real>(vs, qs);
-  const int which = p.prop_which[c], pidx = p.prop_idx[c];
-  const real pval = static_cast<real>(p.prop_xnew[c]);
-  const real4 evc = p.evc4[ee];
-  const typename M<real>::real4* obs_row = s_obs + (ev_ok ? lane : n_ev - 1) * row;
-  const real* tc = s_tc + warp * S;
-  const real* ac = s_ac + warp * S;
-  real x = p.hx[ci], y = p.hy[ci], z = p.hz[ci];
-  real Le = p.a_prev[c] ? p.hLp[ci] : p.hLe[ci];  // lazy commit of the last shared-parameter acceptance
-
-  // ---- 1. hypocentre step (same rule as the factorised kernels) ----
+  const Glob<real> g = make_glob<real>(in.vs, in.qs);
   const uint32_t gid = (static_cast<uint32_t>(ee) + p.event_offset) * p.J_total + p.chain_offset + static_cast<uint32_t>(c);
-  const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(p.it), gid, PHX_STEP, 0u);
-  const int icmp = static_cast<int>(below(w.v[0], 3u));
+  const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(it), gid, PHX_STEP, 0u);
+  icmp = static_cast<int>(below(w.v[0], 3u));
   const real gs = M<real>::gauss(w.v[1], w.v[2]);
   const bool isz = icmp == 0;
-  const real mux = reinterpret_cast<const real*>(p.prior_xy)[2 * ee], muy = reinterpret_cast<const real*>(p.prior_xy)[2 * ee + 1];
   const real x_old = isz ? z : (icmp == 1 ? y : x);
   const real mu = isz ? p.prior_z : (icmp == 1 ? muy : mux);
   const real sigma = isz ? p.width_z : p.width_xy;
@@ -482,14 +480,14 @@ __global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsPar
   const real nx = icmp == 2 ? x_new : x, ny = icmp == 1 ? x_new : y, nz = isz ? x_new : z;
   real Lnew;
   if constexpr (kF32) {
-    Lnew = eval_pairs_f32(reinterpret_cast<const float4*>(obs_row), n_pairs, nx - mux, ny - muy, nz, g,
-                          s_cp + warp * n_pairs, s_c0[warp].x, s_c0[warp].y, evc);
+    Lnew = eval_pairs_f32(reinterpret_cast<const float4*>(in.obs_row), in.n_pairs, nx - mux, ny - muy, nz, g, in.cp,
+                          in.c0.x, in.c0.y, evc);
   } else {
-    Lnew = event_loglik_corr<real>(s_sta, obs_row, evc, S, nx, ny, nz, g, tc, ac, 0, -1, 0);
+    Lnew = event_loglik_corr<real>(in.s_sta, in.obs_row, evc, in.S, nx, ny, nz, g, in.tc, in.ac, 0, -1, 0);
   }
-  const real ratio = M<real>::div(Lnew - Le, T, iT) + lpr;
+  const real ratio = M<real>::div(Lnew - Le, in.T, in.iT) + lpr;
   const real ru = M<real>::u_co(w.v[3]);
-  const bool acc = ok && (ru > static_cast<real>(0)) && (M<real>::log(ru) <= ratio);
+  acc = ok && (ru > static_cast<real>(0)) && (M<real>::log(ru) <= ratio);
   if (acc) {
     x = nx;
     y = ny;
@@ -497,49 +495,168 @@ __global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsPar
     Le = Lnew;
   }
   if (TRACE) {
-    if (ev_ok && p.trace) {
+    if (ev_ok && trace) {
       htm_step_trace t;
       t.proposal_type = 5 + icmp;
       t.index = 3 * (e + 1) - icmp;
       t.prior_ok = ok ? 1 : 0;
       t.accepted = acc ? 1 : 0;
       t.log_likelihood = static_cast<double>(Le);
-      p.trace[static_cast<size_t>(e) * J + c] = t;
+      trace[static_cast<size_t>(e) * p.J + c] = t;
     }
   }
-  // ---- 2. the chain's pending shared-parameter proposal, evaluated for this event ----
-  real Lp = Le;
-  if (which != 0) {
-    const Glob<real> gp = make_glob<real>(which == 1 ? pval : vs, which == 3 ? pval : qs);
+  Lp = Le;
+  if (in.which != 0) {
+    const Glob<real> gp = make_glob<real>(in.which == 1 ? in.pval : in.vs, in.which == 3 ? in.pval : in.qs);
     if constexpr (kF32) {
-      Lp = eval_pairs_f32(reinterpret_cast<const float4*>(obs_row), n_pairs, x - mux, y - muy, z, gp,
-                          s_cpP + warp * n_pairs, s_c0[warp].z, s_c0[warp].w, evc);
+      Lp = eval_pairs_f32(reinterpret_cast<const float4*>(in.obs_row), in.n_pairs, x - mux, y - muy, z, gp, in.cpP,
+                          in.c0.z, in.c0.w, evc);
     } else {
-      Lp = event_loglik_corr<real>(s_sta, obs_row, evc, S, x, y, z, gp, tc, ac, which,
-                                   (which == 2 || which == 4) ? pidx : -1, pval);
+      Lp = event_loglik_corr<real>(in.s_sta, in.obs_row, evc, in.S, x, y, z, gp, in.tc, in.ac, in.which,
+                                   (in.which == 2 || in.which == 4) ? in.pidx : -1, in.pval);
     }
   }
-  if (ev_ok) {
-    p.hx[ci] = x;
-    p.hy[ci] = y;
-    p.hz[ci] = z;
-    p.hLe[ci] = Le;
-    p.hLp[ci] = Lp;
-    if (p.rec_slot >= 0 && p.slot_of[c] >= 0 && p.hypo_rec) {
-      real4 rec;
-      rec.x = x;
-      rec.y = y;
-      rec.z = z;
-      rec.w = Le;
-      p.hypo_rec[(static_cast<size_t>(p.rec_slot) * p.n_cool_total + p.slot_of[c]) * E + e] = rec;
+}
+
+// shared-memory carve-up common to both kernels
+template <typename real>
+struct SweepSm {
+  typedef typename M<real>::real4 real4;
+  uint64_t* bar;
+  real4* obs;   // [kTile][row]
+  real4* sta;   // f64: [S]
+  real* tc;     // f64: [kCW][S]
+  real* ac;     // f64: [kCW][S]
+  float4* cp;   // f32: [kCW][n_pairs]
+  float4* cpP;  // f32: [kCW][n_pairs]
+  float4* c0;   // f32: [kCW]
+  int row;
+  unsigned char* end;  // first byte after the sweep's own shared memory (16-byte aligned)
+};
+template <typename real>
+__device__ __forceinline__ SweepSm<real> carve_sweep_sm(unsigned char* base, int S, int xrow) {
+  typedef typename M<real>::real4 real4;
+  constexpr bool kF32 = sizeof(real) == 4;
+  SweepSm<real> m;
+  const int n_pairs = S / 2;
+  m.row = kF32 ? xrow + 1 : S + 1;
+  m.bar = reinterpret_cast<uint64_t*>(base);
+  m.obs = reinterpret_cast<real4*>(base + 16);
+  m.sta = m.obs + kTile * m.row;
+  m.tc = reinterpret_cast<real*>(m.sta + S);
+  m.ac = m.tc + kCW * S;
+  m.cp = reinterpret_cast<float4*>(m.obs + kTile * m.row);
+  m.cpP = m.cp + kCW * n_pairs;
+  m.c0 = m.cpP + kCW * n_pairs;
+  unsigned char* e = kF32 ? reinterpret_cast<unsigned char*>(m.c0 + kCW) : reinterpret_cast<unsigned char*>(m.ac + kCW * S);
+  m.end = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(e) + 15) & ~static_cast<uintptr_t>(15));
+  return m;
+}
+template <typename real>
+static size_t sweep_smem(int S) {
+  typedef typename M<real>::real4 real4;
+  if (sizeof(real) == 4) {
+    const int n_pairs = S / 2, xrow = 2 + 4 * n_pairs;
+    return 16 + static_cast<size_t>(kTile) * (xrow + 1) * sizeof(float4) + (2 * kCW * n_pairs + kCW) * sizeof(float4) + 16;
+  }
+  return 16 + static_cast<size_t>(kTile) * (S + 1) * sizeof(real4) + S * sizeof(real4) + 2 * kCW * S * sizeof(real) + 16;
+}
+
+// TMA-stage the tile's observation rows (and, float64, the station table); caller syncs and waits
+template <typename real>
+__device__ __forceinline__ void stage_tile(const GibbsParams<real>& p, const SweepSm<real>& m, int tile, int n_ev) {
+  typedef typename M<real>::real4 real4;
+  constexpr bool kF32 = sizeof(real) == 4;
+  const int lane = threadIdx.x & 31;
+  if (kF32) {
+    const uint32_t bytes = static_cast<uint32_t>(p.xrow * sizeof(float4));
+    if (lane == 0) mbar_expect_tx(m.bar, bytes * n_ev);
+    __syncwarp();
+    if (lane < n_ev)
+      tma_load_1d(m.obs + lane * m.row, p.obsx + static_cast<size_t>(tile * kTile + lane) * p.xrow, bytes, m.bar);
+  } else {
+    const uint32_t bytes = static_cast<uint32_t>(p.S * sizeof(real4));
+    if (lane == 0) mbar_expect_tx(m.bar, bytes * (n_ev + 1));
+    __syncwarp();
+    if (lane < n_ev)
+      tma_load_1d(m.obs + lane * m.row, p.obs4 + static_cast<size_t>(tile * kTile + lane) * p.S, bytes, m.bar);
+    if (lane == 0) tma_load_1d(m.sta, p.sta4, bytes, m.bar);
+  }
+}
+
+// the warp's chain operands in shared memory, from (tc, ac) arrays of any addressable memory
+template <typename real>
+__device__ __forceinline__ void stage_chain_terms(const SweepSm<real>& m, int warp, int S, const double* gtc,
+                                                  const double* gac, int wh, int pi, double pvd) {
+  constexpr bool kF32 = sizeof(real) == 4;
+  const int lane = threadIdx.x & 31, n_pairs = S / 2;
+  if (kF32) {
+    const float pv = static_cast<float>(pvd);
+    for (int mm = lane; mm < n_pairs; mm += 32) {
+      const int j0 = 1 + 2 * mm, j1 = j0 + 1;
+      float4 cur = make_float4(-static_cast<float>(gtc[j0]), 0.f, -static_cast<float>(gac[j0]), 0.f);
+      if (j1 < S) {
+        cur.y = -static_cast<float>(gtc[j1]);
+        cur.w = -static_cast<float>(gac[j1]);
+      }
+      float4 prp = cur;
+      if (wh == 2 && pi == j0) prp.x = -pv;
+      if (wh == 2 && pi == j1) prp.y = -pv;
+      if (wh == 4 && pi == j0) prp.z = -pv;
+      if (wh == 4 && pi == j1) prp.w = -pv;
+      m.cp[warp * n_pairs + mm] = cur;
+      m.cpP[warp * n_pairs + mm] = prp;
+    }
+    if (lane == 0) {
+      float4 c0 = make_float4(-static_cast<float>(gtc[0]), -static_cast<float>(gac[0]), 0.f, 0.f);
+      c0.z = (wh == 2 && pi == 0) ? -pv : c0.x;
+      c0.w = (wh == 4 && pi == 0) ? -pv : c0.y;
+      m.c0[warp] = c0;
+    }
+  } else {
+    for (int j = lane; j < S; j += 32) {
+      m.tc[warp * S + j] = static_cast<real>(gtc[j]);
+      m.ac[warp * S + j] = static_cast<real>(gac[j]);
     }
   }
-  // ---- partial sums over the tile (float64, butterfly = fixed order) and counters ----
+}
+
+template <typename real>
+__device__ __forceinline__ StepIn<real> make_step_in(const SweepSm<real>& m, int warp, int S, double Td, double vs,
+                                                     double qs, int which, int pidx, double pval,
+                                                     const typename M<real>::real4* obs_row) {
+  StepIn<real> in;
+  in.T = static_cast<real>(Td);
+  in.iT = static_cast<real>(1) / in.T;
+  in.cold = gibbs_is_cold<real>(Td);
+  in.vs = static_cast<real>(vs);
+  in.qs = static_cast<real>(qs);
+  in.which = which;
+  in.pidx = pidx;
+  in.pval = static_cast<real>(pval);
+  in.S = S;
+  in.n_pairs = S / 2;
+  in.obs_row = obs_row;
+  in.cp = m.cp + warp * in.n_pairs;
+  in.cpP = m.cpP + warp * in.n_pairs;
+  in.c0 = sizeof(real) == 4 ? m.c0[warp] : make_float4(0.f, 0.f, 0.f, 0.f);
+  in.s_sta = m.sta;
+  in.tc = m.tc + warp * S;
+  in.ac = m.ac + warp * S;
+  return in;
+}
+
+// per-tile partial sums (float64, butterfly = fixed order) and cold-chain counters
+template <typename real>
+__device__ __forceinline__ void tile_sums_and_counts(const GibbsParams<real>& p, double* part_cur, double* part_prop,
+                                                     int c, int tile, bool ev_ok, bool cold, real Le, real Lp, int icmp,
+                                                     bool acc) {
+  const int lane = threadIdx.x & 31;
   const double s_cur = warp_sum<double>(ev_ok ? static_cast<double>(Le) : 0.0);
   const double s_prop = warp_sum<double>(ev_ok ? static_cast<double>(Lp) : 0.0);
   if (lane == 0) {
-    p.part_cur[static_cast<size_t>(c) * p.n_tiles + tile] = s_cur;
-    p.part_prop[static_cast<size_t>(c) * p.n_tiles + tile] = s_prop;
+    part_cur[static_cast<size_t>(c) * p.n_tiles + tile] = s_cur;
+    part_prop[static_cast<size_t>(c) * p.n_tiles + tile] = s_prop;
   }
   if (cold) {
 #pragma unroll
@@ -552,7 +669,64 @@ __global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsPar
       }
     }
   }
-  }  // chain_ok
+}
+
+// ---- one iteration per launch: sweep + (last CTA) decide --------------------------------------------------
+template <typename real, bool TRACE>
+__global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsParams<real> p, const GibbsDecide dec,
+                                                                  unsigned int* done_counter) {
+  typedef typename M<real>::real4 real4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, J = p.J, E = p.E;
+  const int tile = blockIdx.x, e = tile * kTile + lane;
+  const int c = blockIdx.y * kCW + warp;
+  const SweepSm<real> m = carve_sweep_sm<real>(smem_raw, S, p.xrow);
+  const int n_ev = min(kTile, E - tile * kTile);
+  if (threadIdx.x == 0) {
+    mbar_init(m.bar, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (warp == 0) stage_tile<real>(p, m, tile, n_ev);
+  const bool chain_ok = c < J;
+  if (chain_ok)
+    stage_chain_terms<real>(m, warp, S, p.g_tc + static_cast<size_t>(c) * S, p.g_ac + static_cast<size_t>(c) * S,
+                            p.prop_which[c], p.prop_idx[c], p.prop_xnew[c]);
+  __syncthreads();
+  mbar_wait(m.bar, 0);
+  if (chain_ok) {
+    const bool ev_ok = e < E;
+    const int ee = ev_ok ? e : E - 1;  // idle lanes clone the last event and never write
+    const size_t ci = static_cast<size_t>(c) * E + ee;
+    const StepIn<real> in = make_step_in<real>(m, warp, S, p.g_T[c], p.g_vs[c], p.g_qs[c], p.prop_which[c], p.prop_idx[c],
+                                               p.prop_xnew[c], m.obs + (ev_ok ? lane : n_ev - 1) * m.row);
+    const real4 evc = p.evc4[ee];
+    const real mux = reinterpret_cast<const real*>(p.prior_xy)[2 * ee], muy = reinterpret_cast<const real*>(p.prior_xy)[2 * ee + 1];
+    real x = p.hx[ci], y = p.hy[ci], z = p.hz[ci];
+    real Le = p.a_prev[c] ? p.hLp[ci] : p.hLe[ci];  // lazy commit of the last shared-parameter acceptance
+    real Lp;
+    int icmp;
+    bool acc;
+    gibbs_thread_step<real, TRACE>(p, p.it, in, c, e, ee, ev_ok, evc, mux, muy, x, y, z, Le, Lp, icmp, acc, p.trace);
+    if (ev_ok) {
+      p.hx[ci] = x;
+      p.hy[ci] = y;
+      p.hz[ci] = z;
+      p.hLe[ci] = Le;
+      p.hLp[ci] = Lp;
+      if (p.rec_slot >= 0 && p.slot_of[c] >= 0 && p.hypo_rec) {
+        real4 rec;
+        rec.x = x;
+        rec.y = y;
+        rec.z = z;
+        rec.w = Le;
+        p.hypo_rec[(static_cast<size_t>(p.rec_slot) * p.n_cool_total + p.slot_of[c]) * E + e] = rec;
+      }
+    }
+    tile_sums_and_counts<real>(p, p.part_cur, p.part_prop, c, tile, ev_ok, in.cold, Le, Lp, icmp, acc);
+  }
 
   // ---- the last CTA to finish judges the shared-parameter proposals (fixed-order sums: deterministic) ----
   __shared__ int s_last;
@@ -565,9 +739,96 @@ __global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsPar
   __syncthreads();
   if (s_last) {
     __threadfence();
-    gibbs_decide(dec, reinterpret_cast<double*>(smem_raw));
+    gibbs_decide(dec, smem_raw);
     if (threadIdx.x == 0) *done_counter = 0u;
   }
+}
+
+// ---- persistent cooperative kernel: all iterations in one launch -------------------------------------------
+// Every (chain, event) keeps its state in registers, the tile's rows stay in shared memory, the chain-level
+// state of ALL chains lives in every CTA's shared memory.  Per iteration: step -> partial sums to global ->
+// ONE grid barrier -> every CTA adds the partials in the same fixed order and takes the same decisions
+// (CTA (0,0) alone writes counters, records, traces).  Bit-identical to the per-iteration path.
+template <typename real, bool TRACE>
+__global__ void __launch_bounds__(kCW * 32, 2) gibbs_persist_kernel(const GibbsParams<real> p, const GibbsDecide d,
+                                                                    const int iter_first, const int iter_last,
+                                                                    const int rec_origin, const int rec_cap,
+                                                                    htm_step_trace* trace_base, htm_swap_trace* swap_base,
+                                                                    double* part /* [2][2][J][n_tiles] */) {
+  typedef typename M<real>::real4 real4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::grid_group grid = cg::this_grid();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, J = p.J, E = p.E;
+  const int tile = blockIdx.x, e = tile * kTile + lane;
+  const int c = blockIdx.y * kCW + warp;
+  const bool writer = blockIdx.x == 0 && blockIdx.y == 0;
+  const SweepSm<real> m = carve_sweep_sm<real>(smem_raw, S, p.xrow);
+  const ChainSm cs = carve_chain_sm(m.end, J, S);
+  const int n_ev = min(kTile, E - tile * kTile);
+  if (threadIdx.x == 0) {
+    mbar_init(m.bar, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (warp == 0) stage_tile<real>(p, m, tile, n_ev);
+  chain_load(d, cs);
+  __syncthreads();
+  mbar_wait(m.bar, 0);
+
+  const bool chain_ok = c < J;
+  const bool ev_ok = e < E;
+  const int ee = ev_ok ? e : E - 1;
+  const int cc = chain_ok ? c : J - 1;
+  const size_t ci = static_cast<size_t>(cc) * E + ee;
+  const real4 evc = p.evc4[ee];
+  const real mux = reinterpret_cast<const real*>(p.prior_xy)[2 * ee], muy = reinterpret_cast<const real*>(p.prior_xy)[2 * ee + 1];
+  const real4* obs_row = m.obs + (ev_ok ? lane : n_ev - 1) * m.row;
+  real x = p.hx[ci], y = p.hy[ci], z = p.hz[ci], Le = p.hLe[ci], Lp = p.hLp[ci];
+  const size_t per_it = static_cast<size_t>(E + 1) * J, psz = static_cast<size_t>(J) * p.n_tiles;
+
+  for (int it = iter_first; it <= iter_last; ++it) {
+    const int buf = it & 1;
+    double* part_cur = part + static_cast<size_t>(buf) * 2 * psz;
+    double* part_prop = part_cur + psz;
+    const bool rec = p.n_interval > 1 && (it % p.n_interval) == 1;
+    int rec_slot = rec ? (it - 1) / p.n_interval - rec_origin : -1;
+    if (rec_slot >= rec_cap) rec_slot = -1;
+    if (chain_ok) {
+      stage_chain_terms<real>(m, warp, S, cs.tc + static_cast<size_t>(c) * S, cs.ac + static_cast<size_t>(c) * S,
+                              cs.which[c], cs.idx[c], cs.xnew[c]);
+      __syncwarp();
+      const StepIn<real> in = make_step_in<real>(m, warp, S, cs.T[c], cs.vs[c], cs.qs[c], cs.which[c], cs.idx[c],
+                                                 cs.xnew[c], obs_row);
+      Le = cs.aprev[c] ? Lp : Le;  // lazy commit of the last shared-parameter acceptance
+      int icmp;
+      bool acc;
+      gibbs_thread_step<real, TRACE>(p, it, in, c, e, ee, ev_ok, evc, mux, muy, x, y, z, Le, Lp, icmp, acc,
+                                     trace_base ? trace_base + static_cast<size_t>(it - iter_first) * per_it : nullptr);
+      if (ev_ok && rec_slot >= 0 && cs.slot[c] >= 0 && p.hypo_rec) {
+        real4 r4;
+        r4.x = x;
+        r4.y = y;
+        r4.z = z;
+        r4.w = Le;
+        p.hypo_rec[(static_cast<size_t>(rec_slot) * p.n_cool_total + cs.slot[c]) * E + e] = r4;
+      }
+      tile_sums_and_counts<real>(p, part_cur, part_prop, c, tile, ev_ok, in.cold, Le, Lp, icmp, acc);
+    }
+    grid.sync();
+    decide_core(d, cs, it, it + 1, part_cur, part_prop, rec_slot,
+                trace_base ? trace_base + static_cast<size_t>(it - iter_first) * per_it + static_cast<size_t>(E) * J : nullptr,
+                swap_base ? swap_base + (it - iter_first) : nullptr, writer);
+  }
+  if (chain_ok && ev_ok) {
+    p.hx[ci] = x;
+    p.hy[ci] = y;
+    p.hz[ci] = z;
+    p.hLe[ci] = Le;
+    p.hLp[ci] = Lp;
+  }
+  if (writer) chain_store(d, cs);
 }
 
 // ---- chain set-up ---------------------------------------------------------------------------------
@@ -681,8 +942,8 @@ static GibbsParams<real> make_gibbs_params(const GibbsLaunch& a) {
   p.prop_lpr = a.prop_lpr;
   p.a_prev = a.a_prev;
   p.slot_of = a.slot_of;
-  p.part_cur = a.part_cur;
-  p.part_prop = a.part_prop;
+  p.part_cur = a.part_cur;  // one allocation [2][2][J][n_tiles]; the per-iteration path uses buffer 0
+  p.part_prop = a.part_cur + static_cast<size_t>(a.J) * ((a.E + kTile - 1) / kTile);
   p.E = a.E;
   p.S = a.S;
   p.J = a.J;
@@ -724,7 +985,7 @@ static GibbsDecide make_decide(const GibbsLaunch& a) {
   d.a_prev = a.a_prev;
   d.slot_of = a.slot_of;
   d.part_cur = a.part_cur;
-  d.part_prop = a.part_prop;
+  d.part_prop = a.part_cur + static_cast<size_t>(a.J) * ((a.E + kTile - 1) / kTile);
   d.S = a.S;
   d.J = a.J;
   d.K = a.K;
@@ -756,40 +1017,65 @@ static GibbsDecide make_decide(const GibbsLaunch& a) {
   return d;
 }
 
-template <typename real>
-static size_t sweep_smem(int S) {
-  typedef typename M<real>::real4 real4;
-  if (sizeof(real) == 4) {
-    const int n_pairs = S / 2, xrow = 2 + 4 * n_pairs;
-    return 16 + static_cast<size_t>(kTile) * (xrow + 1) * sizeof(float4) + (2 * kCW * n_pairs + kCW) * sizeof(float4);
-  }
-  return static_cast<size_t>(kTile) * (S + 1) * sizeof(real4) + S * sizeof(real4) + 2 * kCW * S * sizeof(real) + 32;
+// HTM_GIBBS_PERSIST=0 forces one launch per iteration, =1 insists on the persistent kernel (tests)
+static int persist_env() {
+  const char* v = std::getenv("HTM_GIBBS_PERSIST");
+  return v ? std::atoi(v) : -1;
 }
 
-template <typename real>
-static cudaError_t launch_gibbs_t(const GibbsLaunch& a, cudaStream_t stream, int* n_launches) {
+template <typename real, bool TRACE>
+static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, int* n_launches) {
   GibbsParams<real> p = make_gibbs_params<real>(a);
   GibbsDecide d = make_decide(a);
-  size_t smem = sweep_smem<real>(a.S);
-  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // reported as "n_sta too large" by the caller
-  if (smem < 4 * static_cast<size_t>(a.J) * sizeof(double)) smem = 4 * static_cast<size_t>(a.J) * sizeof(double);
-  cudaError_t err;
-  const bool tracing = a.trace || a.swaps;
-  if (tracing)
-    err = cudaFuncSetAttribute(gibbs_sweep_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  else
-    err = cudaFuncSetAttribute(gibbs_sweep_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
+  const size_t sm_sweep = sweep_smem<real>(a.S), sm_chain = chain_sm_bytes(a.J, a.S);
+  if (sm_sweep > 200 * 1024 || sm_chain > 200 * 1024) return cudaErrorInvalidConfiguration;
+  const size_t smem_iter = sm_sweep > sm_chain ? sm_sweep : sm_chain;  // the last CTA reuses its smem for the decide
+  const size_t smem_pers = sm_sweep + sm_chain;
   const dim3 grid(p.n_tiles, (a.J + kCW - 1) / kCW);
-  const size_t dsm = 4 * static_cast<size_t>(a.J) * sizeof(double);
+  cudaError_t err = cudaFuncSetAttribute(gibbs_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(sm_chain));
+  if (err != cudaSuccess) return err;
   int nl = 0;
   // prepare: cold slots + the proposal of the first iteration (a pure function of state and iteration)
   d.it = 0;
   d.it_next = a.iter_first;
-  gibbs_decide_kernel<<<1, 256, dsm, stream>>>(d);
+  gibbs_decide_kernel<<<1, 256, sm_chain, stream>>>(d);
   ++nl;
+
+  // ---- persistent cooperative kernel when every CTA can be resident at once ----
+  const int want = persist_env();
+  bool persistent = false;
+  if (want != 0 && smem_pers <= 200 * 1024) {
+    err = cudaFuncSetAttribute(gibbs_persist_kernel<real, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem_pers));
+    if (err != cudaSuccess) return err;
+    int per_sm = 0, dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_persist_kernel<real, TRACE>, kCW * 32, smem_pers);
+    if (err != cudaSuccess) return err;
+    persistent = static_cast<long>(per_sm) * n_sm >= static_cast<long>(grid.x) * grid.y;
+  }
+  if (want == 1 && !persistent) return cudaErrorCooperativeLaunchTooLarge;
+  if (persistent) {
+    int iter_first = a.iter_first, iter_last = a.iter_last, rec_origin = a.rec_origin, rec_cap = a.rec_cap;
+    htm_step_trace* tr = a.trace;
+    htm_swap_trace* sw = a.swaps;
+    double* part = a.part_cur;  // [2][2][J][n_tiles]: part_cur and part_prop are one allocation
+    void* args[] = {&p, &d, &iter_first, &iter_last, &rec_origin, &rec_cap, &tr, &sw, &part};
+    err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gibbs_persist_kernel<real, TRACE>), grid, dim3(kCW * 32),
+                                      args, smem_pers, stream);
+    if (err != cudaSuccess) return err;
+    ++nl;
+    if (n_launches) *n_launches = nl;
+    return cudaGetLastError();
+  }
+
+  // ---- one launch per iteration: the sweep, and in its last CTA the chain-level decide step ----
+  err = cudaFuncSetAttribute(gibbs_sweep_kernel<real, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem_iter));
+  if (err != cudaSuccess) return err;
   const size_t per_it = static_cast<size_t>(a.E + 1) * a.J;
-  // one launch per iteration: the sweep, and in its last CTA the chain-level decide step
   for (int it = a.iter_first; it <= a.iter_last; ++it) {
     const bool rec = a.n_interval > 1 && (it % a.n_interval) == 1;
     const int slot = rec ? (it - 1) / a.n_interval - a.rec_origin : -1;
@@ -801,14 +1087,17 @@ static cudaError_t launch_gibbs_t(const GibbsLaunch& a, cudaStream_t stream, int
     d.rec_slot = p.rec_slot;
     d.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it + static_cast<size_t>(a.E) * a.J : nullptr;
     d.swap = a.swaps ? a.swaps + (it - a.iter_first) : nullptr;
-    if (tracing)
-      gibbs_sweep_kernel<real, true><<<grid, kCW * 32, smem, stream>>>(p, d, a.done_counter);
-    else
-      gibbs_sweep_kernel<real, false><<<grid, kCW * 32, smem, stream>>>(p, d, a.done_counter);
+    gibbs_sweep_kernel<real, TRACE><<<grid, kCW * 32, smem_iter, stream>>>(p, d, a.done_counter);
     ++nl;
   }
   if (n_launches) *n_launches = nl;
   return cudaGetLastError();
+}
+
+template <typename real>
+static cudaError_t launch_gibbs_t(const GibbsLaunch& a, cudaStream_t stream, int* n_launches) {
+  return (a.trace || a.swaps) ? launch_gibbs_tt<real, true>(a, stream, n_launches)
+                              : launch_gibbs_tt<real, false>(a, stream, n_launches);
 }
 
 cudaError_t launch_gibbs(const GibbsLaunch& a, cudaStream_t stream, int* n_launches) {

@@ -442,9 +442,16 @@ def test_nccl_gather_of_histograms_and_counts():
 
 
 # ---- mode C blocked Gibbs (shared parameters solved) ---------------------------------------------------------
+@pytest.fixture(params=[0, 1], ids=["launch-per-iteration", "persistent"])
+def gibbs_path(request, monkeypatch):
+    # HTM_GIBBS_PERSIST: 0 = one launch per iteration, 1 = the persistent cooperative kernel
+    monkeypatch.setenv("HTM_GIBBS_PERSIST", str(request.param))
+    return request.param
+
+
 @pytest.mark.parametrize("E,S,R,K,solve", [(5, 9, 2, 3, (1, 1, 1, 1)), (40, 20, 3, 4, (1, 0, 1, 0)), (3, 33, 1, 2, (0, 1, 0, 1)),
                                             (70, 12, 5, 2, (1, 1, 1, 1)), (4, 8, 2, 3, (0, 0, 0, 0))])
-def test_blocked_gibbs_float64_step_exact(E, S, R, K, solve):
+def test_blocked_gibbs_float64_step_exact(gibbs_path, E, S, R, K, solve):
     syn = H.Synthetic(E, S, 40 + E)
     cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=60, n_burn=12, n_interval=6,
                            mode=H.MODE_BLOCKED_GIBBS, precision=64, max_samples=16, solve_vs=solve[0],
@@ -480,6 +487,32 @@ def test_blocked_gibbs_float64_step_exact(E, S, R, K, solve):
     fo = o.get_chain_state(0, 0)
     assert np.allclose(fin["hypo"], fo["hypo"], rtol=1e-10, atol=1e-10) and abs(fin["vs"] - fo["vs"]) < 1e-12
     assert rel(fin["log_likelihood"], fo["log_likelihood"]) < 1e-9
+
+
+def test_blocked_gibbs_persistent_and_per_iteration_paths_are_bit_identical(monkeypatch):
+    syn = H.Synthetic(300, 20, 8)
+    cfg = H.default_config(n_sta=20, n_events=300, n_procs=3, n_chains=4, n_iter=120, n_burn=20, n_interval=10,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=16)
+    res = []
+    for persist in (0, 1):
+        monkeypatch.setenv("HTM_GIBBS_PERSIST", str(persist))
+        with H.HypoTremorB200(cfg) as g:
+            g.load(syn)
+            g.init_chains()
+            g.run(1, 70)
+            g.run(71, 120)
+            _, nl, _ = g.last_run_stats()
+            assert nl == (2 if persist else 51)
+            res.append(([g.get_chain_state(r, k) for r in range(3) for k in range(4)], g.get_counts(),
+                        [g.fetch_samples(r) for r in range(3)], [g.fetch_likelihood(r) for r in range(3)]))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert np.array_equal(a["hypo"], b["hypo"]) and a["vs"] == b["vs"] and a["qs"] == b["qs"]
+        assert np.array_equal(a["t_corr"], b["t_corr"]) and a["temp"] == b["temp"] and a["log_likelihood"] == b["log_likelihood"]
+    assert np.array_equal(res[0][1][0], res[1][1][0]) and np.array_equal(res[0][1][1], res[1][1][1])
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a["iter"], b["iter"]) and np.array_equal(a["hypo"], b["hypo"]) and np.array_equal(a["vs"], b["vs"])
+    for a, b in zip(res[0][3], res[1][3]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
 def test_blocked_gibbs_chunked_runs_equal_one_run():
