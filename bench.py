@@ -177,7 +177,8 @@ def run_reference(a):
     rates = []
     sample, cores = "", 1
     for i in range(a.warmup + a.steps):
-        r, cores, sample = cpu_reference_rate(a, per_step)
+        # same config as the B200 arm at this N: weak scaling, a.events per GPU
+        r, cores, sample = cpu_reference_rate(a, per_step, n_events=a.events * max(1, a.gpus))
         if i >= a.warmup:
             rates.append(r)
     v = float(np.mean(rates))

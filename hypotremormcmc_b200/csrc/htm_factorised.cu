@@ -167,11 +167,11 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
   // float32: 2 staged + 2 expanded float4 per station (pairs of stations, 4 float4 per pair);
   // float64 reads the staged tables directly
   constexpr bool kF32 = sizeof(real) == 4;
-  constexpr int kF4PerSta = kF32 ? 4 : 2;
-  real4* s_sta = reinterpret_cast<real4*>(smem_raw) + static_cast<size_t>(warp) * kF4PerSta * S;
+  constexpr int kF4PerSta = kF32 ? 4 : 2;  // (+2 float4 per warp for an odd station count, see launcher)
+  const size_t warp_f4 = static_cast<size_t>(kF4PerSta) * S + (kF32 ? 2 : 0);
+  real4* s_sta = reinterpret_cast<real4*>(smem_raw) + static_cast<size_t>(warp) * warp_f4;
   real4* s_obs = s_sta + S;
-  uint64_t* bar =
-      reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(wpb) * kF4PerSta * S * sizeof(real4)) + warp;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(wpb) * warp_f4 * sizeof(real4)) + warp;
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
     float4* s_x = reinterpret_cast<float4*>(s_obs + S);
     const float4* st = reinterpret_cast<const float4*>(s_sta);
     const float4* ob = reinterpret_cast<const float4*>(s_obs);
-    for (int m = lane; m < n_station_pairs(S); m += 32) {
-      const int j0 = 1 + 2 * m, j1 = j0 + 1;
+    for (int m = lane; m < (S + 1) / 2; m += 32) {
+      const int j0 = 2 * m, j1 = j0 + 1;
       const StaRecF a = expand_station(st[j0], ob[j0], pxy.x, pxy.y);
       StaRecF b = a;
       if (j1 < S) {
@@ -243,6 +243,25 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
       store_station_pair(s_x + 4 * m, a, b);
     }
     __syncwarp();
+  }
+  // float32: each chain carries the (negated) weighted mean residuals of its accepted state as the shift
+  float nct[NSLOT], nca[NSLOT];
+  if constexpr (kF32) {
+    const float4* s_x = reinterpret_cast<const float4*>(s_obs + S);
+    float hx[NSLOT], hy[NSLOT], hz[NSLOT], z0[NSLOT], S1t[NSLOT], S1a[NSLOT], S2[NSLOT];
+#pragma unroll
+    for (int q = 0; q < NSLOT; ++q) {
+      hx[q] = x[q] - pxy.x;
+      hy[q] = y[q] - pxy.y;
+      hz[q] = z[q];
+      z0[q] = 0.f;
+    }
+    forward_pairs<NSLOT>(s_x, (S + 1) / 2, hx, hy, hz, g, z0, z0, S1t, S1a, S2);
+#pragma unroll
+    for (int q = 0; q < NSLOT; ++q) {
+      nct[q] = -S1t[q] * evc.y;
+      nca[q] = -S1a[q] * evc.z;
+    }
   }
 
   for (int it = p.iter_first; it <= p.iter_last; ++it) {
@@ -281,8 +300,6 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
     real S1t[NSLOT], S1a[NSLOT], S2[NSLOT];
     if constexpr (kF32) {
       const float4* s_x = reinterpret_cast<const float4*>(s_obs + S);
-      const float4 st0 = reinterpret_cast<const float4*>(s_sta)[0], ob0 = reinterpret_cast<const float4*>(s_obs)[0];
-      const StaRecF r0 = expand_station(st0, ob0, pxy.x, pxy.y);
       float hx[NSLOT], hy[NSLOT], hz[NSLOT];
 #pragma unroll
       for (int q = 0; q < NSLOT; ++q) {
@@ -290,17 +307,17 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
         hy[q] = ny[q] - pxy.y;
         hz[q] = nz[q];
       }
-      forward_pairs<NSLOT>(s_x, n_station_pairs(S), r0.A, ob0.x, ob0.z, hx, hy, hz, g, S1t, S1a, S2);
+      forward_pairs<NSLOT>(s_x, (S + 1) / 2, hx, hy, hz, g, nct, nca, S1t, S1a, S2);
     } else {
-      real nct[NSLOT], nca[NSLOT];
+      real nct64[NSLOT], nca64[NSLOT];
       const real4 st = s_sta[0];
       const real4 ob = s_obs[0];
 #pragma unroll
       for (int q = 0; q < NSLOT; ++q) {
         real ct, ca;
         station_resid(nx[q], ny[q], nz[q], g, st, ob, static_cast<real>(0), static_cast<real>(0), ct, ca);
-        nct[q] = -ct;
-        nca[q] = -ca;
+        nct64[q] = -ct;
+        nca64[q] = -ca;
         S1t[q] = 0;
         S1a[q] = 0;
         S2[q] = 0;
@@ -311,7 +328,7 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
         const real4 obj = s_obs[j];
 #pragma unroll
         for (int q = 0; q < NSLOT; ++q)
-          station_accum(nx[q], ny[q], nz[q], g, nct[q], nca[q], stj, obj, S1t[q], S1a[q], S2[q]);
+          station_accum(nx[q], ny[q], nz[q], g, nct64[q], nca64[q], stj, obj, S1t[q], S1a[q], S2[q]);
       }
     }
     const bool rec_now = rec_left == 0;
@@ -336,6 +353,10 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
       z[q] = acc ? nz[q] : z[q];
       L[q] = acc ? Lnew : L[q];
       lgz[q] = acc ? nlgz[q] : lgz[q];
+      if constexpr (kF32) {  // new shift = weighted mean residual of the accepted state
+        nct[q] = acc ? fmaf(-static_cast<float>(S1t[q]), static_cast<float>(evc.y), nct[q]) : nct[q];
+        nca[q] = acc ? fmaf(-static_cast<float>(S1a[q]), static_cast<float>(evc.z), nca[q]) : nca[q];
+      }
       if (TRACE) {
         if (valid[q] && p.trace) {
           htm_step_trace t;
@@ -725,7 +746,7 @@ static cudaError_t launch_lane(const FactLaunch& a, cudaStream_t stream) {
   // warps are independent, so the CTA size only sets how evenly they spread over the SMs:
   // 1-warp CTAs while everything is resident at once (<= 32 CTAs/SM), else 2 or 4
   int wpb = n_warps <= 148L * 32 ? 1 : (n_warps <= 148L * 64 ? 2 : 4);
-  const size_t per_warp = (sizeof(real) == 4 ? 4 : 2) * a.S * sizeof(real4) + sizeof(uint64_t);
+  const size_t per_warp = ((sizeof(real) == 4 ? 4 : 2) * a.S + (sizeof(real) == 4 ? 2 : 0)) * sizeof(real4) + sizeof(uint64_t);
   while (wpb > 1 && wpb * per_warp > 200 * 1024) wpb >>= 1;  // very large station counts: fewer warps per CTA
   const unsigned grid = static_cast<unsigned>((n_warps + wpb - 1) / wpb);
   const size_t smem = static_cast<size_t>(wpb) * per_warp;
@@ -790,7 +811,7 @@ static cudaError_t launch_factorised_t(const FactLaunch& a, cudaStream_t stream,
     *why = "warp-per-chain kernel supports n_sta <= 128; use the lane-per-chain kernel";
     return cudaErrorInvalidValue;
   }
-  const size_t smem_need = (sizeof(real) == 4 ? 4 : 2) * a.S * sizeof(typename M<real>::real4) + 8;
+  const size_t smem_need = ((sizeof(real) == 4 ? 4 : 2) * a.S + 2) * sizeof(typename M<real>::real4) + 8;
   if (smem_need > 200 * 1024) {
     *why = "n_sta too large for the shared-memory staging of the lane-per-chain kernel";
     return cudaErrorInvalidValue;

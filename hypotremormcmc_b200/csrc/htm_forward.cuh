@@ -133,12 +133,11 @@ __device__ __forceinline__ void station_accum_x(float hx, float hy, float hz, fl
 }
 
 // Packed form (FFMA2 / FADD2 / FMUL2, sm_100a): TWO STATIONS of one chain per instruction, so the
-// 14 operations per station become 7 issue slots while every lane still owns one chain.  Stations
-// 1..S-1 are stored as pairs (station 0 is the shift station and is handled apart); an odd tail is
-// padded with a zero-weight copy.  Shared-memory record per pair, 4 x float4:
+// 14 operations per station become 7 issue slots while every lane still owns one chain.  Stations are
+// stored as pairs (0,1), (2,3), ...; an odd tail is padded with a zero-weight copy.  Shared-memory record
+// per pair, 4 x float4:
 //   {cx0,cx1,cy0,cy1} {cz0,cz1,c0_0,c0_1} {sw_t0,sw_t1,-sw_t t_0,-sw_t t_1} {sw_a0,sw_a1,-sw_a a_0,-sw_a a_1}
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ int n_station_pairs(int S) { return S / 2; }  // ceil((S-1)/2)
 __device__ __forceinline__ void store_station_pair(float4* dst, const StaRecF a, const StaRecF b) {
   dst[0] = make_float4(a.A.x, b.A.x, a.A.y, b.A.y);
   dst[1] = make_float4(a.A.z, b.A.z, a.A.w, b.A.w);
@@ -149,32 +148,28 @@ __device__ __forceinline__ void store_station_pair(float4* dst, const StaRecF a,
 #define HTM_PK_UNROLL 2
 #endif
 constexpr int kPackedUnroll = HTM_PK_UNROLL;
-// hx/hy/hz: hypocentres centred on the event's prior centre; A0: expanded geometry of station 0;
-// t0/a0: raw {t_obs, a_obs} of station 0.  Returns S1t, S1a, S2 per slot.
+// hx/hy/hz: hypocentres centred on the event's prior centre; nct/nca: the NEGATED shifts c_t, c_a of each
+// chain (the lane kernel carries the weighted mean residual of the chain's accepted state, so no station
+// needs special treatment: chi2 = S2 - S1^2/W holds for any shift and S1 stays small).
+// Returns S1t = sum w_t (r_t - c_t), S1a, S2 = sum w (r - c)^2 per slot.
 template <int NSLOT>
-__device__ __forceinline__ void forward_pairs(const float4* __restrict__ s_pk, const int n_pairs, const float4 A0,
-                                              const float t0, const float a0, const float (&hx)[NSLOT],
-                                              const float (&hy)[NSLOT], const float (&hz)[NSLOT],
-                                              const Glob<float>& g, float (&S1t)[NSLOT], float (&S1a)[NSLOT],
-                                              float (&S2)[NSLOT]) {
+__device__ __forceinline__ void forward_pairs(const float4* __restrict__ s_pk, const int n_pairs,
+                                              const float (&hx)[NSLOT], const float (&hy)[NSLOT],
+                                              const float (&hz)[NSLOT], const Glob<float>& g,
+                                              const float (&nct)[NSLOT], const float (&nca)[NSLOT],
+                                              float (&S1t)[NSLOT], float (&S1a)[NSLOT], float (&S2)[NSLOT]) {
   const float2 ivs2 = f2(g.ivs, g.ivs), nB2 = f2(-g.B, -g.B);
   const float2 nc2 = f2(-0.34657359027997264f, -0.34657359027997264f);
-  float2 px[NSLOT], py[NSLOT], pz[NSLOT], hh[NSLOT], nct[NSLOT], nca[NSLOT], a1t[NSLOT], a1a[NSLOT], a2[NSLOT];
+  float2 px[NSLOT], py[NSLOT], pz[NSLOT], hh[NSLOT], ct2[NSLOT], ca2[NSLOT], a1t[NSLOT], a1a[NSLOT], a2[NSLOT];
 #pragma unroll
   for (int q = 0; q < NSLOT; ++q) {
     const float h2 = fmaf(hz[q], hz[q], fmaf(hy[q], hy[q], hx[q] * hx[q]));
-    // shift station: raw residuals of station 0 (negated)
-    const float d2 = fmaf(hx[q], A0.x, fmaf(hy[q], A0.y, fmaf(hz[q], A0.z, A0.w + h2)));
-    const float d = d2 * mufu_rsq(d2);
-    const float l2 = mufu_lg2(d2);
-    const float ct = -fmaf(d, g.ivs, -t0);
-    const float ca = -fmaf(-0.34657359027997264f, l2, fmaf(-g.B, d, -a0));
     px[q] = f2(hx[q], hx[q]);
     py[q] = f2(hy[q], hy[q]);
     pz[q] = f2(hz[q], hz[q]);
     hh[q] = f2(h2, h2);
-    nct[q] = f2(ct, ct);
-    nca[q] = f2(ca, ca);
+    ct2[q] = f2(nct[q], nct[q]);
+    ca2[q] = f2(nca[q], nca[q]);
     a1t[q] = f2(0.f, 0.f);
     a1a[q] = f2(0.f, 0.f);
     a2[q] = f2(0.f, 0.f);
@@ -190,8 +185,8 @@ __device__ __forceinline__ void forward_pairs(const float4* __restrict__ s_pk, c
                                               __ffma2_rn(pz[q], f2(r1.x, r1.y), __fadd2_rn(f2(r1.z, r1.w), hh[q]))));
       const float2 d = __fmul2_rn(d2, f2(mufu_rsq(d2.x), mufu_rsq(d2.y)));
       const float2 l2 = f2(mufu_lg2(d2.x), mufu_lg2(d2.y));
-      const float2 ut = __ffma2_rn(swt, __ffma2_rn(d, ivs2, nct[q]), f2(r2.z, r2.w));
-      const float2 ua = __ffma2_rn(swa, __ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, nca[q])), f2(r3.z, r3.w));
+      const float2 ut = __ffma2_rn(swt, __ffma2_rn(d, ivs2, ct2[q]), f2(r2.z, r2.w));
+      const float2 ua = __ffma2_rn(swa, __ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, ca2[q])), f2(r3.z, r3.w));
       a2[q] = __ffma2_rn(ut, ut, a2[q]);
       a1t[q] = __ffma2_rn(swt, ut, a1t[q]);
       a2[q] = __ffma2_rn(ua, ua, a2[q]);
