@@ -390,6 +390,40 @@ def test_float32_posterior_matches_reference_schedule_oracle():
             assert np.all(np.abs(qa - qb) < 0.35 * np.std(xa))
 
 
+def test_float32_posterior_at_config2_size_matches_float64_oracle_on_a_subset():
+    # BASELINE configs[1] at full size on the GPU (1000 events x 20 stations x 16 temperatures x 4 chains, float32)
+    # against the float64 oracle run on a SUBSET of the same events (events are independent in this mode, and
+    # Philox ids are global, so the oracle samples exactly those events' chains).  KS p > 1e-3 per marginal,
+    # medians within 0.15 sigma.
+    E, S, R, K = 1000, 20, 4, 16
+    n_it, burn, interval = 12000, 2000, 5
+    syn = H.Synthetic(E, S, 20231002)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=n_it, n_burn=burn,
+                           n_interval=interval, mode=H.MODE_FACTORISED, precision=32, seed=77,
+                           max_samples=n_it // interval + 2, **NOSOLVE)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        g.run(1, n_it)
+        sg = np.concatenate([g.fetch_samples(r)["hypo"] for r in range(R)])
+    assert sg.shape == (R * (n_it - burn) // interval, 3 * E)
+    lo, n_sub = 417, 6                                    # events 417..422
+    sub = syn.shard(0, 1)
+    for name in ("true_x", "true_y", "true_z", "x_mu", "y_mu", "t_obs", "t_stdv", "a_obs", "a_stdv"):
+        setattr(sub, name, np.ascontiguousarray(getattr(syn, name)[lo:lo + n_sub]))
+    sub.n_events = n_sub
+    ocfg = H.copy_config(cfg, precision=64, n_events=n_sub)
+    o = Oracle(ocfg, sub, event_offset=lo)
+    o.init_chains()
+    o.run(1, n_it, trace=False)
+    so = np.concatenate([o.fetch_samples(r)["hypo"] for r in range(R)])
+    for e in range(n_sub):
+        for c in range(3):
+            a, b = so[::8, 3 * e + c], sg[::8, 3 * (lo + e) + c]
+            assert stats.ks_2samp(a, b).pvalue > 1e-3, (e, c)
+            assert abs(np.median(a) - np.median(b)) < 0.15 * np.std(a), (e, c)
+
+
 def test_float32_prior_only_samples_the_priors():
     syn = H.Synthetic(64, 6, 22)
     cfg = H.default_config(n_sta=6, n_events=64, n_procs=2, n_chains=4, n_cool=1, n_iter=20000, n_burn=500,
