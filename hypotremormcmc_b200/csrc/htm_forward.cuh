@@ -118,20 +118,6 @@ __device__ __forceinline__ StaRecF expand_station(const float4 st, const float4 
   r.B = make_float4(swt, -swt * ob.x, swa, -swa * ob.z);
   return r;
 }
-__device__ __forceinline__ void station_accum_x(float hx, float hy, float hz, float hh, const Glob<float>& g,
-                                                float nct, float nca, const float4 A, const float4 B, float& S1t,
-                                                float& S1a, float& S2) {
-  const float d2 = fmaf(hx, A.x, fmaf(hy, A.y, fmaf(hz, A.z, A.w + hh)));
-  const float d = d2 * mufu_rsq(d2);
-  const float l2 = mufu_lg2(d2);
-  const float ut = fmaf(B.x, fmaf(d, g.ivs, nct), B.y);
-  const float ua = fmaf(B.z, fmaf(-0.34657359027997264f, l2, fmaf(-g.B, d, nca)), B.w);
-  S2 = fmaf(ut, ut, S2);
-  S1t = fmaf(B.x, ut, S1t);
-  S2 = fmaf(ua, ua, S2);
-  S1a = fmaf(B.z, ua, S1a);
-}
-
 // Packed form (FFMA2 / FADD2 / FMUL2, sm_100a): TWO STATIONS of one chain per instruction, so the
 // 14 operations per station become 7 issue slots while every lane still owns one chain.  Stations are
 // stored as pairs (0,1), (2,3), ...; an odd tail is padded with a zero-weight copy.  Shared-memory record

@@ -165,10 +165,11 @@ def test_replay_reports_exhausted_draws():
 
 # ---- mode B factorised: step-exact in float64 against the oracle's statement of the schedule --------
 @pytest.mark.parametrize("kernel,slots", [(2, 1), (2, 2), (2, 4), (1, 0)])
-@pytest.mark.parametrize("E,S,R,K", [(6, 10, 4, 5), (5, 50, 2, 16), (3, 20, 3, 1), (4, 33, 5, 7), (2, 12, 1, 32)])
+@pytest.mark.parametrize("E,S,R,K", [(6, 10, 4, 5), (5, 50, 2, 16), (3, 20, 3, 1), (4, 33, 5, 7), (2, 12, 1, 32),
+                                     (1, 1, 1, 2), (3, 130, 2, 3), (7, 5, 9, 4)])
 def test_factorised_float64_step_exact(kernel, slots, E, S, R, K):
-    if kernel == 1 and K > 16:
-        pytest.skip("warp-per-chain kernel: n_chains <= 16")
+    if kernel == 1 and (K > 16 or S > 128):
+        pytest.skip("warp-per-chain kernel: n_chains <= 16, n_sta <= 128")
     syn = H.Synthetic(E, S, 13 + E)
     cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=80, n_burn=20, n_interval=8,
                            mode=H.MODE_FACTORISED, precision=64, kernel=kernel, lane_slots=slots, max_samples=16,
@@ -244,7 +245,7 @@ def test_factorised_fixed_globals_are_folded_exactly():
 
 
 @pytest.mark.parametrize("kernel,slots", [(2, 1), (2, 2), (2, 4), (1, 0)])
-@pytest.mark.parametrize("S", [20, 50])
+@pytest.mark.parametrize("S", [20, 50, 33, 7, 1])
 def test_factorised_float32_kernel_likelihood_accuracy(kernel, slots, S):
     # the float32 throughput kernels' own log-likelihood (carried in registers across steps) against a
     # float64 evaluation of the SAME float32 states by the oracle: isolates the kernels' arithmetic
@@ -634,3 +635,67 @@ def test_blocked_gibbs_rank_shards_are_independent_ensembles():
         assert np.array_equal(sw_o, sw_g)
         assert rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
     assert not np.allclose(finals[0], finals[1])
+
+
+def test_argument_and_state_errors():
+    syn = H.Synthetic(4, 6, 2)
+    cfg = fact_cfg(4, 6, 2, 3, max_samples=4, n_interval=10)
+    with H.HypoTremorB200(cfg) as g:
+        with pytest.raises(H.HtmError) as ei:          # nothing set yet
+            g.init_chains()
+        assert ei.value.code == H.config.HTM_ERR_STATE
+        g.load(syn)
+        with pytest.raises(H.HtmError) as ei:          # chains not initialised
+            g.run(1, 10)
+        assert ei.value.code == H.config.HTM_ERR_STATE
+        g.init_chains()
+        with pytest.raises(H.HtmError) as ei:
+            g.run(0, 10)
+        assert ei.value.code == H.config.HTM_ERR_ARG
+        g.run(1, 40)                                    # 4 recorded iterations fill the ring
+        with pytest.raises(H.HtmError) as ei:          # ring full until fetched
+            g.run(41, 80)
+        assert ei.value.code == H.config.HTM_ERR_STATE and "sample ring full" in str(ei.value)
+        for r in range(2):
+            g.fetch_samples(r)
+            g.fetch_likelihood(r)
+        g.run(41, 80)
+        with pytest.raises(H.HtmError):                 # wrong mode
+            g.replay(1, 2, [np.zeros(4, dtype=np.int32)] * 2)
+    big = fact_cfg(2, 6, 1, 33)                          # n_chains > 32 in factorised mode
+    with H.HypoTremorB200(big) as g:
+        g.load(H.Synthetic(2, 6, 1))
+        g.init_chains()
+        with pytest.raises(H.HtmError) as ei:
+            g.run(1, 2)
+        assert ei.value.code == H.config.HTM_ERR_UNSUPPORTED
+    wide = H.default_config(n_sta=400, n_events=2, mode=H.MODE_BLOCKED_GIBBS, precision=32, n_procs=1, n_chains=2)
+    with H.HypoTremorB200(wide) as g:                    # blocked-Gibbs stages 32 rows per CTA: n_sta limit
+        g.load(H.Synthetic(2, 400, 1))
+        g.init_chains()
+        with pytest.raises(H.HtmError) as ei:
+            g.run(1, 2)
+        assert ei.value.code == H.config.HTM_ERR_UNSUPPORTED
+
+
+def test_many_stations_lane_kernel():
+    # 1000 stations: the lane kernel falls back to one warp per CTA to fit its shared-memory slice
+    syn = H.Synthetic(3, 1000, 4)
+    cfg = fact_cfg(3, 1000, 1, 4, precision=64, n_iter=6, n_interval=2)
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    tr_o, _ = o.run(1, 6)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        tr_g, _ = g.run_traced(1, 6)
+    for f in FLAGS:
+        assert np.array_equal(tr_o[f], tr_g[f])
+    assert rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
+    cfg32 = H.copy_config(cfg, precision=32)
+    with H.HypoTremorB200(cfg32) as g:
+        g.load(syn)
+        g.init_chains()
+        g.run(1, 50)
+        p, a = g.get_counts()
+    assert p[4:].sum() == 50 * 3
