@@ -140,7 +140,8 @@ def cpu_reference_rate(a, seconds, n_events=None):
     from oracle.pyoracle import Oracle
     cores = os.cpu_count() or 1
     total = a.ranks * a.chains
-    ranks = max(d for d in range(1, total + 1) if total % d == 0 and d <= cores)
+    # as many virtual ranks (threads) as cores allow, keeping at least one hot chain per rank
+    ranks = max(d for d in range(1, total + 1) if total % d == 0 and d <= cores and total // d >= 2)
     chains = total // ranks
     E = n_events or a.events
     syn = H.Synthetic(E, a.stations, 20231002)
