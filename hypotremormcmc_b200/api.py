@@ -22,7 +22,7 @@ EXPORTS = [
     "htm_set_chain_state", "htm_get_chain_state", "htm_loglik", "htm_run", "htm_run_traced",
     "htm_synchronize", "htm_replay", "htm_fetch_samples", "htm_fetch_likelihood",
     "htm_discard_samples", "htm_get_counts", "htm_get_histograms", "htm_device_ptr",
-    "htm_last_run_stats", "htm_measure_fp32_peak",
+    "htm_last_run_stats", "htm_measure_fp32_peak", "htm_comm_unique_id", "htm_comm_init", "htm_gather",
 ]
 
 
@@ -80,6 +80,9 @@ def load_library():
         "htm_device_ptr": [vp, i32, ctypes.POINTER(vp), lp],
         "htm_last_run_stats": [vp, dp, lp, lp],
         "htm_measure_fp32_peak": [i32, dp, dp],
+        "htm_comm_unique_id": [ctypes.c_char_p],
+        "htm_comm_init": [vp, ctypes.c_char_p],
+        "htm_gather": [vp, ctypes.POINTER(ctypes.c_uint32), lp, lp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -290,6 +293,31 @@ class HypoTremorB200:
         h = np.zeros((self.n_events, 3, self.cfg.hist_bins), dtype=np.uint32)
         self._ck(self.lib.htm_get_histograms(self._h, h.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))))
         return h
+
+    # -- multi-GPU at the ABI level (NCCL inside the library) ----------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id; create on one shard, hand to every shard."""
+        lib = load_library()
+        buf = ctypes.create_string_buffer(128)
+        rc = lib.htm_comm_unique_id(buf)
+        if rc != HTM_OK:
+            err = ctypes.create_string_buffer(512)
+            lib.htm_last_error(None, err, 512)
+            raise HtmError(rc, err.value.decode())
+        return buf.raw
+
+    def comm_init(self, unique_id):
+        self._ck(self.lib.htm_comm_init(self._h, ctypes.create_string_buffer(unique_id, 128)))
+
+    def gather(self, histograms=True):
+        """(hist_all [n_events_total, 3, bins] or None, n_propose[7], n_accept[7]) over all shards."""
+        hist = np.zeros((self.cfg.n_events, 3, self.cfg.hist_bins), dtype=np.uint32) if histograms else None
+        p, a = np.zeros(7, dtype=np.int64), np.zeros(7, dtype=np.int64)
+        lp = ctypes.POINTER(ctypes.c_int64)
+        hp = hist.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)) if histograms else None
+        self._ck(self.lib.htm_gather(self._h, hp, p.ctypes.data_as(lp), a.ctypes.data_as(lp)))
+        return hist, p, a
 
     def device_ptr(self, what):
         p, n = ctypes.c_void_p(), ctypes.c_int64()

@@ -52,6 +52,8 @@ struct htm_handle_s {
   std::vector<char> host_hypo_rec;
   std::vector<int> host_rec_chain;
   std::vector<double> host_rec_vs, host_rec_qs, host_rec_L, host_rec_tc, host_rec_ac;
+  // multi-GPU (event shards): NCCL communicator, created by htm_comm_init
+  void* comm = nullptr;
   // stats
   bool timed = false;
   int64_t last_launches = 0, last_proposals = 0;
@@ -554,6 +556,7 @@ int32_t htm_destroy(htm_handle h) {
     free_dev(p);
   for (void* p : h->gibbs_bufs) free_dev(p);
   free_dev(h->d_obsx);
+  nccl_destroy(h->comm);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1175,6 +1178,78 @@ int32_t htm_get_histograms(htm_handle h, uint32_t* hist) {
   HTM_CK(h, cudaStreamSynchronize(h->stream));
   HTM_CK(h, cudaMemcpy(hist, h->d_hist, static_cast<size_t>(h->E) * 3 * h->cfg.hist_bins * sizeof(uint32_t),
                        cudaMemcpyDeviceToHost));
+  return HTM_OK;
+}
+
+int32_t htm_comm_unique_id(char id[128]) {
+  if (!id) return fail(nullptr, HTM_ERR_ARG, "null argument");
+  std::string why;
+  if (!nccl_unique_id(id, &why)) return fail(nullptr, HTM_ERR_CUDA, why);
+  return HTM_OK;
+}
+
+int32_t htm_comm_init(htm_handle h, const char id[128]) {
+  if (!h || !id) return fail(h, HTM_ERR_ARG, "null argument");
+  if (h->comm) return fail(h, HTM_ERR_STATE, "communicator already initialised");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  std::string why;
+  if (!nccl_init(&h->comm, id, h->cfg.shard_rank, h->cfg.shard_count, &why)) return fail(h, HTM_ERR_CUDA, why);
+  return HTM_OK;
+}
+
+int32_t htm_gather(htm_handle h, uint32_t* hist_all, int64_t n_propose[7], int64_t n_accept[7]) {
+  if (!h) return HTM_ERR_ARG;
+  if (!h->comm) return fail(h, HTM_ERR_STATE, "htm_comm_init was not called");
+  if (h->cfg.mode == HTM_MODE_REPLAY) return fail(h, HTM_ERR_UNSUPPORTED, "replay mode does not shard");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  const int W = h->cfg.shard_count;
+  std::string why;
+  // ---- counters: all-reduce (the MPI_Reduce of src/cls_parallel.f90:265-268) ----
+  if (n_propose && n_accept) {
+    unsigned long long* d_sum = nullptr;
+    HTM_CK(h, cudaMalloc(&d_sum, 14 * sizeof(unsigned long long)));
+    bool ok = nccl_allreduce_u64(h->comm, h->d_counts, d_sum, 14, h->stream, &why);
+    unsigned long long c[14];
+    cudaError_t e = ok ? cudaMemcpyAsync(c, d_sum, sizeof(c), cudaMemcpyDeviceToHost, h->stream) : cudaSuccess;
+    if (ok && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    free_dev(d_sum);
+    if (!ok) return fail(h, HTM_ERR_CUDA, why);
+    HTM_CK(h, e);
+    for (int k = 0; k < 7; ++k) {
+      n_propose[k] = static_cast<int64_t>(c[k]);
+      n_accept[k] = static_cast<int64_t>(c[7 + k]);
+    }
+  }
+  // ---- histograms: all-gather of the event blocks (mode B shards events; blocks padded to the largest) ----
+  if (hist_all) {
+    if (!h->d_hist) return fail(h, HTM_ERR_STATE, "histograms are off (hist_bins = 0)");
+    if (h->cfg.mode != HTM_MODE_FACTORISED) return fail(h, HTM_ERR_UNSUPPORTED, "histograms exist in the factorised mode only");
+    const size_t per_ev = static_cast<size_t>(3) * h->cfg.hist_bins;
+    int biggest = 0;
+    for (int r = 0; r < W; ++r) {
+      int lo, hi;
+      shard_bounds(h->E_total, r, W, &lo, &hi);
+      if (hi - lo > biggest) biggest = hi - lo;
+    }
+    uint32_t *d_send = nullptr, *d_recv = nullptr;
+    HTM_CK(h, cudaMalloc(&d_send, biggest * per_ev * sizeof(uint32_t)));
+    HTM_CK(h, cudaMalloc(&d_recv, static_cast<size_t>(W) * biggest * per_ev * sizeof(uint32_t)));
+    cudaError_t e = cudaMemsetAsync(d_send, 0, biggest * per_ev * sizeof(uint32_t), h->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d_send, h->d_hist, h->E * per_ev * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream);
+    bool ok = e == cudaSuccess && nccl_allgather_u32(h->comm, d_send, d_recv, biggest * per_ev, h->stream, &why);
+    for (int r = 0; r < W && ok && e == cudaSuccess; ++r) {
+      int lo, hi;
+      shard_bounds(h->E_total, r, W, &lo, &hi);
+      e = cudaMemcpyAsync(hist_all + lo * per_ev, d_recv + static_cast<size_t>(r) * biggest * per_ev,
+                          (hi - lo) * per_ev * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (ok && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    free_dev(d_send);
+    free_dev(d_recv);
+    if (!ok && !why.empty()) return fail(h, HTM_ERR_CUDA, why);
+    HTM_CK(h, e);
+  }
   return HTM_OK;
 }
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "../../include/htm_b200.h"
 
 namespace htm {
@@ -111,6 +113,16 @@ cudaError_t launch_gibbs(const GibbsLaunch& a, cudaStream_t stream, int* n_launc
 // float32: build the expanded rows from the raw tables (once per table upload)
 cudaError_t launch_expand_obs(const Tables& tab, int E, int S, void* obsx, cudaStream_t stream);
 cudaError_t launch_gibbs_init(const GibbsLaunch& a, double temp_high, int ladder, int n_cool, cudaStream_t stream);
+
+// NCCL, loaded with dlopen (htm_comm.cu)
+struct NcclId {
+  char internal[128];
+};
+bool nccl_unique_id(char id[128], std::string* why);
+bool nccl_init(void** comm, const char id[128], int rank, int nranks, std::string* why);
+void nccl_destroy(void* comm);
+bool nccl_allgather_u32(void* comm, const void* send, void* recv, size_t count, cudaStream_t s, std::string* why);
+bool nccl_allreduce_u64(void* comm, const void* send, void* recv, size_t count, cudaStream_t s, std::string* why);
 
 // FFMA / MUFU microbenchmark (roofline denominators)
 cudaError_t measure_fp32_peak(int device, double* tflops, double* mufu_gops);

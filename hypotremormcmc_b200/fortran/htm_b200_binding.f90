@@ -251,6 +251,27 @@ module htm_b200_binding
        integer(c_int32_t) :: rc
      end function htm_last_run_stats
 
+     function htm_comm_unique_id(id) bind(c, name="htm_comm_unique_id") result(rc)
+       import
+       character(kind=c_char), intent(out) :: id(128)
+       integer(c_int32_t) :: rc
+     end function htm_comm_unique_id
+
+     function htm_comm_init(h, id) bind(c, name="htm_comm_init") result(rc)
+       import
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: id(128)
+       integer(c_int32_t) :: rc
+     end function htm_comm_init
+
+     function htm_gather(h, hist_all, n_propose, n_accept) bind(c, name="htm_gather") result(rc)
+       import
+       type(c_ptr), value :: h
+       type(c_ptr), value :: hist_all
+       integer(c_int64_t), intent(out) :: n_propose(7), n_accept(7)
+       integer(c_int32_t) :: rc
+     end function htm_gather
+
      function htm_measure_fp32_peak(device, tflops, mufu_gops) &
           & bind(c, name="htm_measure_fp32_peak") result(rc)
        import

@@ -263,6 +263,17 @@ int32_t htm_get_counts(htm_handle h, int64_t n_propose[7], int64_t n_accept[7]);
  * hist: [n_events(shard)][3][hist_bins] counts (x, y, z). */
 int32_t htm_get_histograms(htm_handle h, uint32_t* hist);
 
+/* ---- multi-GPU (one process per GPU, events sharded by cfg.shard_rank / cfg.shard_count) -----
+ * The data path needs no exchange; these calls are the once-per-flush gathers.  NCCL is loaded
+ * with dlopen at the first call.  htm_comm_unique_id: called on ONE shard; the HOST program hands
+ * the 128 bytes to every shard (MPI_Bcast in a Fortran/MPI driver, a file, torch.distributed ...).
+ * htm_gather: all-gather of the event-sharded histograms into hist_all[n_events_total][3][bins]
+ * (host, may be NULL) and all-reduce of the proposal counters -- the latter replaces the MPI_Reduce
+ * of parallel%output_proposal, src/cls_parallel.f90:265-268.  Collective: every shard must call. */
+int32_t htm_comm_unique_id(char id[128]);
+int32_t htm_comm_init(htm_handle h, const char id[128]);
+int32_t htm_gather(htm_handle h, uint32_t* hist_all, int64_t n_propose[7], int64_t n_accept[7]);
+
 /* Device pointers for zero-copy consumers in the same process (e.g. a NCCL gather driven
  * by the host program).  what: 0 = histograms (uint32), 1 = counts (int64[14]). */
 int32_t htm_device_ptr(htm_handle h, int32_t what, void** ptr, int64_t* n_bytes);

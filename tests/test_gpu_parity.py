@@ -699,3 +699,19 @@ def test_many_stations_lane_kernel():
         g.run(1, 50)
         p, a = g.get_counts()
     assert p[4:].sum() == 50 * 3
+
+
+def test_abi_level_nccl_gather_single_shard():
+    # htm_comm_unique_id / htm_comm_init / htm_gather with NCCL loaded by the library itself (world of one here;
+    # tools/comm_check.py runs the same calls on several GPUs under torchrun)
+    syn = H.Synthetic(50, 12, 3)
+    cfg = fact_cfg(50, 12, 2, 4, n_iter=100, n_interval=10, hist_bins=16)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        g.run(1, 100)
+        g.comm_init(H.HypoTremorB200.comm_unique_id())
+        hist, p, a = g.gather()
+        assert np.array_equal(hist, g.get_histograms())
+        p0, a0 = g.get_counts()
+        assert np.array_equal(p, p0) and np.array_equal(a, a0)
