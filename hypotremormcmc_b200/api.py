@@ -128,7 +128,7 @@ class HypoTremorB200:
         from .synth import shard_bounds
         self.n_sta, self.n_procs, self.n_chains = cfg.n_sta, cfg.n_procs, cfg.n_chains
         self.rank_offset = 0
-        if cfg.mode == MODE_BLOCKED_GIBBS:
+        if cfg.mode == MODE_BLOCKED_GIBBS and not cfg.gibbs_shard_events:
             # joint chains: the shards split the virtual ranks and every shard holds all events
             lo, hi = shard_bounds(cfg.n_procs, cfg.shard_rank, cfg.shard_count)
             self.event_offset, self.n_events = 0, cfg.n_events

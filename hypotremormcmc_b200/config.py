@@ -5,7 +5,7 @@ The field list follows the getters the reference driver reads from ``cls_param``
 """
 import ctypes
 
-HTM_ABI_VERSION = 1
+HTM_ABI_VERSION = 2
 
 HTM_OK, HTM_ERR_ARG, HTM_ERR_STATE, HTM_ERR_CUDA, HTM_ERR_DRAWS, HTM_ERR_UNSUPPORTED = range(6)
 
@@ -66,6 +66,8 @@ class HtmConfig(ctypes.Structure):
         ("hist_bins", ctypes.c_int32),
         ("max_samples", ctypes.c_int32),
         ("lane_slots", ctypes.c_int32),
+        ("gibbs_shard_events", ctypes.c_int32),
+        ("reserved1", ctypes.c_int32),
     ]
 
 

@@ -3,6 +3,7 @@
 // steps a chain on the CPU.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -300,6 +301,7 @@ int32_t alloc_state(htm_handle h) {
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.part_cur), 4 * J * nt * 8));  // [2 buffers][cur, prop][J][tiles]
     g.part_prop = g.part_cur + J * nt;
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.done_counter), 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.totals), 2 * J * 8));
     if (h->cfg.max_samples > 0) {
       h->rec_cap = h->cfg.max_samples;
       const size_t n = static_cast<size_t>(h->rec_cap) * h->n_cold_total;
@@ -333,7 +335,8 @@ void gibbs_launch_of(htm_handle h) {
   g.event_offset = static_cast<uint32_t>(h->ev_off);
   g.chain_offset = static_cast<uint32_t>(h->rank_off) * h->K;
   g.J_total = static_cast<uint32_t>(h->cfg.n_procs) * h->K;
-  g.swap_stream = static_cast<uint32_t>(h->cfg.shard_rank);
+  // rank shards are independent ensembles (own swap stream each); event shards replicate ONE ensemble
+  g.swap_stream = h->cfg.gibbs_shard_events ? 0u : static_cast<uint32_t>(h->cfg.shard_rank);
   g.prior_z = h->cfg.prior_z;
   g.width_z = h->cfg.prior_width_z;
   g.width_xy = h->cfg.prior_width_xy;
@@ -354,6 +357,10 @@ void gibbs_launch_of(htm_handle h) {
   g.counts = h->d_counts;
   g.rec_origin = h->rec_origin;
   g.rec_cap = h->rec_cap;
+  // event-sharded joint chains (or HTM_GIBBS_FORCE_ALLREDUCE with a communicator, for single-GPU tests)
+  const bool ev_sharded = h->cfg.gibbs_shard_events && h->cfg.shard_count > 1;
+  g.comm = (ev_sharded || (h->comm && std::getenv("HTM_GIBBS_FORCE_ALLREDUCE"))) ? h->comm : nullptr;
+  g.count_globals = (!ev_sharded || h->cfg.shard_rank == 0) ? 1 : 0;
 }
 
 // recorded iterations (mod(it, n_interval) == 1) inside [first, last]: ids m = (it-1)/n_interval
@@ -480,8 +487,10 @@ int32_t htm_create(htm_handle* out, const htm_config* cfg) {
   if (cfg->mode != HTM_MODE_REPLAY && cfg->mode != HTM_MODE_FACTORISED && cfg->mode != HTM_MODE_BLOCKED_GIBBS)
     return fail(nullptr, HTM_ERR_ARG, "unknown mode");
   if (cfg->hist_bins < 0 || cfg->max_samples < 0) return fail(nullptr, HTM_ERR_ARG, "negative hist_bins/max_samples");
-  if (cfg->mode == HTM_MODE_BLOCKED_GIBBS && cfg->shard_count > cfg->n_procs)
+  if (cfg->mode == HTM_MODE_BLOCKED_GIBBS && !cfg->gibbs_shard_events && cfg->shard_count > cfg->n_procs)
     return fail(nullptr, HTM_ERR_ARG, "blocked-Gibbs mode shards the virtual ranks: shard_count must be <= n_procs");
+  if (cfg->gibbs_shard_events && cfg->mode != HTM_MODE_BLOCKED_GIBBS)
+    return fail(nullptr, HTM_ERR_ARG, "gibbs_shard_events applies to the blocked-Gibbs mode only");
 
   int n_dev = 0;
   cudaError_t ce = cudaGetDeviceCount(&n_dev);
@@ -497,8 +506,8 @@ int32_t htm_create(htm_handle* out, const htm_config* cfg) {
   h->cfg = *cfg;
   h->E_total = cfg->n_events;
   int lo, hi;
-  if (cfg->mode == HTM_MODE_BLOCKED_GIBBS) {
-    // joint chains couple all events, so this mode shards the VIRTUAL RANKS instead (the reference's own
+  if (cfg->mode == HTM_MODE_BLOCKED_GIBBS && !cfg->gibbs_shard_events) {
+    // joint chains couple all events, so this mode shards the VIRTUAL RANKS by default (the reference's own
     // decomposition, src/hypo_tremor_mcmc.f90:114-118): every shard holds all events and an independent
     // ensemble of its ranks' chains; swaps stay inside the shard; no collective.
     shard_bounds(cfg->n_procs, cfg->shard_rank, cfg->shard_count, &lo, &hi);
@@ -819,6 +828,8 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
     h->host_samples_valid = false;
   }
   if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
+    if (h->cfg.gibbs_shard_events && h->cfg.shard_count > 1 && !h->comm)
+      return fail(h, HTM_ERR_STATE, "event-sharded blocked-Gibbs run needs htm_comm_init first (one all-reduce per iteration)");
     gibbs_launch_of(h);
     h->gl.iter_first = iter_first;
     h->gl.iter_last = iter_last;

@@ -93,6 +93,11 @@ bool nccl_allgather_u32(void* comm, const void* send, void* recv, size_t count, 
   if (rc != 0) *why = "ncclAllGather: " + nccl_err(rc);
   return rc == 0;
 }
+bool nccl_allreduce_f64(void* comm, const void* send, void* recv, size_t count, cudaStream_t s, std::string* why) {
+  const int rc = api().AllReduce(send, recv, count, 8, 0, comm, s);  // ncclFloat64 = 8, ncclSum = 0
+  if (rc != 0) *why = "ncclAllReduce: " + nccl_err(rc);
+  return rc == 0;
+}
 bool nccl_allreduce_u64(void* comm, const void* send, void* recv, size_t count, cudaStream_t s, std::string* why) {
   const int rc = api().AllReduce(send, recv, count, 5, 0, comm, s);
   if (rc != 0) *why = "ncclAllReduce: " + nccl_err(rc);

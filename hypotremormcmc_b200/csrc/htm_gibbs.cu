@@ -21,6 +21,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdlib>
+#include <string>
 
 #include "htm_forward.cuh"
 #include "htm_kernels.hpp"
@@ -121,6 +122,7 @@ struct GibbsDecide {
   int solved[4];
   double prior[4], width[4], step[4];  // indexed by type-1: vs, t_corr, qs, a_corr
   unsigned long long* counts;
+  int count_globals;  // 0 on shards > 0 of an event-sharded run (the decisions are replicated)
   // shared-parameter records of the cold chains: [cap][n_cool_total]
   int rec_slot;
   int* rec_chain;
@@ -233,7 +235,7 @@ __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int i
         const double ratio = (Lprop - Lcur) / T + cs.lpr[c];
         const double r = M<double>::u_co(wb.v[0]);
         if (r >= kEps64 && ::log(r) <= ratio) acc = true;
-        if (writer && cold && d.counts) {
+        if (writer && cold && d.counts && d.count_globals) {
           atomicAdd(d.counts + (which - 1), 1ull);
           if (acc) atomicAdd(d.counts + 7 + (which - 1), 1ull);
         }
@@ -729,6 +731,7 @@ __global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsPar
   }
 
   // ---- the last CTA to finish judges the shared-parameter proposals (fixed-order sums: deterministic) ----
+  if (done_counter == nullptr) return;  // event-sharded run: totals -> all-reduce -> decide are separate launches
   __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1005,6 +1008,7 @@ static GibbsDecide make_decide(const GibbsLaunch& a) {
     d.step[t] = a.g_step[t];
   }
   d.counts = a.counts;
+  d.count_globals = a.count_globals;
   d.rec_slot = -1;
   d.rec_chain = a.rec_chain;
   d.rec_vs = a.rec_vs;
@@ -1015,6 +1019,23 @@ static GibbsDecide make_decide(const GibbsLaunch& a) {
   d.trace = nullptr;
   d.swap = nullptr;
   return d;
+}
+
+// per-chain sums of the per-tile partials of THIS shard (fixed order): totals[c] = cur, totals[J + c] = proposed
+__global__ void gibbs_totals_kernel(const double* part_cur, const double* part_prop, int J, int n_tiles, double* totals) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= J) return;
+  double a = 0.0, b = 0.0;
+  for (int t = lane; t < n_tiles; t += 32) {
+    a += part_cur[static_cast<size_t>(c) * n_tiles + t];
+    b += part_prop[static_cast<size_t>(c) * n_tiles + t];
+  }
+  a = warp_sum<double>(a);
+  b = warp_sum<double>(b);
+  if (lane == 0) {
+    totals[c] = a;
+    totals[J + c] = b;
+  }
 }
 
 // HTM_GIBBS_PERSIST=0 forces one launch per iteration, =1 insists on the persistent kernel (tests)
@@ -1041,6 +1062,39 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
   d.it_next = a.iter_first;
   gibbs_decide_kernel<<<1, 256, sm_chain, stream>>>(d);
   ++nl;
+
+  // ---- event-sharded joint chains: sweep -> local totals -> all-reduce -> decide (replicated) ----
+  if (a.comm) {
+    err = cudaFuncSetAttribute(gibbs_sweep_kernel<real, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem_iter));
+    if (err != cudaSuccess) return err;
+    const size_t per_it_s = static_cast<size_t>(a.E + 1) * a.J;
+    std::string why;
+    for (int it = a.iter_first; it <= a.iter_last; ++it) {
+      const bool rec = a.n_interval > 1 && (it % a.n_interval) == 1;
+      const int slot = rec ? (it - 1) / a.n_interval - a.rec_origin : -1;
+      p.it = it;
+      p.rec_slot = (slot >= 0 && slot < a.rec_cap) ? slot : -1;
+      p.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it_s : nullptr;
+      gibbs_sweep_kernel<real, TRACE><<<grid, kCW * 32, smem_iter, stream>>>(p, d, nullptr);
+      gibbs_totals_kernel<<<(a.J + 3) / 4, 128, 0, stream>>>(p.part_cur, p.part_prop, a.J, p.n_tiles, a.totals);
+      if (!nccl_allreduce_f64(a.comm, a.totals, a.totals, 2 * static_cast<size_t>(a.J), stream, &why))
+        return cudaErrorUnknown;
+      GibbsDecide dd = d;
+      dd.n_tiles = 1;  // the "partials" are now the global per-chain sums
+      dd.part_cur = a.totals;
+      dd.part_prop = a.totals + a.J;
+      dd.it = it;
+      dd.it_next = it + 1;
+      dd.rec_slot = p.rec_slot;
+      dd.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it_s + static_cast<size_t>(a.E) * a.J : nullptr;
+      dd.swap = a.swaps ? a.swaps + (it - a.iter_first) : nullptr;
+      gibbs_decide_kernel<<<1, 256, sm_chain, stream>>>(dd);
+      nl += 3;
+    }
+    if (n_launches) *n_launches = nl;
+    return cudaGetLastError();
+  }
 
   // ---- persistent cooperative kernel when every CTA can be resident at once ----
   const int want = persist_env();

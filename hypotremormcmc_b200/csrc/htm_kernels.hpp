@@ -92,6 +92,10 @@ struct GibbsLaunch {
   unsigned int* done_counter = nullptr;              // CTAs finished in the current sweep
   const void* obsx = nullptr;                        // float32: expanded station-pair rows [E][xrow] float4
   int xrow = 0;
+  // event-sharded joint chains: all-reduce of the per-chain sums every iteration
+  void* comm = nullptr;       // NCCL communicator (null = single shard)
+  double* totals = nullptr;   // [2][J] scratch
+  int count_globals = 1;      // shared-parameter counters are replicated on every shard: only shard 0 counts
   int E = 0, S = 0, J = 0, K = 0, n_cool_total = 0;
   int iter_first = 0, iter_last = 0, n_burn = 0, n_interval = 1;
   uint64_t seed = 0;
@@ -122,6 +126,7 @@ bool nccl_unique_id(char id[128], std::string* why);
 bool nccl_init(void** comm, const char id[128], int rank, int nranks, std::string* why);
 void nccl_destroy(void* comm);
 bool nccl_allgather_u32(void* comm, const void* send, void* recv, size_t count, cudaStream_t s, std::string* why);
+bool nccl_allreduce_f64(void* comm, const void* send, void* recv, size_t count, cudaStream_t s, std::string* why);
 bool nccl_allreduce_u64(void* comm, const void* send, void* recv, size_t count, cudaStream_t s, std::string* why);
 
 // FFMA / MUFU microbenchmark (roofline denominators)

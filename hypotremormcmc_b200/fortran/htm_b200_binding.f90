@@ -12,7 +12,7 @@ module htm_b200_binding
   use, intrinsic :: iso_c_binding
   implicit none
 
-  integer(c_int32_t), parameter :: HTM_ABI_VERSION = 1
+  integer(c_int32_t), parameter :: HTM_ABI_VERSION = 2
   integer(c_int32_t), parameter :: HTM_OK = 0
   integer(c_int32_t), parameter :: HTM_MODE_REPLAY = 0
   integer(c_int32_t), parameter :: HTM_MODE_FACTORISED = 1
@@ -51,6 +51,8 @@ module htm_b200_binding
      integer(c_int32_t) :: hist_bins
      integer(c_int32_t) :: max_samples
      integer(c_int32_t) :: lane_slots
+     integer(c_int32_t) :: gibbs_shard_events
+     integer(c_int32_t) :: reserved1
   end type htm_config
 
   type, bind(c) :: htm_step_trace

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HTM_ABI_VERSION 1
+#define HTM_ABI_VERSION 2
 
 /* ---- status codes --------------------------------------------------------------- */
 enum {
@@ -113,10 +113,15 @@ typedef struct htm_config {
   int32_t shard_count;      /* modes A/B: EVENTS are split in contiguous blocks over the
                                shards.  Mode C (joint chains): the VIRTUAL RANKS are split
                                instead (every shard holds all events and runs an independent
-                               ensemble of its ranks; `rank` arguments are then shard-local) */
+                               ensemble of its ranks; `rank` arguments are then shard-local),
+                               unless gibbs_shard_events = 1 */
   int32_t hist_bins;        /* bins per coordinate histogram; 0 = no histograms         */
   int32_t max_samples;      /* capacity (in recorded iterations) of the sample ring     */
   int32_t lane_slots;       /* lane-per-chain kernel: chains per thread (1, 2, 4); 0 = auto */
+  int32_t gibbs_shard_events; /* mode C only: 1 = shard the EVENTS of every joint chain over the shards (all
+                               shards hold all chains; one NCCL all-reduce of the per-chain sums per
+                               iteration; needs htm_comm_init).  0 = shard the virtual ranks.        */
+  int32_t reserved1;        /* keeps sizeof(htm_config) a multiple of 8                 */
 } htm_config;
 
 /* One record per (iteration, rank, chain) step of the replay mode, in loop order

@@ -36,11 +36,12 @@ def test_config_struct_matches_c_defaults():
     # every field of the sample-file defaults agrees between the C side and the Python mirror;
     # a layout mismatch would scramble them
     for name, _ in H.HtmConfig._fields_:
-        if name in ("n_sta", "n_events", "device", "shard_rank", "max_samples", "hist_bins", "lane_slots"):
+        if name in ("n_sta", "n_events", "device", "shard_rank", "max_samples", "hist_bins", "lane_slots",
+                    "gibbs_shard_events", "reserved1"):
             continue
         assert getattr(c, name) == getattr(d, name), name
-    assert ctypes.sizeof(H.HtmConfig) == 21 * 8 + 26 * 4
-    assert c.abi_version == 1 and c.temp_high == 200.0 and c.step_size_a_corr == 0.005
+    assert ctypes.sizeof(H.HtmConfig) == 21 * 8 + 28 * 4
+    assert c.abi_version == 2 and c.temp_high == 200.0 and c.step_size_a_corr == 0.005
 
 
 def test_fortran_binding_mirrors_the_struct():

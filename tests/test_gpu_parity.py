@@ -715,3 +715,32 @@ def test_abi_level_nccl_gather_single_shard():
         assert np.array_equal(hist, g.get_histograms())
         p0, a0 = g.get_counts()
         assert np.array_equal(p, p0) and np.array_equal(a, a0)
+
+
+def test_blocked_gibbs_allreduce_path_is_step_exact(monkeypatch):
+    # the event-sharded joint-chain path (sweep -> local totals -> ncclAllReduce -> replicated decide), forced
+    # here on a one-rank communicator; tools/comm_check_gibbs.py runs it on several GPUs
+    monkeypatch.setenv("HTM_GIBBS_FORCE_ALLREDUCE", "1")
+    E, S, R, K = 45, 14, 2, 3
+    syn = H.Synthetic(E, S, 71)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=50, n_burn=10, n_interval=5,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=64, max_samples=16)
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    tr_o, sw_o = o.run(1, 50)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        g.comm_init(H.HypoTremorB200.comm_unique_id())
+        tr_g, sw_g = g.run_traced(1, 50)
+        _, nl, _ = g.last_run_stats()
+        cg = g.get_counts()
+        smp = g.fetch_samples(0)
+    assert nl == 1 + 3 * 50
+    for f in FLAGS:
+        assert np.array_equal(tr_o[f], tr_g[f]), f
+    assert np.array_equal(sw_o, sw_g) and rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
+    co = o.get_counts()
+    assert np.array_equal(co[0], cg[0]) and np.array_equal(co[1], cg[1])
+    so = o.fetch_samples(0)
+    assert np.array_equal(so["iter"], smp["iter"]) and np.allclose(so["vs"], smp["vs"], rtol=1e-12)
