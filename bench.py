@@ -174,7 +174,8 @@ def run_reference(a):
         return
     from oracle import pyoracle
     pyoracle.build()
-    per_step = max(1.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+    # each step a bounded sample; the whole --steps K --warmup W run stays within ~2 minutes
+    per_step = min(a.cpu_seconds, max(1.0, min(20.0, 120.0 / max(1, a.steps + a.warmup))))
     rates = []
     sample, cores = "", 1
     for i in range(a.warmup + a.steps):
