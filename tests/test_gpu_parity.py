@@ -744,3 +744,36 @@ def test_blocked_gibbs_allreduce_path_is_step_exact(monkeypatch):
     assert np.array_equal(co[0], cg[0]) and np.array_equal(co[1], cg[1])
     so = o.fetch_samples(0)
     assert np.array_equal(so["iter"], smp["iter"]) and np.allclose(so["vs"], smp["vs"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("use_time,use_amp", [(1, 0), (0, 1)])
+@pytest.mark.parametrize("mode", [H.MODE_FACTORISED, H.MODE_BLOCKED_GIBBS])
+def test_data_switches_and_degenerate_sigma_inside_the_kernels(mode, use_time, use_amp):
+    # use_time / use_amp drop their sum (src/cls_forward.f90:279,290) and a station with t_stdv = 0 follows the
+    # degenerate-sigma rule (:78-90) in the sampling kernels too, not only in htm_loglik
+    E, S, R, K = 5, 9, 2, 3
+    syn = H.Synthetic(E, S, 88)
+    syn.t_stdv[1, 4] = 0.0
+    syn.t_stdv[3, 0] = 1e-17
+    kw = NOSOLVE if mode == H.MODE_FACTORISED else {}
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=50, n_burn=0, n_interval=5, mode=mode,
+                           precision=64, use_time=use_time, use_amp=use_amp, max_samples=16, **kw)
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    tr_o, sw_o = o.run(1, 50)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        tr_g, sw_g = g.run_traced(1, 50)
+    for f in FLAGS:
+        assert np.array_equal(tr_o[f], tr_g[f]), f
+    assert np.array_equal(sw_o, sw_g) and rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
+    # float32 kernels: same configuration runs and its carried likelihood matches a float64 evaluation
+    c32 = H.copy_config(cfg, precision=32)
+    with H.HypoTremorB200(c32) as g:
+        g.load(syn)
+        g.init_chains()
+        g.run(1, 50)
+        st = g.get_chain_state(1, 2)
+    L64 = o.loglik(st["hypo"][None, :], st["t_corr"][None, :], st["a_corr"][None, :], [st["vs"]], [st["qs"]])[0]
+    assert abs(L64 - st["log_likelihood"]) <= 2e-3 * E + 5e-5 * abs(L64)
