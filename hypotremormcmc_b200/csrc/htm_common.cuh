@@ -131,7 +131,8 @@ struct M<float> {
   static __device__ __forceinline__ float gauss(uint32_t wa, uint32_t wb) {
     // sqrt(-2 ln u1) cos(2 pi u2) = sqrt(-2 ln2 lg2 u1) cos(2 pi u2)
     const float r = mufu_sqrt(-2.0f * kLn2 * mufu_lg2(u_oo(wa)));
-    return r * mufu_cos(6.283185307179586f * u_oo(wb));
+    // angle 2 pi u2 with the uniform's scale folded into one multiply
+    return r * mufu_cos((static_cast<float>(wb >> 9) + 0.5f) * (6.283185307179586f / 8388608.0f));
   }
   // distance and ln(distance) from the squared distance: two independent MUFU ops
   static __device__ __forceinline__ void dist(float d2, float& d, float& lnd) {

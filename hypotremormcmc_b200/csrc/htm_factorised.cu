@@ -54,6 +54,7 @@ struct FactParams {
   PhiloxKeys rk;  // Philox round keys of `seed`
   uint32_t event_offset;
   real vs, qs, prior_z, width_z, width_xy, step_xy, step_z;
+  real inv2s2_xy, inv2s2_z;  // 1/(2 sigma^2) of the x,y and z priors (host-computed: no division in the loop)
   unsigned long long* counts;
   real4* samples;
   int rec_origin, rec_cap;
@@ -193,8 +194,6 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
   const typename R2<real>::type pxy = p.prior_xy[e];
   const Glob<real> g = make_glob<real>(p.vs, p.qs);
   const uint32_t eg = static_cast<uint32_t>(e) + p.event_offset;
-  const real inv2s2_xy = static_cast<real>(1) / (static_cast<real>(2) * p.width_xy * p.width_xy);
-  const real inv2s2_z = static_cast<real>(1) / (static_cast<real>(2) * p.width_z * p.width_z);
   bool valid[NSLOT];
   int rr[NSLOT];
   size_t ci[NSLOT];
@@ -285,7 +284,7 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
       const real step = isz ? p.step_z : p.step_xy;
       const real x_new = x_old + gs * step;
       const real dn = x_new - mu, dl = x_old - mu;
-      real lp = -(dn * dn - dl * dl) * (isz ? inv2s2_z : inv2s2_xy);
+      real lp = -(dn * dn - dl * dl) * (isz ? p.inv2s2_z : p.inv2s2_xy);
       // type-1 prior: + ln(x_new - mu) - ln(x_old - mu); the second log is carried in lgz
       const real lgn = M<real>::log(isz ? fabs(dn) : static_cast<real>(1));
       nlgz[q] = isz ? lgn : lgz[q];
@@ -722,6 +721,8 @@ static FactParams<real> make_params(const FactLaunch& a) {
   p.width_xy = static_cast<real>(a.width_xy);
   p.step_xy = static_cast<real>(a.step_xy);
   p.step_z = static_cast<real>(a.step_z);
+  p.inv2s2_xy = static_cast<real>(1.0 / (2.0 * a.width_xy * a.width_xy));
+  p.inv2s2_z = static_cast<real>(1.0 / (2.0 * a.width_z * a.width_z));
   p.counts = a.counts;
   p.samples = static_cast<real4*>(a.samples);
   p.rec_origin = a.rec_origin;
