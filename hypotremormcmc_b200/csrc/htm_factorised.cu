@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
   size_t ci[NSLOT];
   real x[NSLOT], y[NSLOT], z[NSLOT], L[NSLOT], T[NSLOT], iT[NSLOT], lgz[NSLOT];
   uint32_t cnt_p[3] = {0, 0, 0}, cnt_a[3] = {0, 0, 0};
+  uint32_t pk_p = 0, pk_a = 0;  // packed per-type counters of the last <= 512/NSLOT iterations
 #pragma unroll
   for (int q = 0; q < NSLOT; ++q) {
     const int r = (we * NSLOT + q) * gpw + gl;
@@ -340,12 +341,11 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
       const real ru = M<real>::u_co(wacc[q]);
       const bool acc = ok[q] && (ru > static_cast<real>(0)) && (M<real>::log(ru) <= ratio);
       const bool cold = is_cold<real>(T[q]);
-      if (cold && valid[q]) {  // invalid lanes clone a valid chain and must not count
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          cnt_p[c] += (icmp[q] == c) ? 1u : 0u;
-          cnt_a[c] += (acc && icmp[q] == c) ? 1u : 0u;
-        }
+      {  // cold-chain counters, three 10-bit fields per word (flushed every 512 iterations below);
+         // invalid lanes clone a valid chain and must not count
+        const uint32_t inc = (cold && valid[q]) ? (1u << (10 * icmp[q])) : 0u;
+        pk_p += inc;
+        pk_a += acc ? inc : 0u;
       }
       x[q] = acc ? nx[q] : x[q];
       y[q] = acc ? ny[q] : y[q];
@@ -428,6 +428,15 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
         }
       }
     }
+    if (((it - p.iter_first) & (512 / NSLOT - 1)) == 512 / NSLOT - 1) {  // before a 10-bit field can overflow
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        cnt_p[c] += (pk_p >> (10 * c)) & 1023u;
+        cnt_a[c] += (pk_a >> (10 * c)) & 1023u;
+      }
+      pk_p = 0;
+      pk_a = 0;
+    }
     // advance the swap-draw window and the recording countdown
     sw_fill = false;
     if (++sw_o == K) {
@@ -451,6 +460,8 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {  // proposal types 5,6,7 = icmp 0,1,2 (src/cls_mcmc.f90:163)
+    cnt_p[c] += (pk_p >> (10 * c)) & 1023u;
+    cnt_a[c] += (pk_a >> (10 * c)) & 1023u;
     const uint32_t sp = warp_sum<uint32_t>(cnt_p[c]);
     const uint32_t sa = warp_sum<uint32_t>(cnt_a[c]);
     if (lane == 0 && p.counts) {
