@@ -17,7 +17,9 @@
 // Mapping of the sweep: CTA = tile of 32 events x up to 8 chains; warp = chain, lane = event.  The
 // tile's observation rows are staged by 32 bulk-TMA copies (one per event) into padded shared-memory
 // rows, so the per-lane 16-byte reads are bank-conflict free; station table and the chains' station
-// terms are warp-broadcast reads.
+// terms are warp-broadcast reads.  float32 at large E uses a second mapping (gibbs_sweep_oq_kernel:
+// warp = 8 events x 4 chains, CTA walks event octets through a 2-stage TMA ring); the persistent
+// cooperative kernel takes over whenever every tile can be resident at once.
 #include <cooperative_groups.h>
 
 #include <cstdlib>
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(256) gibbs_decide_kernel(const GibbsDecide d) 
 // per station pair (htm_forward.cuh: store_station_pair).  cp[m] = {-tc_j0, -tc_j1, -ac_j0, -ac_j1} are the
 // chain's station terms of pair m (warp-broadcast), ntc0/nac0 those of station 0.
 __device__ __forceinline__ int gibbs_xrow(int S) { return 2 + 4 * (S / 2); }
+constexpr int kGibbsPairUnroll = 2;
 __device__ __forceinline__ float eval_pairs_f32(const float4* __restrict__ row, const int n_pairs, const float hx,
                                                 const float hy, const float hz, const Glob<float>& g,
                                                 const float4* __restrict__ cp, const float ntc0, const float nac0,
@@ -377,7 +380,7 @@ __device__ __forceinline__ float eval_pairs_f32(const float4* __restrict__ row, 
   const float2 ivs2 = f2(g.ivs, g.ivs), nB2 = f2(-g.B, -g.B), nc2 = f2(-kC, -kC);
   float2 a1t = f2(0.f, 0.f), a1a = f2(0.f, 0.f), a2 = f2(0.f, 0.f);
   const float4* r = row + 2;
-#pragma unroll 2
+#pragma unroll kGibbsPairUnroll
   for (int m = 0; m < n_pairs; ++m) {
     const float4 r0 = r[4 * m], r1 = r[4 * m + 1], r2 = r[4 * m + 2], r3 = r[4 * m + 3];
     const float4 c4 = cp[m];
@@ -747,6 +750,235 @@ __global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsPar
   }
 }
 
+// ---- float32 sweep for large E: warp = 8 events x 4 chains, CTA loops over event octets --------------------
+// Same schedule and the same arithmetic per (chain, event) as gibbs_sweep_kernel.  What changes is the mapping:
+//   * lane = (event of the octet, chain of the quad), chain minor.  A 16-byte row read touches 8 distinct rows
+//     instead of 32 and neighbouring lanes share them: 2 shared-memory wavefronts instead of 4 (the unblocked
+//     sweep is bound by exactly that traffic); the chains' station terms are 4 distinct 16-byte words.
+//   * a CTA keeps its chains' terms in shared memory and walks a contiguous range of octets; the octet rows
+//     arrive through a 2-stage ring of bulk-TMA copies (full / empty mbarriers), so loading octet i+1 overlaps
+//     computing octet i and no block barrier sits in the loop.
+//   * the sums over events stay in registers (float64, fixed order) across the CTA's octets: one partial per
+//     (chain, CTA) instead of one per (chain, 32 events), and one reduction per launch instead of per tile.
+constexpr int kOct = 8;
+constexpr int kQuad = 4;
+struct OqSm {
+  uint64_t* full;   // [2]
+  uint64_t* empty;  // [2]
+  float4* rows;     // [2][kOct][row]
+  float4* cp;       // [nc][cps]
+  float4* cpP;      // [nc][cps]
+  float4* c0;       // [nc]  {-tc0, -ac0, -tc0', -ac0'}
+  int row, cps;
+};
+__host__ __device__ inline int oq_cps(int S) { return (S / 2) | 1; }
+__host__ __device__ inline size_t oq_smem(int S, int nc) {
+  const int xrow = 2 + 4 * (S / 2);
+  return 32 + (static_cast<size_t>(2) * kOct * (xrow + 1) + static_cast<size_t>(nc) * (2 * oq_cps(S) + 1)) * sizeof(float4);
+}
+__device__ __forceinline__ OqSm carve_oq_sm(unsigned char* base, int S, int xrow, int nc) {
+  OqSm m;
+  m.row = xrow + 1;
+  m.cps = oq_cps(S);
+  m.full = reinterpret_cast<uint64_t*>(base);
+  m.empty = m.full + 2;
+  m.rows = reinterpret_cast<float4*>(base + 32);
+  m.cp = m.rows + 2 * kOct * m.row;
+  m.cpP = m.cp + nc * m.cps;
+  m.c0 = m.cpP + nc * m.cps;
+  return m;
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(kCW * 32, 2) gibbs_sweep_oq_kernel(const GibbsParams<float> p, const GibbsDecide dec,
+                                                                     unsigned int* done_counter, const int n_oct) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const int S = p.S, J = p.J, E = p.E, n_pairs = S / 2;
+  const int nc = n_warps * kQuad;
+  const int c_base = blockIdx.y * nc;  // first chain of the CTA
+  const OqSm m = carve_oq_sm(smem_raw, S, p.xrow, nc);
+  const int o_begin = static_cast<int>(static_cast<long>(n_oct) * blockIdx.x / gridDim.x);
+  const int o_end = static_cast<int>(static_cast<long>(n_oct) * (blockIdx.x + 1) / gridDim.x);
+  const int n_my = o_end - o_begin;
+  const uint32_t row_bytes = static_cast<uint32_t>(p.xrow * sizeof(float4));
+  if (threadIdx.x == 0) {
+    mbar_init(m.full, 1);
+    mbar_init(m.full + 1, 1);
+    mbar_init(m.empty, n_warps);
+    mbar_init(m.empty + 1, n_warps);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  // one octet's rows -> ring stage `buf` (warp 0)
+  auto issue = [&](int o, int buf) {
+    const int n_ev = min(kOct, E - o * kOct);
+    if (lane == 0) mbar_expect_tx(m.full + buf, row_bytes * n_ev);
+    __syncwarp();
+    if (lane < n_ev)
+      tma_load_1d(m.rows + (buf * kOct + lane) * m.row, p.obsx + static_cast<size_t>(o * kOct + lane) * p.xrow, row_bytes,
+                  m.full + buf);
+  };
+  if (warp == 0) {
+    if (n_my > 0) issue(o_begin, 0);
+    if (n_my > 1) issue(o_begin + 1, 1);
+  }
+  // the CTA's chain terms (once per launch)
+  for (int i = threadIdx.x; i < nc * n_pairs; i += blockDim.x) {
+    const int lc = i / n_pairs, mm = i - lc * n_pairs, c = c_base + lc;
+    if (c >= J) continue;
+    const double* gtc = p.g_tc + static_cast<size_t>(c) * S;
+    const double* gac = p.g_ac + static_cast<size_t>(c) * S;
+    const int wh = p.prop_which[c], pi = p.prop_idx[c];
+    const float pv = static_cast<float>(p.prop_xnew[c]);
+    const int j0 = 1 + 2 * mm, j1 = j0 + 1;
+    float4 cur = make_float4(-static_cast<float>(gtc[j0]), 0.f, -static_cast<float>(gac[j0]), 0.f);
+    if (j1 < S) {
+      cur.y = -static_cast<float>(gtc[j1]);
+      cur.w = -static_cast<float>(gac[j1]);
+    }
+    float4 prp = cur;
+    if (wh == 2 && pi == j0) prp.x = -pv;
+    if (wh == 2 && pi == j1) prp.y = -pv;
+    if (wh == 4 && pi == j0) prp.z = -pv;
+    if (wh == 4 && pi == j1) prp.w = -pv;
+    m.cp[lc * m.cps + mm] = cur;
+    m.cpP[lc * m.cps + mm] = prp;
+  }
+  for (int lc = threadIdx.x; lc < nc; lc += blockDim.x) {
+    const int c = c_base + lc;
+    if (c >= J) continue;
+    const int wh = p.prop_which[c], pi = p.prop_idx[c];
+    const float pv = static_cast<float>(p.prop_xnew[c]);
+    float4 c0 = make_float4(-static_cast<float>(p.g_tc[static_cast<size_t>(c) * S]), -static_cast<float>(p.g_ac[static_cast<size_t>(c) * S]), 0.f, 0.f);
+    c0.z = (wh == 2 && pi == 0) ? -pv : c0.x;
+    c0.w = (wh == 4 && pi == 0) ? -pv : c0.y;
+    m.c0[lc] = c0;
+  }
+  __syncthreads();
+
+  // this lane's chain (slots past chain J-1 clone the quad's first chain and never write)
+  // the 4 chains of one event sit in adjacent lanes: a 16-byte shared-memory read is served per lane pair,
+  // so lanes that share a row must be neighbours (measured: 2 wavefronts per row read against 4 for the
+  // event-minor order; tools/micro/lds_pattern.cu)
+  const int es = lane >> 2, chs = lane & (kQuad - 1);
+  const bool warp_ok = c_base + warp * kQuad < J;
+  const bool c_ok = c_base + warp * kQuad + chs < J;
+  const int lc = c_ok ? warp * kQuad + chs : warp * kQuad;
+  const int c = warp_ok ? c_base + lc : 0;
+  StepIn<float> in;
+  {
+    const double Td = p.g_T[c];
+    in.T = static_cast<float>(Td);
+    in.iT = 1.f / in.T;
+    in.cold = gibbs_is_cold<float>(Td);
+    in.vs = static_cast<float>(p.g_vs[c]);
+    in.qs = static_cast<float>(p.g_qs[c]);
+    in.which = p.prop_which[c];
+    in.pidx = p.prop_idx[c];
+    in.pval = static_cast<float>(p.prop_xnew[c]);
+    in.S = S;
+    in.n_pairs = n_pairs;
+    in.cp = m.cp + lc * m.cps;
+    in.cpP = m.cpP + lc * m.cps;
+    in.c0 = warp_ok ? m.c0[lc] : make_float4(0.f, 0.f, 0.f, 0.f);
+    in.s_sta = nullptr;
+    in.tc = nullptr;
+    in.ac = nullptr;
+  }
+  const bool a_prev = p.a_prev[c] != 0;
+  const int rec_chain_slot = (p.rec_slot >= 0 && p.hypo_rec) ? p.slot_of[c] : -1;
+  double s_cur = 0.0, s_prop = 0.0;
+  uint32_t cnt_p[3] = {0, 0, 0}, cnt_a[3] = {0, 0, 0};
+
+  for (int i = 0; i < n_my; ++i) {
+    const int buf = i & 1;
+    const uint32_t ph = (i >> 1) & 1;
+    const int o = o_begin + i;
+    mbar_wait(m.full + buf, ph);
+    if (warp_ok) {
+      const int n_ev = min(kOct, E - o * kOct);
+      const int e = o * kOct + es;
+      const bool ev_ok = e < E;
+      const int ee = ev_ok ? e : E - 1;  // idle lanes clone the last event and never write
+      in.obs_row = m.rows + (buf * kOct + (ev_ok ? es : n_ev - 1)) * m.row;
+      const size_t ci = static_cast<size_t>(c) * E + ee;
+      const float4 evc = p.evc4[ee];
+      const float mux = reinterpret_cast<const float*>(p.prior_xy)[2 * ee], muy = reinterpret_cast<const float*>(p.prior_xy)[2 * ee + 1];
+      float x = p.hx[ci], y = p.hy[ci], z = p.hz[ci];
+      float Le = a_prev ? p.hLp[ci] : p.hLe[ci];  // lazy commit of the last shared-parameter acceptance
+      float Lp;
+      int icmp;
+      bool acc;
+      gibbs_thread_step<float, TRACE>(p, p.it, in, c, e, ee, ev_ok && c_ok, evc, mux, muy, x, y, z, Le, Lp, icmp, acc, p.trace);
+      if (ev_ok && c_ok) {
+        p.hx[ci] = x;
+        p.hy[ci] = y;
+        p.hz[ci] = z;
+        p.hLe[ci] = Le;
+        p.hLp[ci] = Lp;
+        if (rec_chain_slot >= 0)
+          p.hypo_rec[(static_cast<size_t>(p.rec_slot) * p.n_cool_total + rec_chain_slot) * E + e] = make_float4(x, y, z, Le);
+        s_cur += static_cast<double>(Le);
+        s_prop += static_cast<double>(Lp);
+        if (in.cold) {
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            cnt_p[t] += icmp == t ? 1u : 0u;
+            cnt_a[t] += (icmp == t && acc) ? 1u : 0u;
+          }
+        }
+      }
+    }
+    // release the stage; warp 0 refills it with octet i+2 once every warp has let go of it
+    __syncwarp();
+    if (lane == 0) mbar_arrive(m.empty + buf);
+    if (warp == 0 && i + 2 < n_my) {
+      if (lane == 0) mbar_wait(m.empty + buf, ph);
+      __syncwarp();
+      issue(o + 2, buf);
+    }
+  }
+
+  // per-(chain, CTA) partial sums: the 8 event lanes of a chain in a fixed order
+  if (warp_ok) {
+#pragma unroll
+    for (int off = 16; off >= kQuad; off >>= 1) {
+      s_cur += __shfl_xor_sync(0xffffffffu, s_cur, off);
+      s_prop += __shfl_xor_sync(0xffffffffu, s_prop, off);
+    }
+    if (es == 0 && c_ok) {
+      p.part_cur[static_cast<size_t>(c) * p.n_tiles + blockIdx.x] = s_cur;
+      p.part_prop[static_cast<size_t>(c) * p.n_tiles + blockIdx.x] = s_prop;
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const uint32_t np = warp_sum<uint32_t>(cnt_p[t]), na = warp_sum<uint32_t>(cnt_a[t]);
+      if (lane == 0 && p.counts) {
+        if (np) atomicAdd(p.counts + 4 + t, static_cast<unsigned long long>(np));
+        if (na) atomicAdd(p.counts + 11 + t, static_cast<unsigned long long>(na));
+      }
+    }
+  }
+
+  // ---- the last CTA to finish judges the shared-parameter proposals (as in gibbs_sweep_kernel) ----
+  if (done_counter == nullptr) return;
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(done_counter, 1u);
+    s_last = ticket == gridDim.x * gridDim.y - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    gibbs_decide(dec, smem_raw);
+    if (threadIdx.x == 0) *done_counter = 0u;
+  }
+}
+
 // ---- persistent cooperative kernel: all iterations in one launch -------------------------------------------
 // Every (chain, event) keeps its state in registers, the tile's rows stay in shared memory, the chain-level
 // state of ALL chains lives in every CTA's shared memory.  Per iteration: step -> partial sums to global ->
@@ -1043,6 +1275,37 @@ static int persist_env() {
   const char* v = std::getenv("HTM_GIBBS_PERSIST");
   return v ? std::atoi(v) : -1;
 }
+// HTM_GIBBS_SWEEP=chain|octet fixes the layout of the float32 per-iteration sweep (tests, tuning)
+static int sweep_env() {
+  const char* v = std::getenv("HTM_GIBBS_SWEEP");
+  if (!v) return -1;
+  return std::string(v) == "octet" ? 1 : 0;
+}
+
+// One sweep launch of the per-iteration paths
+struct SweepShape {
+  bool octet = false;  // gibbs_sweep_oq_kernel (float32) instead of gibbs_sweep_kernel
+  int n_warps = kCW;
+  dim3 grid;
+  size_t smem = 0;  // sweep part only
+};
+template <typename real, bool TRACE>
+static cudaError_t sweep_set_smem(const SweepShape& s, size_t smem) {
+  const void* f = reinterpret_cast<const void*>(gibbs_sweep_kernel<real, TRACE>);
+  if (s.octet) f = reinterpret_cast<const void*>(gibbs_sweep_oq_kernel<TRACE>);
+  return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+}
+template <typename real, bool TRACE>
+static void sweep_launch(const SweepShape& s, size_t smem, cudaStream_t stream, const GibbsParams<real>& p,
+                         const GibbsDecide& d, unsigned int* done_counter) {
+  if constexpr (sizeof(real) == 4) {
+    if (s.octet) {
+      gibbs_sweep_oq_kernel<TRACE><<<s.grid, s.n_warps * 32, smem, stream>>>(p, d, done_counter, (p.E + kOct - 1) / kOct);
+      return;
+    }
+  }
+  gibbs_sweep_kernel<real, TRACE><<<s.grid, kCW * 32, smem, stream>>>(p, d, done_counter);
+}
 
 template <typename real, bool TRACE>
 static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, int* n_launches) {
@@ -1050,11 +1313,52 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
   GibbsDecide d = make_decide(a);
   const size_t sm_sweep = sweep_smem<real>(a.S), sm_chain = chain_sm_bytes(a.J, a.S);
   if (sm_sweep > 200 * 1024 || sm_chain > 200 * 1024) return cudaErrorInvalidConfiguration;
-  const size_t smem_iter = sm_sweep > sm_chain ? sm_sweep : sm_chain;  // the last CTA reuses its smem for the decide
+  SweepShape shape;
+  shape.grid = dim3(p.n_tiles, (a.J + kCW - 1) / kCW);
+  shape.smem = sm_sweep;
+  // the last CTA reuses its shared memory for the decide step
+  size_t smem_iter = sm_sweep > sm_chain ? sm_sweep : sm_chain;
+  GibbsParams<real> ps = p;  // what the per-iteration sweeps see
+  GibbsDecide ds = d;
+  cudaError_t err = cudaSuccess;
+  if constexpr (sizeof(real) == 4) {
+    // octet layout: one wave of CTAs, each walking a contiguous range of event octets with the terms of up to
+    // 32 chains in shared memory; worth its set-up cost once every CTA gets a few octets
+    const int quads = (a.J + kQuad - 1) / kQuad;
+    const int gy = (quads + kCW - 1) / kCW;
+    const int n_warps = (quads + gy - 1) / gy;
+    const size_t sm_oq = oq_smem(a.S, n_warps * kQuad);
+    const size_t smem_oq = sm_oq > sm_chain ? sm_oq : sm_chain;
+    const int want = sweep_env();
+    if (want != 0 && smem_oq <= 200 * 1024) {
+      err = cudaFuncSetAttribute(gibbs_sweep_oq_kernel<TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem_oq));
+      if (err != cudaSuccess) return err;
+      int per_sm = 0, dev = 0, n_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_sweep_oq_kernel<TRACE>, n_warps * 32, smem_oq);
+      if (err != cudaSuccess) return err;
+      const long n_oct = (a.E + kOct - 1) / kOct;
+      long gx = static_cast<long>(per_sm) * n_sm / gy;
+      const bool pays = gx >= 1 && n_oct >= 3 * gx;
+      if (gx > n_oct) gx = n_oct;
+      if (gx > 2L * p.n_tiles) gx = 2L * p.n_tiles;  // the partial-sum buffers hold 2 x ceil(E/32) entries per chain
+      if (gx >= 1 && (want == 1 || pays)) {
+        shape.octet = true;
+        shape.n_warps = n_warps;
+        shape.grid = dim3(static_cast<unsigned>(gx), gy);
+        shape.smem = sm_oq;
+        smem_iter = smem_oq;
+        ps.n_tiles = ds.n_tiles = static_cast<int>(gx);  // one partial sum per (chain, CTA)
+        ps.part_prop = ps.part_cur + static_cast<size_t>(a.J) * gx;
+        ds.part_prop = ps.part_prop;
+      }
+    }
+  }
   const size_t smem_pers = sm_sweep + sm_chain;
-  const dim3 grid(p.n_tiles, (a.J + kCW - 1) / kCW);
-  cudaError_t err = cudaFuncSetAttribute(gibbs_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sm_chain));
+  const dim3 grid(p.n_tiles, (a.J + kCW - 1) / kCW);  // persistent kernel: one chain per warp
+  err = cudaFuncSetAttribute(gibbs_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_chain));
   if (err != cudaSuccess) return err;
   int nl = 0;
   // prepare: cold slots + the proposal of the first iteration (a pure function of state and iteration)
@@ -1065,28 +1369,27 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
 
   // ---- event-sharded joint chains: sweep -> local totals -> all-reduce -> decide (replicated) ----
   if (a.comm) {
-    err = cudaFuncSetAttribute(gibbs_sweep_kernel<real, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem_iter));
+    err = sweep_set_smem<real, TRACE>(shape, smem_iter);
     if (err != cudaSuccess) return err;
     const size_t per_it_s = static_cast<size_t>(a.E + 1) * a.J;
     std::string why;
     for (int it = a.iter_first; it <= a.iter_last; ++it) {
       const bool rec = a.n_interval > 1 && (it % a.n_interval) == 1;
       const int slot = rec ? (it - 1) / a.n_interval - a.rec_origin : -1;
-      p.it = it;
-      p.rec_slot = (slot >= 0 && slot < a.rec_cap) ? slot : -1;
-      p.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it_s : nullptr;
-      gibbs_sweep_kernel<real, TRACE><<<grid, kCW * 32, smem_iter, stream>>>(p, d, nullptr);
-      gibbs_totals_kernel<<<(a.J + 3) / 4, 128, 0, stream>>>(p.part_cur, p.part_prop, a.J, p.n_tiles, a.totals);
+      ps.it = it;
+      ps.rec_slot = (slot >= 0 && slot < a.rec_cap) ? slot : -1;
+      ps.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it_s : nullptr;
+      sweep_launch<real, TRACE>(shape, smem_iter, stream, ps, ds, nullptr);
+      gibbs_totals_kernel<<<(a.J + 3) / 4, 128, 0, stream>>>(ps.part_cur, ps.part_prop, a.J, ps.n_tiles, a.totals);
       if (!nccl_allreduce_f64(a.comm, a.totals, a.totals, 2 * static_cast<size_t>(a.J), stream, &why))
         return cudaErrorUnknown;
-      GibbsDecide dd = d;
+      GibbsDecide dd = ds;
       dd.n_tiles = 1;  // the "partials" are now the global per-chain sums
       dd.part_cur = a.totals;
       dd.part_prop = a.totals + a.J;
       dd.it = it;
       dd.it_next = it + 1;
-      dd.rec_slot = p.rec_slot;
+      dd.rec_slot = ps.rec_slot;
       dd.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it_s + static_cast<size_t>(a.E) * a.J : nullptr;
       dd.swap = a.swaps ? a.swaps + (it - a.iter_first) : nullptr;
       gibbs_decide_kernel<<<1, 256, sm_chain, stream>>>(dd);
@@ -1126,22 +1429,21 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
   }
 
   // ---- one launch per iteration: the sweep, and in its last CTA the chain-level decide step ----
-  err = cudaFuncSetAttribute(gibbs_sweep_kernel<real, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem_iter));
+  err = sweep_set_smem<real, TRACE>(shape, smem_iter);
   if (err != cudaSuccess) return err;
   const size_t per_it = static_cast<size_t>(a.E + 1) * a.J;
   for (int it = a.iter_first; it <= a.iter_last; ++it) {
     const bool rec = a.n_interval > 1 && (it % a.n_interval) == 1;
     const int slot = rec ? (it - 1) / a.n_interval - a.rec_origin : -1;
-    p.it = it;
-    p.rec_slot = (slot >= 0 && slot < a.rec_cap) ? slot : -1;
-    p.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it : nullptr;
-    d.it = it;
-    d.it_next = it + 1;
-    d.rec_slot = p.rec_slot;
-    d.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it + static_cast<size_t>(a.E) * a.J : nullptr;
-    d.swap = a.swaps ? a.swaps + (it - a.iter_first) : nullptr;
-    gibbs_sweep_kernel<real, TRACE><<<grid, kCW * 32, smem_iter, stream>>>(p, d, a.done_counter);
+    ps.it = it;
+    ps.rec_slot = (slot >= 0 && slot < a.rec_cap) ? slot : -1;
+    ps.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it : nullptr;
+    ds.it = it;
+    ds.it_next = it + 1;
+    ds.rec_slot = ps.rec_slot;
+    ds.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it + static_cast<size_t>(a.E) * a.J : nullptr;
+    ds.swap = a.swaps ? a.swaps + (it - a.iter_first) : nullptr;
+    sweep_launch<real, TRACE>(shape, smem_iter, stream, ps, ds, a.done_counter);
     ++nl;
   }
   if (n_launches) *n_launches = nl;

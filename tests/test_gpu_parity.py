@@ -550,6 +550,40 @@ def test_blocked_gibbs_persistent_and_per_iteration_paths_are_bit_identical(monk
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+@pytest.mark.parametrize("E,S,R,K", [(300, 20, 3, 4), (77, 13, 5, 5), (33, 50, 1, 3), (200, 8, 9, 8), (10, 1, 2, 2)])
+def test_blocked_gibbs_sweep_layouts_are_bit_identical(monkeypatch, E, S, R, K):
+    """HTM_GIBBS_SWEEP = layout of the float32 per-iteration sweep: chain (warp = chain, lane = event) or octet
+    (warp = 8 events x 4 chains, the CTA walks event octets through a TMA ring)."""
+    syn = H.Synthetic(E, S, 8)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_iter=60, n_burn=10, n_interval=10,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=16)
+    monkeypatch.setenv("HTM_GIBBS_PERSIST", "0")
+    res = []
+    for layout in ("chain", "octet"):
+        monkeypatch.setenv("HTM_GIBBS_SWEEP", layout)
+        with H.HypoTremorB200(cfg) as g:
+            g.load(syn)
+            g.init_chains()
+            tr, sw = g.run_traced(1, 25)
+            g.run(26, 60)
+            res.append(([g.get_chain_state(r, k) for r in range(R) for k in range(K)], g.get_counts(),
+                        [g.fetch_samples(r) for r in range(R)], [g.fetch_likelihood(r) for r in range(R)], tr, sw))
+    for other in res[1:]:
+        for a, b in zip(res[0][0], other[0]):
+            assert np.array_equal(a["hypo"], b["hypo"]) and a["vs"] == b["vs"] and a["qs"] == b["qs"]
+            assert np.array_equal(a["t_corr"], b["t_corr"]) and np.array_equal(a["a_corr"], b["a_corr"])
+            assert a["temp"] == b["temp"] and a["log_likelihood"] == b["log_likelihood"]
+        assert np.array_equal(res[0][1][0], other[1][0]) and np.array_equal(res[0][1][1], other[1][1])
+        for a, b in zip(res[0][2], other[2]):
+            assert np.array_equal(a["iter"], b["iter"]) and np.array_equal(a["hypo"], b["hypo"]) and np.array_equal(a["vs"], b["vs"])
+        for a, b in zip(res[0][3], other[3]):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        for f in FLAGS:
+            assert np.array_equal(res[0][4][f], other[4][f]), f
+        assert np.array_equal(res[0][4]["log_likelihood"], other[4]["log_likelihood"])
+        assert np.array_equal(res[0][5], other[5])
+
+
 def test_blocked_gibbs_chunked_runs_equal_one_run():
     syn = H.Synthetic(100, 20, 3)
     cfg = H.default_config(n_sta=20, n_events=100, n_procs=2, n_chains=4, n_iter=80, n_burn=0, n_interval=10,
