@@ -21,6 +21,8 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 namespace htmio {
@@ -139,28 +141,72 @@ inline std::vector<int> read_selected_windows(const std::string& path) {
 // obs arrays in Fortran (n_sta, n_events) column-major order == C [n_events][n_sta]
 struct Observations {
   std::vector<double> t_obs, t_stdv, a_obs, a_stdv;
-  void read(const std::vector<int>& win_id, int n_sta, const std::string& dir = ".") {
+  // One opt_data.NNNNNN.dat per event (src/cls_obs_data.f90:83-112 opens them one after the other on every
+  // rank).  Here the events are split over host threads and every file is read in one piece: at 10^4-10^5
+  // events this stage would otherwise dominate the wall clock once the chains run on the GPU.
+  void read(const std::vector<int>& win_id, int n_sta, const std::string& dir = ".", unsigned n_threads = 0) {
     const size_t E = win_id.size();
     t_obs.resize(E * n_sta);
     t_stdv.resize(E * n_sta);
     a_obs.resize(E * n_sta);
     a_stdv.resize(E * n_sta);
-    char fname[64];
-    for (size_t i = 0; i < E; ++i) {
-      std::snprintf(fname, sizeof(fname), "opt_data.%06d.dat", win_id[i]);
-      std::ifstream in(dir + "/" + fname);
-      if (!in) throw std::runtime_error(std::string("ERROR: obs_file is not found: ") + fname);
-      for (int j = 0; j < n_sta; ++j) {
-        std::string c[7];
-        for (auto& s : c)
-          if (!(in >> s)) throw std::runtime_error(std::string("short obs file ") + fname);
-        const size_t k = i * n_sta + j;
-        t_obs[k] = parse_real("t_obs", c[3]);
-        t_stdv[k] = parse_real("t_stdv", c[4]);
-        a_obs[k] = parse_real("a_obs", c[5]);
-        a_stdv[k] = parse_real("a_stdv", c[6]);
+    if (n_threads == 0) n_threads = std::max(1u, std::thread::hardware_concurrency());
+    n_threads = static_cast<unsigned>(std::min<size_t>(n_threads, std::max<size_t>(1, E / 64)));
+    std::mutex err_lock;
+    std::string first_error;
+    size_t first_error_event = E;
+    auto work = [&](size_t i0, size_t i1) {
+      std::string buf, tok;
+      char fname[64];
+      for (size_t i = i0; i < i1; ++i) {
+        try {
+          std::snprintf(fname, sizeof(fname), "opt_data.%06d.dat", win_id[i]);
+          const std::string path = dir + "/" + fname;
+          FILE* f = std::fopen(path.c_str(), "rb");
+          if (!f) throw std::runtime_error(std::string("ERROR: obs_file is not found: ") + fname);
+          buf.clear();
+          char chunk[16384];
+          size_t got;
+          while ((got = std::fread(chunk, 1, sizeof(chunk), f)) > 0) buf.append(chunk, got);
+          std::fclose(f);
+          // list-directed reals: 7 per station, separated by blanks, commas or line ends
+          size_t pos = 0;
+          auto next = [&]() -> bool {
+            while (pos < buf.size() && (std::isspace(static_cast<unsigned char>(buf[pos])) || buf[pos] == ',')) ++pos;
+            if (pos >= buf.size()) return false;
+            const size_t b0 = pos;
+            while (pos < buf.size() && !std::isspace(static_cast<unsigned char>(buf[pos])) && buf[pos] != ',') ++pos;
+            tok.assign(buf, b0, pos - b0);
+            return true;
+          };
+          for (int j = 0; j < n_sta; ++j) {
+            const size_t k = i * n_sta + j;
+            for (int c = 0; c < 7; ++c) {
+              if (!next()) throw std::runtime_error(std::string("short obs file ") + fname);
+              if (c == 3) t_obs[k] = parse_real("t_obs", tok);
+              if (c == 4) t_stdv[k] = parse_real("t_stdv", tok);
+              if (c == 5) a_obs[k] = parse_real("a_obs", tok);
+              if (c == 6) a_stdv[k] = parse_real("a_stdv", tok);
+            }
+          }
+        } catch (const std::exception& e) {
+          std::lock_guard<std::mutex> g(err_lock);
+          if (i < first_error_event) {  // report what the sequential reader would have hit first
+            first_error_event = i;
+            first_error = e.what();
+          }
+          return;
+        }
       }
+    };
+    if (n_threads <= 1) {
+      work(0, E);
+    } else {
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < n_threads; ++t) pool.emplace_back(work, E * t / n_threads, E * (t + 1) / n_threads);
+      for (auto& th : pool) th.join();
     }
+    if (first_error_event < E) throw std::runtime_error(first_error);
   }
   // obs%make_initial_guess (src/cls_obs_data.f90:120-134): station of the FIRST maximum of a_obs
   void initial_guess(const Stations& st, std::vector<double>& x_mu, std::vector<double>& y_mu) const {

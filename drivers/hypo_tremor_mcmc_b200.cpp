@@ -3,12 +3,13 @@
 // same order, so the boundary is exercised end to end in an image that has no Fortran compiler.
 //
 //   hypo_tremor_mcmc_b200 <parameter file> [--precision 32|64] [--seed N] [--little-endian]
-//                         [--chunk RECORDS] [--dry-run]
+//                         [--chunk RECORDS] [--dry-run] [--loader-threads N]
 //
 // Inputs in the working directory as for the reference (src/hypo_tremor_mcmc.f90:53-98): the
 // parameter file's station_file, selected_win.dat, opt_data.NNNNNN.dat.  Outputs: hypo.RR.out,
 // t_corr.RR.out, vs.RR.out, a_corr.RR.out, qs.RR.out, likelihoodRR.out per virtual rank RR, and
 // proposal_count.txt.  n_procs of the parameter file = number of virtual ranks (no MPI).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -30,6 +31,7 @@ int main(int argc, char** argv) {
   int precision = 32, chunk = 64;
   unsigned long long seed = 20231001ull;
   bool big_endian = true, dry = false;
+  unsigned loader_threads = 0;  // 0 = all host cores
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--precision" && i + 1 < argc) precision = std::atoi(argv[++i]);
@@ -37,6 +39,7 @@ int main(int argc, char** argv) {
     else if (a == "--chunk" && i + 1 < argc) chunk = std::atoi(argv[++i]);
     else if (a == "--little-endian") big_endian = false;
     else if (a == "--dry-run") dry = true;
+    else if (a == "--loader-threads" && i + 1 < argc) loader_threads = static_cast<unsigned>(std::atoi(argv[++i]));
     else if (param_file.empty()) param_file = a;
     else param_file = "?";
   }
@@ -52,7 +55,10 @@ int main(int argc, char** argv) {
     const std::vector<int> win_id = htmio::read_selected_windows("selected_win.dat");
     const int n_sta = static_cast<int>(sta.x.size()), n_events = static_cast<int>(win_id.size());
     htmio::Observations obs;
-    obs.read(win_id, n_sta);
+    const auto t_load = std::chrono::steady_clock::now();
+    obs.read(win_id, n_sta, ".", loader_threads);
+    std::printf("read %d observation files in %.3f s\n", n_events,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count());
     std::vector<double> x_mu, y_mu;
     obs.initial_guess(sta, x_mu, y_mu);
 
