@@ -58,8 +58,10 @@ def parse():
 
 
 def workload_name(a, n_gpus):
-    return ("%d synthetic events x %d stations x %d temperatures x %d chains per GPU (BASELINE configs[1])"
-            % (a.events, a.stations, a.chains, a.ranks))
+    shape = (a.events, a.stations, a.chains, a.ranks)
+    tag = {(1000, 20, 16, 4): "BASELINE configs[1]", (10000, 50, 16, 4): "events x stations of BASELINE configs[2]",
+           (12500, 50, 16, 4): "BASELINE configs[3] when run on 8 GPUs"}.get(shape, "not a BASELINE config")
+    return "%d synthetic events x %d stations x %d temperatures x %d chains per GPU (%s)" % (shape + (tag,))
 
 
 def make_cfg(H, a, n_events_total, shard_rank, shard_count, device, max_samples, hist_bins):
