@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
     htmio::Observations obs;
     const auto t_load = std::chrono::steady_clock::now();
     obs.read(win_id, n_sta, ".", loader_threads);
-    std::printf("read %d observation files in %.3f s\n", n_events,
+    std::fprintf(stderr, "read %d observation files in %.3f s\n", n_events,
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count());
     std::vector<double> x_mu, y_mu;
     obs.initial_guess(sta, x_mu, y_mu);
