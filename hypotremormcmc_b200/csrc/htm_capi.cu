@@ -271,7 +271,10 @@ int32_t alloc_state(htm_handle h) {
   HTM_CK(h, cudaMemset(h->d_counts, 0, 14 * sizeof(unsigned long long)));
   if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
     GibbsLaunch& g = h->gl;
-    const size_t J = h->C, E = h->E, S = h->S, nt = (E + 31) / 32;
+    const size_t J = h->C, E = h->E, S = h->S;
+    // partial sums per chain: one per 32-event tile, or one per CTA of a one-wave grid (at most 8 CTAs per SM)
+    const size_t nt = std::max<size_t>((E + 31) / 32, 8 * 160);
+    g.part_tiles = static_cast<int>(nt);
     h->n_cold_total = h->R * h->cfg.n_cool;
     auto grab = [&](void** p, size_t bytes) -> cudaError_t {
       cudaError_t e = cudaMalloc(p, bytes ? bytes : 8);

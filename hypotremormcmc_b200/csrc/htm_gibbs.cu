@@ -676,6 +676,25 @@ __device__ __forceinline__ void tile_sums_and_counts(const GibbsParams<real>& p,
   }
 }
 
+// Tail of both sweep kernels: the last CTA to finish judges the shared-parameter proposals (fixed-order sums:
+// deterministic), reusing its shared memory for the chain-level state.  Every thread of the CTA must call it.
+__device__ __forceinline__ void last_cta_decides(const GibbsDecide& dec, unsigned int* done_counter, unsigned char* smem) {
+  if (done_counter == nullptr) return;  // event-sharded run: totals -> all-reduce -> decide are separate launches
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // the CTA's partial sums (ordered before by the barrier) become visible device-wide
+    const unsigned int ticket = atomicAdd(done_counter, 1u);
+    s_last = ticket == gridDim.x * gridDim.y - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    gibbs_decide(dec, smem);
+    if (threadIdx.x == 0) *done_counter = 0u;
+  }
+}
+
 // ---- one iteration per launch: sweep + (last CTA) decide --------------------------------------------------
 template <typename real, bool TRACE>
 __global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsParams<real> p, const GibbsDecide dec,
@@ -733,21 +752,7 @@ __global__ void __launch_bounds__(kCW * 32, 3) gibbs_sweep_kernel(const GibbsPar
     tile_sums_and_counts<real>(p, p.part_cur, p.part_prop, c, tile, ev_ok, in.cold, Le, Lp, icmp, acc);
   }
 
-  // ---- the last CTA to finish judges the shared-parameter proposals (fixed-order sums: deterministic) ----
-  if (done_counter == nullptr) return;  // event-sharded run: totals -> all-reduce -> decide are separate launches
-  __shared__ int s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();  // the CTA's partial sums (ordered before by the barrier) become visible device-wide
-    const unsigned int ticket = atomicAdd(done_counter, 1u);
-    s_last = ticket == gridDim.x * gridDim.y - 1 ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    gibbs_decide(dec, smem_raw);
-    if (threadIdx.x == 0) *done_counter = 0u;
-  }
+  last_cta_decides(dec, done_counter, smem_raw);
 }
 
 // ---- float32 sweep for large E: warp = 8 events x 4 chains, CTA loops over event octets --------------------
@@ -789,6 +794,45 @@ __device__ __forceinline__ OqSm carve_oq_sm(unsigned char* base, int S, int xrow
   return m;
 }
 
+// the station terms of the CTA's nc chains (current and with the pending proposal applied), all threads
+__device__ __forceinline__ void oq_stage_chain_terms(const OqSm& m, int nc, int c_base, int J, int S, const double* tc,
+                                                     const double* ac, const int* which, const int* idx,
+                                                     const double* xnew) {
+  const int n_pairs = S / 2;
+  for (int i = threadIdx.x; i < nc * n_pairs; i += blockDim.x) {
+    const int lc = i / n_pairs, mm = i - lc * n_pairs, c = c_base + lc;
+    if (c >= J) continue;
+    const double* gtc = tc + static_cast<size_t>(c) * S;
+    const double* gac = ac + static_cast<size_t>(c) * S;
+    const int wh = which[c], pi = idx[c];
+    const float pv = static_cast<float>(xnew[c]);
+    const int j0 = 1 + 2 * mm, j1 = j0 + 1;
+    float4 cur = make_float4(-static_cast<float>(gtc[j0]), 0.f, -static_cast<float>(gac[j0]), 0.f);
+    if (j1 < S) {
+      cur.y = -static_cast<float>(gtc[j1]);
+      cur.w = -static_cast<float>(gac[j1]);
+    }
+    float4 prp = cur;
+    if (wh == 2 && pi == j0) prp.x = -pv;
+    if (wh == 2 && pi == j1) prp.y = -pv;
+    if (wh == 4 && pi == j0) prp.z = -pv;
+    if (wh == 4 && pi == j1) prp.w = -pv;
+    m.cp[lc * m.cps + mm] = cur;
+    m.cpP[lc * m.cps + mm] = prp;
+  }
+  for (int lc = threadIdx.x; lc < nc; lc += blockDim.x) {
+    const int c = c_base + lc;
+    if (c >= J) continue;
+    const int wh = which[c], pi = idx[c];
+    const float pv = static_cast<float>(xnew[c]);
+    float4 c0 = make_float4(-static_cast<float>(tc[static_cast<size_t>(c) * S]), -static_cast<float>(ac[static_cast<size_t>(c) * S]),
+                            0.f, 0.f);
+    c0.z = (wh == 2 && pi == 0) ? -pv : c0.x;
+    c0.w = (wh == 4 && pi == 0) ? -pv : c0.y;
+    m.c0[lc] = c0;
+  }
+}
+
 template <bool TRACE>
 __global__ void __launch_bounds__(kCW * 32, 2) gibbs_sweep_oq_kernel(const GibbsParams<float> p, const GibbsDecide dec,
                                                                      unsigned int* done_counter, const int n_oct) {
@@ -825,37 +869,7 @@ __global__ void __launch_bounds__(kCW * 32, 2) gibbs_sweep_oq_kernel(const Gibbs
     if (n_my > 1) issue(o_begin + 1, 1);
   }
   // the CTA's chain terms (once per launch)
-  for (int i = threadIdx.x; i < nc * n_pairs; i += blockDim.x) {
-    const int lc = i / n_pairs, mm = i - lc * n_pairs, c = c_base + lc;
-    if (c >= J) continue;
-    const double* gtc = p.g_tc + static_cast<size_t>(c) * S;
-    const double* gac = p.g_ac + static_cast<size_t>(c) * S;
-    const int wh = p.prop_which[c], pi = p.prop_idx[c];
-    const float pv = static_cast<float>(p.prop_xnew[c]);
-    const int j0 = 1 + 2 * mm, j1 = j0 + 1;
-    float4 cur = make_float4(-static_cast<float>(gtc[j0]), 0.f, -static_cast<float>(gac[j0]), 0.f);
-    if (j1 < S) {
-      cur.y = -static_cast<float>(gtc[j1]);
-      cur.w = -static_cast<float>(gac[j1]);
-    }
-    float4 prp = cur;
-    if (wh == 2 && pi == j0) prp.x = -pv;
-    if (wh == 2 && pi == j1) prp.y = -pv;
-    if (wh == 4 && pi == j0) prp.z = -pv;
-    if (wh == 4 && pi == j1) prp.w = -pv;
-    m.cp[lc * m.cps + mm] = cur;
-    m.cpP[lc * m.cps + mm] = prp;
-  }
-  for (int lc = threadIdx.x; lc < nc; lc += blockDim.x) {
-    const int c = c_base + lc;
-    if (c >= J) continue;
-    const int wh = p.prop_which[c], pi = p.prop_idx[c];
-    const float pv = static_cast<float>(p.prop_xnew[c]);
-    float4 c0 = make_float4(-static_cast<float>(p.g_tc[static_cast<size_t>(c) * S]), -static_cast<float>(p.g_ac[static_cast<size_t>(c) * S]), 0.f, 0.f);
-    c0.z = (wh == 2 && pi == 0) ? -pv : c0.x;
-    c0.w = (wh == 4 && pi == 0) ? -pv : c0.y;
-    m.c0[lc] = c0;
-  }
+  oq_stage_chain_terms(m, nc, c_base, J, S, p.g_tc, p.g_ac, p.prop_which, p.prop_idx, p.prop_xnew);
   __syncthreads();
 
   // this lane's chain (slots past chain J-1 clone the quad's first chain and never write)
@@ -962,21 +976,7 @@ __global__ void __launch_bounds__(kCW * 32, 2) gibbs_sweep_oq_kernel(const Gibbs
     }
   }
 
-  // ---- the last CTA to finish judges the shared-parameter proposals (as in gibbs_sweep_kernel) ----
-  if (done_counter == nullptr) return;
-  __shared__ int s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int ticket = atomicAdd(done_counter, 1u);
-    s_last = ticket == gridDim.x * gridDim.y - 1 ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    gibbs_decide(dec, smem_raw);
-    if (threadIdx.x == 0) *done_counter = 0u;
-  }
+  last_cta_decides(dec, done_counter, smem_raw);
 }
 
 // ---- persistent cooperative kernel: all iterations in one launch -------------------------------------------
@@ -1149,6 +1149,178 @@ __global__ void gibbs_total_kernel(const real* hLe, int E, int J, double* g_L) {
   if (lane == 0) g_L[c] = a;
 }
 
+// ---- persistent octet sweep: every iteration of a run in one cooperative launch, any E ----------------------
+// gibbs_sweep_oq_kernel with the iteration loop inside: the grid is one wave of CTAs by construction, so the
+// per-iteration launch, the re-staging of the chain terms from global memory and the single-CTA decide tail
+// are replaced by ONE grid barrier per iteration and a decide step taken redundantly (and identically) by
+// every CTA on its own shared-memory copy of the chain-level state, as in gibbs_persist_kernel.  Hypocentre
+// state stays in global memory (L2): a (chain, event) is always visited by the same thread.  The TMA ring runs
+// across iteration boundaries (rows never change), so the first octets of iteration i+1 arrive during the
+// barrier and decide step of iteration i.
+template <bool TRACE>
+__global__ void __launch_bounds__(kCW * 32, 2) gibbs_persist_oq_kernel(const GibbsParams<float> p, const GibbsDecide d,
+                                                                       const int iter_first, const int iter_last,
+                                                                       const int rec_origin, const int rec_cap,
+                                                                       htm_step_trace* trace_base, htm_swap_trace* swap_base,
+                                                                       double* part /* [2][2][J][gridDim.x] */,
+                                                                       const int n_oct) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::grid_group grid = cg::this_grid();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const int S = p.S, J = p.J, E = p.E, n_pairs = S / 2;
+  const int nc = n_warps * kQuad;
+  const int c_base = blockIdx.y * nc;
+  const bool writer = blockIdx.x == 0 && blockIdx.y == 0;
+  const OqSm m = carve_oq_sm(smem_raw, S, p.xrow, nc);
+  const ChainSm cs = carve_chain_sm(smem_raw + oq_smem(S, nc), J, S);
+  const int o_begin = static_cast<int>(static_cast<long>(n_oct) * blockIdx.x / gridDim.x);
+  const int o_end = static_cast<int>(static_cast<long>(n_oct) * (blockIdx.x + 1) / gridDim.x);
+  const int n_my = o_end - o_begin;  // >= 1: the launcher never starts more CTAs per chain group than octets
+  const long n_run = static_cast<long>(n_my) * (iter_last - iter_first + 1);  // octet visits of this CTA
+  const uint32_t row_bytes = static_cast<uint32_t>(p.xrow * sizeof(float4));
+  if (threadIdx.x == 0) {
+    mbar_init(m.full, 1);
+    mbar_init(m.full + 1, 1);
+    mbar_init(m.empty, n_warps);
+    mbar_init(m.empty + 1, n_warps);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  auto issue = [&](long t) {  // visit t of this CTA -> ring stage t & 1
+    const int buf = static_cast<int>(t & 1), o = o_begin + static_cast<int>(t % n_my);
+    const int n_ev = min(kOct, E - o * kOct);
+    if (lane == 0) mbar_expect_tx(m.full + buf, row_bytes * n_ev);
+    __syncwarp();
+    if (lane < n_ev)
+      tma_load_1d(m.rows + (buf * kOct + lane) * m.row, p.obsx + static_cast<size_t>(o * kOct + lane) * p.xrow, row_bytes,
+                  m.full + buf);
+  };
+  if (warp == 0) {
+    if (n_run > 0) issue(0);
+    if (n_run > 1) issue(1);
+  }
+  chain_load(d, cs);
+  __syncthreads();
+
+  const int es = lane >> 2, chs = lane & (kQuad - 1);  // chain minor: see gibbs_sweep_oq_kernel
+  const bool warp_ok = c_base + warp * kQuad < J;
+  const bool c_ok = c_base + warp * kQuad + chs < J;
+  const int lc = c_ok ? warp * kQuad + chs : warp * kQuad;
+  const int c = warp_ok ? c_base + lc : 0;
+  const size_t per_it = static_cast<size_t>(E + 1) * J, psz = static_cast<size_t>(J) * gridDim.x;
+  uint32_t cnt_p[3] = {0, 0, 0}, cnt_a[3] = {0, 0, 0};
+  long t_run = 0;
+
+  for (int it = iter_first; it <= iter_last; ++it) {
+    double* part_cur = part + static_cast<size_t>(it & 1) * 2 * psz;
+    double* part_prop = part_cur + psz;
+    const bool rec = p.n_interval > 1 && (it % p.n_interval) == 1;
+    int rec_slot = rec ? (it - 1) / p.n_interval - rec_origin : -1;
+    if (rec_slot >= rec_cap) rec_slot = -1;
+    htm_step_trace* trace_it = trace_base ? trace_base + static_cast<size_t>(it - iter_first) * per_it : nullptr;
+    // the CTA's chain terms for this iteration, from the shared-memory chain state (decide_core ended with a
+    // block barrier; the previous iteration's reads of cp/cpP are over)
+    oq_stage_chain_terms(m, nc, c_base, J, S, cs.tc, cs.ac, cs.which, cs.idx, cs.xnew);
+    __syncthreads();
+    StepIn<float> in;
+    {
+      const double Td = cs.T[c];
+      in.T = static_cast<float>(Td);
+      in.iT = 1.f / in.T;
+      in.cold = gibbs_is_cold<float>(Td);
+      in.vs = static_cast<float>(cs.vs[c]);
+      in.qs = static_cast<float>(cs.qs[c]);
+      in.which = cs.which[c];
+      in.pidx = cs.idx[c];
+      in.pval = static_cast<float>(cs.xnew[c]);
+      in.S = S;
+      in.n_pairs = n_pairs;
+      in.cp = m.cp + lc * m.cps;
+      in.cpP = m.cpP + lc * m.cps;
+      in.c0 = warp_ok ? m.c0[lc] : make_float4(0.f, 0.f, 0.f, 0.f);
+      in.s_sta = nullptr;
+      in.tc = nullptr;
+      in.ac = nullptr;
+    }
+    const bool a_prev = cs.aprev[c] != 0;
+    const int rec_chain_slot = (rec_slot >= 0 && p.hypo_rec) ? cs.slot[c] : -1;
+    double s_cur = 0.0, s_prop = 0.0;
+    for (int i = 0; i < n_my; ++i, ++t_run) {
+      const int buf = static_cast<int>(t_run & 1);
+      const uint32_t ph = static_cast<uint32_t>((t_run >> 1) & 1);
+      const int o = o_begin + i;
+      mbar_wait(m.full + buf, ph);
+      if (warp_ok) {
+        const int n_ev = min(kOct, E - o * kOct);
+        const int e = o * kOct + es;
+        const bool ev_ok = e < E;
+        const int ee = ev_ok ? e : E - 1;
+        in.obs_row = m.rows + (buf * kOct + (ev_ok ? es : n_ev - 1)) * m.row;
+        const size_t ci = static_cast<size_t>(c) * E + ee;
+        const float4 evc = p.evc4[ee];
+        const float mux = reinterpret_cast<const float*>(p.prior_xy)[2 * ee], muy = reinterpret_cast<const float*>(p.prior_xy)[2 * ee + 1];
+        float x = p.hx[ci], y = p.hy[ci], z = p.hz[ci];
+        float Le = a_prev ? p.hLp[ci] : p.hLe[ci];  // lazy commit of the last shared-parameter acceptance
+        float Lp;
+        int icmp;
+        bool acc;
+        gibbs_thread_step<float, TRACE>(p, it, in, c, e, ee, ev_ok && c_ok, evc, mux, muy, x, y, z, Le, Lp, icmp, acc, trace_it);
+        if (ev_ok && c_ok) {
+          p.hx[ci] = x;
+          p.hy[ci] = y;
+          p.hz[ci] = z;
+          p.hLe[ci] = Le;
+          p.hLp[ci] = Lp;
+          if (rec_chain_slot >= 0)
+            p.hypo_rec[(static_cast<size_t>(rec_slot) * p.n_cool_total + rec_chain_slot) * E + e] = make_float4(x, y, z, Le);
+          s_cur += static_cast<double>(Le);
+          s_prop += static_cast<double>(Lp);
+          if (in.cold) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              cnt_p[t] += icmp == t ? 1u : 0u;
+              cnt_a[t] += (icmp == t && acc) ? 1u : 0u;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(m.empty + buf);
+      if (warp == 0 && t_run + 2 < n_run) {
+        if (lane == 0) mbar_wait(m.empty + buf, ph);
+        __syncwarp();
+        issue(t_run + 2);
+      }
+    }
+    if (warp_ok) {
+#pragma unroll
+      for (int off = 16; off >= kQuad; off >>= 1) {
+        s_cur += __shfl_xor_sync(0xffffffffu, s_cur, off);
+        s_prop += __shfl_xor_sync(0xffffffffu, s_prop, off);
+      }
+      if (es == 0 && c_ok) {
+        part_cur[static_cast<size_t>(c) * gridDim.x + blockIdx.x] = s_cur;
+        part_prop[static_cast<size_t>(c) * gridDim.x + blockIdx.x] = s_prop;
+      }
+    }
+    grid.sync();
+    decide_core(d, cs, it, it + 1, part_cur, part_prop, rec_slot, trace_it ? trace_it + static_cast<size_t>(E) * J : nullptr,
+                swap_base ? swap_base + (it - iter_first) : nullptr, writer);
+  }
+  if (warp_ok) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const uint32_t np = warp_sum<uint32_t>(cnt_p[t]), na = warp_sum<uint32_t>(cnt_a[t]);
+      if (lane == 0 && p.counts) {
+        if (np) atomicAdd(p.counts + 4 + t, static_cast<unsigned long long>(np));
+        if (na) atomicAdd(p.counts + 11 + t, static_cast<unsigned long long>(na));
+      }
+    }
+  }
+  if (writer) chain_store(d, cs);
+}
+
 // ---- host launchers ---------------------------------------------------------------------------------
 template <typename real>
 static GibbsParams<real> make_gibbs_params(const GibbsLaunch& a) {
@@ -1275,7 +1447,7 @@ static int persist_env() {
   const char* v = std::getenv("HTM_GIBBS_PERSIST");
   return v ? std::atoi(v) : -1;
 }
-// HTM_GIBBS_SWEEP=chain|octet fixes the layout of the float32 per-iteration sweep (tests, tuning)
+// HTM_GIBBS_SWEEP=chain|octet fixes the layout of the float32 sweeps, per-iteration and persistent (tests, tuning)
 static int sweep_env() {
   const char* v = std::getenv("HTM_GIBBS_SWEEP");
   if (!v) return -1;
@@ -1343,7 +1515,7 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
       long gx = static_cast<long>(per_sm) * n_sm / gy;
       const bool pays = gx >= 1 && n_oct >= 3 * gx;
       if (gx > n_oct) gx = n_oct;
-      if (gx > 2L * p.n_tiles) gx = 2L * p.n_tiles;  // the partial-sum buffers hold 2 x ceil(E/32) entries per chain
+      if (gx > 2L * a.part_tiles) gx = 2L * a.part_tiles;  // [cur, prop][J][gx] must fit the 4 * J * part_tiles buffer
       if (gx >= 1 && (want == 1 || pays)) {
         shape.octet = true;
         shape.n_warps = n_warps;
@@ -1402,7 +1574,7 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
   // ---- persistent cooperative kernel when every CTA can be resident at once ----
   const int want = persist_env();
   bool persistent = false;
-  if (want != 0 && smem_pers <= 200 * 1024) {
+  if (want != 0 && smem_pers <= 200 * 1024 && !(sizeof(real) == 4 && sweep_env() == 1)) {  // HTM_GIBBS_SWEEP=octet skips it
     err = cudaFuncSetAttribute(gibbs_persist_kernel<real, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem_pers));
     if (err != cudaSuccess) return err;
@@ -1412,6 +1584,45 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_persist_kernel<real, TRACE>, kCW * 32, smem_pers);
     if (err != cudaSuccess) return err;
     persistent = static_cast<long>(per_sm) * n_sm >= static_cast<long>(grid.x) * grid.y;
+  }
+  // float32, too many tiles for that: the persistent octet sweep (one wave of CTAs walking event octets)
+  if constexpr (sizeof(real) == 4) {
+    if (!persistent && want != 0 && sweep_env() != 0) {
+      const int quads = (a.J + kQuad - 1) / kQuad;
+      const int gy = (quads + kCW - 1) / kCW;
+      const int n_warps = (quads + gy - 1) / gy;
+      const size_t smem_po = oq_smem(a.S, n_warps * kQuad) + sm_chain;
+      if (smem_po <= 200 * 1024) {
+        err = cudaFuncSetAttribute(gibbs_persist_oq_kernel<TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem_po));
+        if (err != cudaSuccess) return err;
+        int per_sm = 0, dev = 0, n_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_persist_oq_kernel<TRACE>, n_warps * 32, smem_po);
+        if (err != cudaSuccess) return err;
+        int n_oct = (a.E + kOct - 1) / kOct;
+        long gx = static_cast<long>(per_sm) * n_sm / gy;
+        if (gx > n_oct) gx = n_oct;
+        if (gx > a.part_tiles) gx = a.part_tiles;  // [2][cur, prop][J][gx]
+        if (gx >= 1) {
+          GibbsParams<real> pp = p;
+          GibbsDecide dp = d;
+          pp.n_tiles = dp.n_tiles = static_cast<int>(gx);
+          int iter_first = a.iter_first, iter_last = a.iter_last, rec_origin = a.rec_origin, rec_cap = a.rec_cap;
+          htm_step_trace* tr = a.trace;
+          htm_swap_trace* sw = a.swaps;
+          double* part = a.part_cur;
+          void* args[] = {&pp, &dp, &iter_first, &iter_last, &rec_origin, &rec_cap, &tr, &sw, &part, &n_oct};
+          err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gibbs_persist_oq_kernel<TRACE>),
+                                            dim3(static_cast<unsigned>(gx), gy), dim3(n_warps * 32), args, smem_po, stream);
+          if (err != cudaSuccess) return err;
+          ++nl;
+          if (n_launches) *n_launches = nl;
+          return cudaGetLastError();
+        }
+      }
+    }
   }
   if (want == 1 && !persistent) return cudaErrorCooperativeLaunchTooLarge;
   if (persistent) {

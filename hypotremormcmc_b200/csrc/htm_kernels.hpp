@@ -88,7 +88,8 @@ struct GibbsLaunch {
   double *g_vs = nullptr, *g_qs = nullptr, *g_tc = nullptr, *g_ac = nullptr, *g_T = nullptr, *g_L = nullptr;
   int *prop_which = nullptr, *prop_idx = nullptr, *a_prev = nullptr, *slot_of = nullptr;
   double *prop_xnew = nullptr, *prop_lpr = nullptr;
-  double *part_cur = nullptr, *part_prop = nullptr;  // [J][ceil(E/32)]
+  double *part_cur = nullptr, *part_prop = nullptr;  // one allocation of 4 * J * part_tiles doubles
+  int part_tiles = 0;                                // >= ceil(E/32)
   unsigned int* done_counter = nullptr;              // CTAs finished in the current sweep
   const void* obsx = nullptr;                        // float32: expanded station-pair rows [E][xrow] float4
   int xrow = 0;

@@ -552,20 +552,24 @@ def test_blocked_gibbs_persistent_and_per_iteration_paths_are_bit_identical(monk
 
 @pytest.mark.parametrize("E,S,R,K", [(300, 20, 3, 4), (77, 13, 5, 5), (33, 50, 1, 3), (200, 8, 9, 8), (10, 1, 2, 2)])
 def test_blocked_gibbs_sweep_layouts_are_bit_identical(monkeypatch, E, S, R, K):
-    """HTM_GIBBS_SWEEP = layout of the float32 per-iteration sweep: chain (warp = chain, lane = event) or octet
-    (warp = 8 events x 4 chains, the CTA walks event octets through a TMA ring)."""
+    """HTM_GIBBS_SWEEP = layout of the float32 sweep: chain (warp = chain, lane = event) or octet (warp = 8 events
+    x 4 chains, the CTA walks event octets through a TMA ring); HTM_GIBBS_PERSIST = one launch per iteration (0)
+    or one cooperative launch per run (1).  All four kernels must agree bit for bit."""
     syn = H.Synthetic(E, S, 8)
     cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_iter=60, n_burn=10, n_interval=10,
                            mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=16)
-    monkeypatch.setenv("HTM_GIBBS_PERSIST", "0")
     res = []
-    for layout in ("chain", "octet"):
+    for persist, layout in (("0", "chain"), ("0", "octet"), ("1", "octet"), ("1", "chain")):
+        monkeypatch.setenv("HTM_GIBBS_PERSIST", persist)
         monkeypatch.setenv("HTM_GIBBS_SWEEP", layout)
         with H.HypoTremorB200(cfg) as g:
             g.load(syn)
             g.init_chains()
             tr, sw = g.run_traced(1, 25)
-            g.run(26, 60)
+            g.run(26, 47)
+            g.run(48, 60)
+            _, nl, _ = g.last_run_stats()
+            assert nl == (2 if persist == "1" else 14)
             res.append(([g.get_chain_state(r, k) for r in range(R) for k in range(K)], g.get_counts(),
                         [g.fetch_samples(r) for r in range(R)], [g.fetch_likelihood(r) for r in range(R)], tr, sw))
     for other in res[1:]:
