@@ -588,6 +588,43 @@ def test_blocked_gibbs_sweep_layouts_are_bit_identical(monkeypatch, E, S, R, K):
         assert np.array_equal(res[0][5], other[5])
 
 
+def test_blocked_gibbs_full_size_properties():
+    """20 000 events x 50 stations x 20 joint chains (the persistent octet sweep): size-independent invariants."""
+    E, S, R, K, n_it, n_int = 20000, 50, 4, 5, 120, 20
+    syn = H.Synthetic(E, S, 77)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=2, n_iter=n_it, n_burn=40, n_interval=n_int,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=8)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        temps0 = sorted(g.get_chain_state(r, k)["temp"] for r in range(R) for k in range(K))
+        g.run(1, 70)
+        g.run(71, n_it)
+        _, nl, _ = g.last_run_stats()
+        assert nl == 2  # prepare + one cooperative launch
+        states = [g.get_chain_state(r, k) for r in range(R) for k in range(K)]
+        p, a = g.get_counts()
+        L64 = g.loglik(np.stack([s["hypo"] for s in states]), np.stack([s["t_corr"] for s in states]),
+                       np.stack([s["a_corr"] for s in states]), [s["vs"] for s in states], [s["qs"] for s in states])
+        smp = [g.fetch_samples(r) for r in range(R)]
+        lik = [g.fetch_likelihood(r) for r in range(R)]
+    # temperatures are only ever exchanged
+    assert sorted(s["temp"] for s in states) == temps0
+    # every cold chain proposes one hypocentre coordinate per event and one shared parameter per iteration
+    n_cold = R * 2
+    assert p[4:7].sum() == n_it * E * n_cold and p[:4].sum() == n_it * n_cold
+    assert (a <= p).all() and 0.05 < a[4:7].sum() / p[4:7].sum() < 0.95
+    # the carried log-likelihood of every chain is the likelihood of its state (float32 sums over 10^6 terms)
+    for s, L in zip(states, L64):
+        assert abs(s["log_likelihood"] - L) <= 2e-5 * abs(L), (s["log_likelihood"], L)
+    # records: iterations 1, 21, ..., 101; hypocentres only after the burn-in (41, 61, 81, 101), n_cold per record
+    n_rec = sum(len(x["iter"]) for x in smp)
+    assert n_rec == 4 * n_cold and sum(len(l[0]) for l in lik) == 6 * n_cold
+    for x in smp:
+        assert set(np.unique(x["iter"])) <= {41, 61, 81, 101}
+        assert np.isfinite(x["hypo"]).all() and (x["hypo"][:, 2::3] > cfg.prior_z).all()
+
+
 def test_blocked_gibbs_chunked_runs_equal_one_run():
     syn = H.Synthetic(100, 20, 3)
     cfg = H.default_config(n_sta=20, n_events=100, n_procs=2, n_chains=4, n_iter=80, n_burn=0, n_interval=10,
