@@ -210,18 +210,53 @@ __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int J = d.J, S = d.S;
   if (it > 0) {
-    // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly
-    for (int c = warp; c < J; c += nw) {
-      double a = 0.0, b = 0.0;
-      for (int t = lane; t < d.n_tiles; t += 32) {
-        a += __ldcg(part_cur + static_cast<size_t>(c) * d.n_tiles + t);
-        b += __ldcg(part_prop + static_cast<size_t>(c) * d.n_tiles + t);
+    // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly.  With fewer than
+    // 32 partials per chain a warp serves 32/g chains at once (g = lanes per chain, a power of two): the
+    // butterfly levels it skips would only have added the zeros of lanes that hold no partial, so the sums
+    // are the same bits as with one chain per warp.
+    if (d.n_tiles <= 16) {
+      int g = 16;
+      while (g > 1 && (g >> 1) >= d.n_tiles) g >>= 1;
+      const int per_warp = 32 / g, sub = lane / g, l = lane - sub * g;
+      for (int c0 = warp * per_warp; c0 < J; c0 += nw * per_warp) {
+        const int c = c0 + sub;
+        double a = 0.0, b = 0.0;
+        if (c < J && l < d.n_tiles) {  // g >= n_tiles: at most one partial per lane
+          a = __ldcg(part_cur + static_cast<size_t>(c) * d.n_tiles + l);
+          b = __ldcg(part_prop + static_cast<size_t>(c) * d.n_tiles + l);
+        }
+        for (int o = g >> 1; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (l == 0 && c < J) {
+          cs.tot[c] = a;
+          cs.tot[J + c] = b;
+        }
       }
-      a = warp_sum<double>(a);
-      b = warp_sum<double>(b);
-      if (lane == 0) {
-        cs.tot[c] = a;
-        cs.tot[J + c] = b;
+    } else {
+      // four chains per pass, so that eight independent loads are in flight per lane instead of two
+      constexpr int kCh = 4;
+      for (int c0 = warp * kCh; c0 < J; c0 += nw * kCh) {
+        double a[kCh], b[kCh];
+#pragma unroll
+        for (int q = 0; q < kCh; ++q) a[q] = b[q] = 0.0;
+        for (int t = lane; t < d.n_tiles; t += 32) {
+#pragma unroll
+          for (int q = 0; q < kCh; ++q) {
+            const int c = min(c0 + q, J - 1);
+            a[q] += __ldcg(part_cur + static_cast<size_t>(c) * d.n_tiles + t);
+            b[q] += __ldcg(part_prop + static_cast<size_t>(c) * d.n_tiles + t);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kCh; ++q) {
+          const double sa = warp_sum<double>(a[q]), sb = warp_sum<double>(b[q]);
+          if (lane == 0 && c0 + q < J) {
+            cs.tot[c0 + q] = sa;
+            cs.tot[J + c0 + q] = sb;
+          }
+        }
       }
     }
     __syncthreads();
@@ -309,9 +344,25 @@ __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int i
     __syncthreads();
   }
   // ---- slots of the cold chains (in chain order) for the next iteration's records ----
-  if (threadIdx.x == 0) {
-    int sl = 0;
-    for (int c = 0; c < J; ++c) cs.slot[c] = (cs.T[c] < 1.0 + kEps64) ? sl++ : -1;
+  {
+    __shared__ int s_cold_in_warp[32];
+    int before = 0;  // cold chains in earlier passes
+    for (int base = 0; base < J; base += blockDim.x) {
+      const int c = base + threadIdx.x;
+      const bool cold = c < J && cs.T[c] < 1.0 + kEps64;
+      const uint32_t m = __ballot_sync(0xffffffffu, cold);
+      if (lane == 0) s_cold_in_warp[warp] = __popc(m);
+      __syncthreads();
+      int off = before, all = 0;
+      for (int w = 0; w < nw; ++w) {
+        const int n = s_cold_in_warp[w];
+        off += w < warp ? n : 0;
+        all += n;
+      }
+      if (c < J) cs.slot[c] = cold ? off + __popc(m & ((1u << lane) - 1u)) : -1;
+      before += all;
+      __syncthreads();
+    }
   }
   // ---- next shared-parameter proposal (src/cls_mcmc.f90:134-157 restricted to the solved ones) ----
   for (int c = threadIdx.x; c < J; c += blockDim.x) {
