@@ -23,6 +23,7 @@ EXPORTS = [
     "htm_synchronize", "htm_replay", "htm_fetch_samples", "htm_fetch_likelihood",
     "htm_discard_samples", "htm_get_counts", "htm_get_histograms", "htm_device_ptr",
     "htm_last_run_stats", "htm_measure_fp32_peak", "htm_comm_unique_id", "htm_comm_init", "htm_gather",
+    "htm_comm_p2p_export", "htm_comm_p2p_import",
 ]
 
 
@@ -83,6 +84,8 @@ def load_library():
         "htm_comm_unique_id": [ctypes.c_char_p],
         "htm_comm_init": [vp, ctypes.c_char_p],
         "htm_gather": [vp, ctypes.POINTER(ctypes.c_uint32), lp, lp],
+        "htm_comm_p2p_export": [vp, ctypes.c_char_p],
+        "htm_comm_p2p_import": [vp, ctypes.c_char_p],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -309,6 +312,18 @@ class HypoTremorB200:
 
     def comm_init(self, unique_id):
         self._ck(self.lib.htm_comm_init(self._h, ctypes.create_string_buffer(unique_id, 128)))
+
+    def comm_p2p_export(self):
+        """64-byte CUDA IPC handle of this shard's exchange buffer (event-sharded blocked Gibbs)."""
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self.lib.htm_comm_p2p_export(self._h, buf))
+        return buf.raw
+
+    def comm_p2p_import(self, handles):
+        """handles: the 64-byte handles of all shards in shard order (the host program all-gathers them)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.cfg.shard_count
+        self._ck(self.lib.htm_comm_p2p_import(self._h, ctypes.create_string_buffer(blob, len(blob))))
 
     def gather(self, histograms=True):
         """(hist_all [n_events_total, 3, bins] or None, n_propose[7], n_accept[7]) over all shards."""

@@ -55,6 +55,12 @@ struct htm_handle_s {
   std::vector<double> host_rec_vs, host_rec_qs, host_rec_L, host_rec_tc, host_rec_ac;
   // multi-GPU (event shards): NCCL communicator, created by htm_comm_init
   void* comm = nullptr;
+  // event-sharded blocked Gibbs: per-iteration exchange through peer memory (htm_comm_p2p_export / _import)
+  double* xch_buf = nullptr;               // this shard's exchange buffer (cudaMalloc: IPC-exportable)
+  void* xch_peer[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool xch_on = false;
+  uint32_t xch_epoch = 1;                  // number of the next exchange; advances identically on every shard
+  int* d_xch_status = nullptr;
   // stats
   bool timed = false;
   int64_t last_launches = 0, last_proposals = 0;
@@ -364,6 +370,15 @@ void gibbs_launch_of(htm_handle h) {
   const bool ev_sharded = h->cfg.gibbs_shard_events && h->cfg.shard_count > 1;
   g.comm = (ev_sharded || (h->comm && std::getenv("HTM_GIBBS_FORCE_ALLREDUCE"))) ? h->comm : nullptr;
   g.count_globals = (!ev_sharded || h->cfg.shard_rank == 0) ? 1 : 0;
+  g.xch = PeerExchange();
+  const char* force = std::getenv("HTM_GIBBS_EXCHANGE");  // "nccl": keep the all-reduce although peer memory is mapped
+  if (ev_sharded && h->xch_on && !(force && std::string(force) == "nccl" && h->comm)) {
+    for (int r = 0; r < h->cfg.shard_count; ++r) g.xch.peer[r] = static_cast<double*>(h->xch_peer[r]);
+    g.xch.n = h->cfg.shard_count;
+    g.xch.rank = h->cfg.shard_rank;
+    g.xch.status = h->d_xch_status;
+  }
+  g.xch_epoch0 = h->xch_epoch;
 }
 
 // recorded iterations (mod(it, n_interval) == 1) inside [first, last]: ids m = (it-1)/n_interval
@@ -569,6 +584,10 @@ int32_t htm_destroy(htm_handle h) {
   for (void* p : h->gibbs_bufs) free_dev(p);
   free_dev(h->d_obsx);
   nccl_destroy(h->comm);
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (h->xch_peer[r] && h->xch_peer[r] != static_cast<void*>(h->xch_buf)) cudaIpcCloseMemHandle(h->xch_peer[r]);
+  free_dev(h->xch_buf);
+  free_dev(h->d_xch_status);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -831,9 +850,12 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
     h->host_samples_valid = false;
   }
   if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
-    if (h->cfg.gibbs_shard_events && h->cfg.shard_count > 1 && !h->comm)
-      return fail(h, HTM_ERR_STATE, "event-sharded blocked-Gibbs run needs htm_comm_init first (one all-reduce per iteration)");
+    if (h->cfg.gibbs_shard_events && h->cfg.shard_count > 1 && !h->comm && !h->xch_on)
+      return fail(h, HTM_ERR_STATE,
+                  "event-sharded blocked-Gibbs run needs htm_comm_p2p_export/_import or htm_comm_init first "
+                  "(one exchange of the per-chain sums per iteration)");
     gibbs_launch_of(h);
+    if (h->gl.xch.n > 1) h->xch_epoch += static_cast<uint32_t>(iter_last - iter_first + 1);
     h->gl.iter_first = iter_first;
     h->gl.iter_last = iter_last;
     h->gl.trace = d_trace;
@@ -920,6 +942,11 @@ int32_t htm_synchronize(htm_handle h) {
   if (!h) return HTM_ERR_ARG;
   HTM_CK(h, cudaSetDevice(h->cfg.device));
   HTM_CK(h, cudaStreamSynchronize(h->stream));
+  if (h->d_xch_status) {
+    int st = 0;
+    HTM_CK(h, cudaMemcpy(&st, h->d_xch_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st != 0) return fail(h, HTM_ERR_CUDA, "peer-memory exchange timed out: a shard did not reach the same iteration");
+  }
   return HTM_OK;
 }
 
@@ -1208,6 +1235,45 @@ int32_t htm_comm_init(htm_handle h, const char id[128]) {
   HTM_CK(h, cudaSetDevice(h->cfg.device));
   std::string why;
   if (!nccl_init(&h->comm, id, h->cfg.shard_rank, h->cfg.shard_count, &why)) return fail(h, HTM_ERR_CUDA, why);
+  return HTM_OK;
+}
+
+int32_t htm_comm_p2p_export(htm_handle h, unsigned char handle[64]) {
+  if (!h || !handle) return fail(h, HTM_ERR_ARG, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (h->cfg.mode != HTM_MODE_BLOCKED_GIBBS || !h->cfg.gibbs_shard_events || h->cfg.shard_count < 2)
+    return fail(h, HTM_ERR_STATE, "peer-memory exchange serves event-sharded blocked-Gibbs runs (gibbs_shard_events, shard_count >= 2)");
+  if (h->cfg.shard_count > kMaxPeers) return fail(h, HTM_ERR_UNSUPPORTED, "peer-memory exchange supports up to 8 shards");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  if (!h->xch_buf) {
+    const size_t bytes = peer_exchange_bytes(h->cfg.shard_count, h->C);
+    HTM_CK(h, cudaMalloc(&h->xch_buf, bytes));
+    HTM_CK(h, cudaMemset(h->xch_buf, 0, bytes));
+    HTM_CK(h, cudaMalloc(&h->d_xch_status, sizeof(int)));
+    HTM_CK(h, cudaMemset(h->d_xch_status, 0, sizeof(int)));
+    HTM_CK(h, cudaDeviceSynchronize());  // zeroed before any peer can see the handle
+  }
+  cudaIpcMemHandle_t ipc;
+  HTM_CK(h, cudaIpcGetMemHandle(&ipc, h->xch_buf));
+  std::memcpy(handle, &ipc, 64);
+  return HTM_OK;
+}
+
+int32_t htm_comm_p2p_import(htm_handle h, const unsigned char* handles) {
+  if (!h || !handles) return fail(h, HTM_ERR_ARG, "null argument");
+  if (!h->xch_buf) return fail(h, HTM_ERR_STATE, "call htm_comm_p2p_export first");
+  if (h->xch_on) return fail(h, HTM_ERR_STATE, "peer memory already mapped");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  for (int r = 0; r < h->cfg.shard_count; ++r) {
+    if (r == h->cfg.shard_rank) {
+      h->xch_peer[r] = h->xch_buf;
+      continue;
+    }
+    cudaIpcMemHandle_t ipc;
+    std::memcpy(&ipc, handles + static_cast<size_t>(64) * r, 64);
+    HTM_CK(h, cudaIpcOpenMemHandle(&h->xch_peer[r], ipc, cudaIpcMemLazyEnablePeerAccess));
+  }
+  h->xch_on = true;
   return HTM_OK;
 }
 

@@ -125,6 +125,7 @@ struct GibbsDecide {
   double prior[4], width[4], step[4];  // indexed by type-1: vs, t_corr, qs, a_corr
   unsigned long long* counts;
   int count_globals;  // 0 on shards > 0 of an event-sharded run (the decisions are replicated)
+  PeerExchange xch;   // event shards: sums of all shards through peer memory (n <= 1: off)
   // shared-parameter records of the cold chains: [cap][n_cool_total]
   int rec_slot;
   int* rec_chain;
@@ -200,6 +201,47 @@ __device__ void chain_store(const GibbsDecide& d, const ChainSm& cs) {
   }
 }
 
+// ---- event shards: all-reduce of the per-chain sums over NVLink peer memory --------------------------------
+// Called by every thread of ONE CTA per shard (the last CTA of the sweep).  Each shard stores its W sums into
+// slot [parity][rank] of every shard's buffer, publishes the exchange number with a system-scope release, waits
+// for the numbers of all shards, and adds the n slots of its own buffer in shard order -- the same operands in
+// the same order everywhere, so every shard takes bit-identical decisions.  Two parities: a shard can be at most
+// one exchange ahead of the slowest one (it cannot pass exchange e+1 before everyone has published e+1, i.e.
+// has finished reading e).  The wait is bounded: a missing peer raises *status instead of hanging the GPU.
+__device__ __forceinline__ uint32_t* peer_flags(double* base, int n, int W) {
+  return reinterpret_cast<uint32_t*>(base + static_cast<size_t>(2) * n * W);
+}
+__device__ void peer_allreduce(const PeerExchange& x, double* tot /* shared memory, W values, in/out */, const int W) {
+  const int n = x.n, me = x.rank, par = static_cast<int>(x.epoch & 1u);
+  for (int i = threadIdx.x; i < n * W; i += blockDim.x) {
+    const int r = i / W, t = i - r * W;
+    x.peer[r][(static_cast<size_t>(par) * n + me) * W + t] = tot[t];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < static_cast<unsigned>(n)) {
+    uint32_t* theirs = peer_flags(x.peer[threadIdx.x], n, W) + par * n + me;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(x.epoch) : "memory");
+    const uint32_t* mine = peer_flags(x.peer[me], n, W) + par * n + threadIdx.x;
+    uint32_t seen = 0;
+    long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      if (++spins > (1L << 24)) {
+        if (x.status) *x.status = 1;
+        break;
+      }
+    } while (seen != x.epoch);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < W; t += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += __ldcg(x.peer[me] + (static_cast<size_t>(par) * n + r) * W + t);
+    tot[t] = s;
+  }
+  __syncthreads();
+}
+
 // The decide step on the staged state.  Every thread of the CTA takes part; a CTA that is not the
 // `writer` computes exactly the same values but leaves counters, records and traces alone (the
 // persistent kernel runs this redundantly on every CTA so that one grid barrier per iteration suffices).
@@ -260,6 +302,7 @@ __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int i
       }
     }
     __syncthreads();
+    if (d.xch.n > 1) peer_allreduce(d.xch, cs.tot, 2 * J);
     // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----
     for (int c = threadIdx.x; c < J; c += blockDim.x) {
       const int which = cs.which[c];
@@ -1464,6 +1507,7 @@ static GibbsDecide make_decide(const GibbsLaunch& a) {
   }
   d.counts = a.counts;
   d.count_globals = a.count_globals;
+  d.xch = a.xch;
   d.rec_slot = -1;
   d.rec_chain = a.rec_chain;
   d.rec_vs = a.rec_vs;
@@ -1590,8 +1634,9 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
   gibbs_decide_kernel<<<1, 256, sm_chain, stream>>>(d);
   ++nl;
 
+  const bool peer_xch = a.xch.n > 1;  // one launch per iteration; its last CTA exchanges the sums and decides
   // ---- event-sharded joint chains: sweep -> local totals -> all-reduce -> decide (replicated) ----
-  if (a.comm) {
+  if (a.comm && !peer_xch) {
     err = sweep_set_smem<real, TRACE>(shape, smem_iter);
     if (err != cudaSuccess) return err;
     const size_t per_it_s = static_cast<size_t>(a.E + 1) * a.J;
@@ -1625,7 +1670,7 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
   // ---- persistent cooperative kernel when every CTA can be resident at once ----
   const int want = persist_env();
   bool persistent = false;
-  if (want != 0 && smem_pers <= 200 * 1024 && !(sizeof(real) == 4 && sweep_env() == 1)) {  // HTM_GIBBS_SWEEP=octet skips it
+  if (want != 0 && !peer_xch && smem_pers <= 200 * 1024 && !(sizeof(real) == 4 && sweep_env() == 1)) {  // HTM_GIBBS_SWEEP=octet skips it
     err = cudaFuncSetAttribute(gibbs_persist_kernel<real, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem_pers));
     if (err != cudaSuccess) return err;
@@ -1638,7 +1683,7 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
   }
   // float32, too many tiles for that: the persistent octet sweep (one wave of CTAs walking event octets)
   if constexpr (sizeof(real) == 4) {
-    if (!persistent && want != 0 && sweep_env() != 0) {
+    if (!persistent && !peer_xch && want != 0 && sweep_env() != 0) {
       const int quads = (a.J + kQuad - 1) / kQuad;
       const int gy = (quads + kCW - 1) / kCW;
       const int n_warps = (quads + gy - 1) / gy;
@@ -1675,7 +1720,7 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
       }
     }
   }
-  if (want == 1 && !persistent) return cudaErrorCooperativeLaunchTooLarge;
+  if (want == 1 && !persistent && !peer_xch) return cudaErrorCooperativeLaunchTooLarge;
   if (persistent) {
     int iter_first = a.iter_first, iter_last = a.iter_last, rec_origin = a.rec_origin, rec_cap = a.rec_cap;
     htm_step_trace* tr = a.trace;
@@ -1705,6 +1750,7 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
     ds.rec_slot = ps.rec_slot;
     ds.trace = a.trace ? a.trace + static_cast<size_t>(it - a.iter_first) * per_it + static_cast<size_t>(a.E) * a.J : nullptr;
     ds.swap = a.swaps ? a.swaps + (it - a.iter_first) : nullptr;
+    ds.xch.epoch = a.xch_epoch0 + static_cast<uint32_t>(it - a.iter_first);
     sweep_launch<real, TRACE>(shape, smem_iter, stream, ps, ds, a.done_counter);
     ++nl;
   }

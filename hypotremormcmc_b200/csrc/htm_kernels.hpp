@@ -80,6 +80,21 @@ struct ReplayLaunch {
 };
 cudaError_t launch_replay(const ReplayLaunch& a, cudaStream_t stream);
 
+// Event-sharded joint chains: all-reduce of the per-chain sums through peer memory (NVLink), inside the last
+// CTA of the sweep.  Every shard owns one buffer, mapped into the others with CUDA IPC:
+//   double   data [2][n][2*J]   slot [parity][writer shard]; parity = exchange number & 1
+//   uint32_t flag [2][n]        exchange number published by `writer shard`
+constexpr int kMaxPeers = 8;
+struct PeerExchange {
+  double* peer[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n = 0, rank = 0;    // n <= 1: no exchange
+  uint32_t epoch = 0;     // exchange number of this launch, the same on every shard, never reused
+  int* status = nullptr;  // device flag: 1 = a peer never answered
+};
+inline size_t peer_exchange_bytes(int n, int J) {
+  return static_cast<size_t>(2) * n * 2 * J * sizeof(double) + static_cast<size_t>(2) * n * sizeof(uint32_t);
+}
+
 // mode C (blocked Gibbs): joint chains with solved shared parameters
 struct GibbsLaunch {
   int precision = 32;
@@ -95,6 +110,8 @@ struct GibbsLaunch {
   int xrow = 0;
   // event-sharded joint chains: all-reduce of the per-chain sums every iteration
   void* comm = nullptr;       // NCCL communicator (null = single shard)
+  PeerExchange xch;           // peer-memory exchange (preferred over the NCCL all-reduce when set up)
+  uint32_t xch_epoch0 = 0;    // exchange number of iteration iter_first
   double* totals = nullptr;   // [2][J] scratch
   int count_globals = 1;      // shared-parameter counters are replicated on every shard: only shard 0 counts
   int E = 0, S = 0, J = 0, K = 0, n_cool_total = 0;

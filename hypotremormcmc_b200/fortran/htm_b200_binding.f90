@@ -274,6 +274,21 @@ module htm_b200_binding
        integer(c_int32_t) :: rc
      end function htm_gather
 
+     ! handles of all shards, 64 bytes each, in shard order (MPI_Allgather of the exported one)
+     function htm_comm_p2p_export(h, handle) bind(c, name="htm_comm_p2p_export") result(rc)
+       import
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(out) :: handle(64)
+       integer(c_int32_t) :: rc
+     end function htm_comm_p2p_export
+
+     function htm_comm_p2p_import(h, handles) bind(c, name="htm_comm_p2p_import") result(rc)
+       import
+       type(c_ptr), value :: h
+       character(kind=c_char), intent(in) :: handles(*)
+       integer(c_int32_t) :: rc
+     end function htm_comm_p2p_import
+
      function htm_measure_fp32_peak(device, tflops, mufu_gops) &
           & bind(c, name="htm_measure_fp32_peak") result(rc)
        import

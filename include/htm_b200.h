@@ -279,6 +279,17 @@ int32_t htm_comm_unique_id(char id[128]);
 int32_t htm_comm_init(htm_handle h, const char id[128]);
 int32_t htm_gather(htm_handle h, uint32_t* hist_all, int64_t n_propose[7], int64_t n_accept[7]);
 
+/* Event-sharded blocked Gibbs (cfg.gibbs_shard_events): the one exchange step of the path -- the sum over
+ * ALL events of every joint chain's log-likelihood, needed for each shared-parameter move (the reference
+ * recomputes it with forward%calc_log_likelihood, src/cls_forward.f90:268-303, on one rank) -- done inside
+ * the sweep kernel through NVLink peer memory instead of a separate all-reduce.  Every shard calls
+ * htm_comm_p2p_export, the HOST program all-gathers the 64-byte handles in shard order (MPI_Allgather in a
+ * Fortran/MPI driver), every shard calls htm_comm_p2p_import with handles[shard_count][64].  All shards must
+ * be processes on one NVLink/NVSwitch box (CUDA IPC).  With both this and htm_comm_init set up, the
+ * peer-memory path is used. */
+int32_t htm_comm_p2p_export(htm_handle h, unsigned char handle[64]);
+int32_t htm_comm_p2p_import(htm_handle h, const unsigned char* handles);
+
 /* Device pointers for zero-copy consumers in the same process (e.g. a NCCL gather driven
  * by the host program).  what: 0 = histograms (uint32), 1 = counts (int64[14]). */
 int32_t htm_device_ptr(htm_handle h, int32_t what, void** ptr, int64_t* n_bytes);

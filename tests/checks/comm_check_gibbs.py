@@ -28,6 +28,11 @@ with H.HypoTremorB200(cfg) as g:
     g.load(sh)
     g.init_chains()
     g.comm_init(ids[0])
+    if os.environ.get("HTM_GIBBS_EXCHANGE", "p2p") != "nccl":  # per-iteration exchange through NVLink peer memory
+        mine = g.comm_p2p_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        g.comm_p2p_import(handles)
     tr, sw = g.run_traced(1, n_it)
     st = g.get_chain_state(1, 2)
     _, p, a = g.gather(histograms=False)

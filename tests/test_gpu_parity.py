@@ -792,9 +792,30 @@ def test_abi_level_nccl_gather_single_shard():
         assert np.array_equal(p, p0) and np.array_equal(a, a0)
 
 
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_event_sharded_gibbs_on_two_gpus(exchange):
+    """Event-sharded joint chains, one process per GPU: the per-iteration exchange of the per-chain sums (fused
+    into the sweep over NVLink peer memory, or NCCL) must reproduce the UNSHARDED oracle step by step."""
+    import subprocess, sys, os, socket
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HTM_GIBBS_EXCHANGE=exchange)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), "tests/checks/comm_check_gibbs.py"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("matches the unsharded oracle: True") == 2, r.stdout[-2000:]
+
+
 def test_blocked_gibbs_allreduce_path_is_step_exact(monkeypatch):
     # the event-sharded joint-chain path (sweep -> local totals -> ncclAllReduce -> replicated decide), forced
-    # here on a one-rank communicator; tools/comm_check_gibbs.py runs it on several GPUs
+    # here on a one-rank communicator; tests/checks/comm_check_gibbs.py runs it on several GPUs
     monkeypatch.setenv("HTM_GIBBS_FORCE_ALLREDUCE", "1")
     E, S, R, K = 45, 14, 2, 3
     syn = H.Synthetic(E, S, 71)

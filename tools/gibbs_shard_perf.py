@@ -23,6 +23,11 @@ with H.HypoTremorB200(cfg) as g:
     g.load(syn)
     g.init_chains()
     g.comm_init(ids[0])
+    if os.environ.get("HTM_GIBBS_EXCHANGE", "p2p") != "nccl":  # per-iteration exchange through NVLink peer memory
+        mine = g.comm_p2p_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        g.comm_p2p_import(handles)
     g.run(1, 10)
     g.synchronize()
     dist.barrier()
@@ -34,6 +39,6 @@ with H.HypoTremorB200(cfg) as g:
 t = torch.tensor([dt])
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("event-sharded blocked Gibbs, %d GPUs, E=%d S=%d J=%d: %.1f us/iteration, %.3g proposals/s (all shards)"
-          % (world, E, S, R * K, float(t) * 1e6 / n_it, n_it * (E + 1) * R * K / float(t)))
+    print("event-sharded blocked Gibbs (%s exchange), %d GPUs, E=%d S=%d J=%d: %.1f us/iteration, %.3g proposals/s (all shards)"
+          % (os.environ.get("HTM_GIBBS_EXCHANGE", "p2p"), world, E, S, R * K, float(t) * 1e6 / n_it, n_it * (E + 1) * R * K / float(t)))
 dist.destroy_process_group()
