@@ -242,67 +242,75 @@ __device__ void peer_allreduce(const PeerExchange& x, double* tot /* shared memo
   __syncthreads();
 }
 
+// Per-chain sums of the per-tile (or per-CTA) partial sums, in a fixed order; every thread of the CTA calls it
+// (no barrier inside: the caller synchronises before reading tot).
+__device__ void sum_partials(const int n_tiles, const double* part_cur, const double* part_prop, const int J, double* tot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly.  With fewer than
+  // 32 partials per chain a warp serves 32/g chains at once (g = lanes per chain, a power of two): the
+  // butterfly levels it skips would only have added the zeros of lanes that hold no partial, so the sums
+  // are the same bits as with one chain per warp.
+  if (n_tiles <= 16) {
+    int g = 16;
+    while (g > 1 && (g >> 1) >= n_tiles) g >>= 1;
+    const int per_warp = 32 / g, sub = lane / g, l = lane - sub * g;
+    for (int c0 = warp * per_warp; c0 < J; c0 += nw * per_warp) {
+      const int c = c0 + sub;
+      double a = 0.0, b = 0.0;
+      if (c < J && l < n_tiles) {  // g >= n_tiles: at most one partial per lane
+        a = __ldcg(part_cur + static_cast<size_t>(c) * n_tiles + l);
+        b = __ldcg(part_prop + static_cast<size_t>(c) * n_tiles + l);
+      }
+      for (int o = g >> 1; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (l == 0 && c < J) {
+        tot[c] = a;
+        tot[J + c] = b;
+      }
+    }
+  } else {
+    // four chains per pass, so that eight independent loads are in flight per lane instead of two
+    constexpr int kCh = 4;
+    for (int c0 = warp * kCh; c0 < J; c0 += nw * kCh) {
+      double a[kCh], b[kCh];
+#pragma unroll
+      for (int q = 0; q < kCh; ++q) a[q] = b[q] = 0.0;
+      for (int t = lane; t < n_tiles; t += 32) {
+#pragma unroll
+        for (int q = 0; q < kCh; ++q) {
+          const int c = min(c0 + q, J - 1);
+          a[q] += __ldcg(part_cur + static_cast<size_t>(c) * n_tiles + t);
+          b[q] += __ldcg(part_prop + static_cast<size_t>(c) * n_tiles + t);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kCh; ++q) {
+        const double sa = warp_sum<double>(a[q]), sb = warp_sum<double>(b[q]);
+        if (lane == 0 && c0 + q < J) {
+          tot[c0 + q] = sa;
+          tot[J + c0 + q] = sb;
+        }
+      }
+    }
+  }
+}
+
 // The decide step on the staged state.  Every thread of the CTA takes part; a CTA that is not the
 // `writer` computes exactly the same values but leaves counters, records and traces alone (the
 // persistent kernel runs this redundantly on every CTA so that one grid barrier per iteration suffices).
 // Ends with a block barrier.
 __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int it, const int it_next,
                             const double* part_cur, const double* part_prop, const int rec_slot,
-                            htm_step_trace* trace, htm_swap_trace* swap, const bool writer) {
+                            htm_step_trace* trace, htm_swap_trace* swap, const bool writer,
+                            const bool summed = false /* part_* are already the sums over all tiles and shards */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int J = d.J, S = d.S;
   if (it > 0) {
-    // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly.  With fewer than
-    // 32 partials per chain a warp serves 32/g chains at once (g = lanes per chain, a power of two): the
-    // butterfly levels it skips would only have added the zeros of lanes that hold no partial, so the sums
-    // are the same bits as with one chain per warp.
-    if (d.n_tiles <= 16) {
-      int g = 16;
-      while (g > 1 && (g >> 1) >= d.n_tiles) g >>= 1;
-      const int per_warp = 32 / g, sub = lane / g, l = lane - sub * g;
-      for (int c0 = warp * per_warp; c0 < J; c0 += nw * per_warp) {
-        const int c = c0 + sub;
-        double a = 0.0, b = 0.0;
-        if (c < J && l < d.n_tiles) {  // g >= n_tiles: at most one partial per lane
-          a = __ldcg(part_cur + static_cast<size_t>(c) * d.n_tiles + l);
-          b = __ldcg(part_prop + static_cast<size_t>(c) * d.n_tiles + l);
-        }
-        for (int o = g >> 1; o > 0; o >>= 1) {
-          a += __shfl_xor_sync(0xffffffffu, a, o);
-          b += __shfl_xor_sync(0xffffffffu, b, o);
-        }
-        if (l == 0 && c < J) {
-          cs.tot[c] = a;
-          cs.tot[J + c] = b;
-        }
-      }
-    } else {
-      // four chains per pass, so that eight independent loads are in flight per lane instead of two
-      constexpr int kCh = 4;
-      for (int c0 = warp * kCh; c0 < J; c0 += nw * kCh) {
-        double a[kCh], b[kCh];
-#pragma unroll
-        for (int q = 0; q < kCh; ++q) a[q] = b[q] = 0.0;
-        for (int t = lane; t < d.n_tiles; t += 32) {
-#pragma unroll
-          for (int q = 0; q < kCh; ++q) {
-            const int c = min(c0 + q, J - 1);
-            a[q] += __ldcg(part_cur + static_cast<size_t>(c) * d.n_tiles + t);
-            b[q] += __ldcg(part_prop + static_cast<size_t>(c) * d.n_tiles + t);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < kCh; ++q) {
-          const double sa = warp_sum<double>(a[q]), sb = warp_sum<double>(b[q]);
-          if (lane == 0 && c0 + q < J) {
-            cs.tot[c0 + q] = sa;
-            cs.tot[J + c0 + q] = sb;
-          }
-        }
-      }
-    }
+    sum_partials(summed ? 1 : d.n_tiles, part_cur, part_prop, J, cs.tot);
     __syncthreads();
-    if (d.xch.n > 1) peer_allreduce(d.xch, cs.tot, 2 * J);
+    if (!summed && d.xch.n > 1) peer_allreduce(d.xch, cs.tot, 2 * J);
     // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----
     for (int c = threadIdx.x; c < J; c += blockDim.x) {
       const int which = cs.which[c];
@@ -1257,7 +1265,7 @@ __global__ void __launch_bounds__(kCW * 32, 2) gibbs_persist_oq_kernel(const Gib
                                                                        const int rec_origin, const int rec_cap,
                                                                        htm_step_trace* trace_base, htm_swap_trace* swap_base,
                                                                        double* part /* [2][2][J][gridDim.x] */,
-                                                                       const int n_oct) {
+                                                                       const int n_oct, double* totals /* [2*J] */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::grid_group grid = cg::this_grid();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
@@ -1399,8 +1407,25 @@ __global__ void __launch_bounds__(kCW * 32, 2) gibbs_persist_oq_kernel(const Gib
       }
     }
     grid.sync();
-    decide_core(d, cs, it, it + 1, part_cur, part_prop, rec_slot, trace_it ? trace_it + static_cast<size_t>(E) * J : nullptr,
-                swap_base ? swap_base + (it - iter_first) : nullptr, writer);
+    htm_step_trace* trace_g = trace_it ? trace_it + static_cast<size_t>(E) * J : nullptr;
+    htm_swap_trace* swap_it = swap_base ? swap_base + (it - iter_first) : nullptr;
+    if (d.xch.n > 1) {
+      // event shards: CTA (0,0) adds this shard's partials, exchanges the sums with the other GPUs through peer
+      // memory and hands the totals over all events to every CTA of its grid
+      if (writer) {
+        sum_partials(d.n_tiles, part_cur, part_prop, J, cs.tot);
+        __syncthreads();
+        PeerExchange x = d.xch;
+        x.epoch = d.xch.epoch + static_cast<uint32_t>(it - iter_first);
+        peer_allreduce(x, cs.tot, 2 * J);
+        for (int t = threadIdx.x; t < 2 * J; t += blockDim.x) totals[t] = cs.tot[t];
+        __threadfence();
+      }
+      grid.sync();
+      decide_core(d, cs, it, it + 1, totals, totals + J, rec_slot, trace_g, swap_it, writer, true);
+    } else {
+      decide_core(d, cs, it, it + 1, part_cur, part_prop, rec_slot, trace_g, swap_it, writer);
+    }
   }
   if (warp_ok) {
 #pragma unroll
@@ -1683,7 +1708,7 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
   }
   // float32, too many tiles for that: the persistent octet sweep (one wave of CTAs walking event octets)
   if constexpr (sizeof(real) == 4) {
-    if (!persistent && !peer_xch && want != 0 && sweep_env() != 0) {
+    if (!persistent && want != 0 && sweep_env() != 0) {  // also the event-sharded run with peer-memory exchange
       const int quads = (a.J + kQuad - 1) / kQuad;
       const int gy = (quads + kCW - 1) / kCW;
       const int n_warps = (quads + gy - 1) / gy;
@@ -1709,7 +1734,9 @@ static cudaError_t launch_gibbs_tt(const GibbsLaunch& a, cudaStream_t stream, in
           htm_step_trace* tr = a.trace;
           htm_swap_trace* sw = a.swaps;
           double* part = a.part_cur;
-          void* args[] = {&pp, &dp, &iter_first, &iter_last, &rec_origin, &rec_cap, &tr, &sw, &part, &n_oct};
+          double* totals = a.totals;
+          dp.xch.epoch = a.xch_epoch0;  // exchange number of iter_first; the kernel counts on from there
+          void* args[] = {&pp, &dp, &iter_first, &iter_last, &rec_origin, &rec_cap, &tr, &sw, &part, &n_oct, &totals};
           err = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gibbs_persist_oq_kernel<TRACE>),
                                             dim3(static_cast<unsigned>(gx), gy), dim3(n_warps * 32), args, smem_po, stream);
           if (err != cudaSuccess) return err;

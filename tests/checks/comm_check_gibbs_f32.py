@@ -1,0 +1,63 @@
+"""Event-sharded blocked Gibbs in float32 under torchrun (one rank per GPU): the sharded run (persistent octet sweep
+with the peer-memory exchange, or the per-iteration paths) must reproduce, flag for flag and bit for bit, the
+UNSHARDED float32 run of the same library on one GPU (which the single-GPU suite ties to the oracle)."""
+import os
+import sys
+
+sys.path.insert(0, ".")
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import hypotremormcmc_b200 as H
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("gloo")
+E, S, R, K, n_it = 2011, 20, 2, 4, 80
+syn = H.Synthetic(E, S, 9)
+base = dict(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=n_it, n_burn=10, n_interval=5,
+            mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=32)
+cfg = H.default_config(device=local, shard_rank=rank, shard_count=world, gibbs_shard_events=1, **base)
+sh = syn.shard(rank, world)
+ids = [H.HypoTremorB200.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+with H.HypoTremorB200(cfg) as g:
+    g.load(sh)
+    g.init_chains()
+    g.comm_init(ids[0])
+    if os.environ.get("HTM_GIBBS_EXCHANGE", "p2p") != "nccl":
+        mine = g.comm_p2p_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        g.comm_p2p_import(handles)
+    tr, sw = g.run_traced(1, 50)
+    g.run(51, n_it)
+    _, nl, _ = g.last_run_stats()
+    st = g.get_chain_state(1, 2)
+    _, p, a = g.gather(histograms=False)
+    smp = g.fetch_samples(0)
+with H.HypoTremorB200(H.default_config(device=local, **base)) as u:  # the same chains, unsharded, on this GPU
+    u.load(syn)
+    u.init_chains()
+    tr_u, sw_u = u.run_traced(1, 50)
+    u.run(51, n_it)
+    su = u.get_chain_state(1, 2)
+    pu, au = u.get_counts()
+    smp_u = u.fetch_samples(0)
+lo = sh.event_offset
+ok = True
+for f in ("proposal_type", "prior_ok", "accepted"):
+    ok &= bool(np.array_equal(tr[f][:, :-1], tr_u[f][:, lo:lo + sh.n_events]) and np.array_equal(tr[f][:, -1], tr_u[f][:, -1]))
+ok &= bool(np.array_equal(sw, sw_u))
+ok &= bool(np.array_equal(tr["log_likelihood"][:, -1], tr_u["log_likelihood"][:, -1]))  # sums of float32 values: exact in float64
+ok &= st["vs"] == su["vs"] and st["qs"] == su["qs"] and st["temp"] == su["temp"] and st["log_likelihood"] == su["log_likelihood"]
+ok &= bool(np.array_equal(st["hypo"], su["hypo"][3 * lo:3 * (lo + sh.n_events)]) and np.array_equal(st["t_corr"], su["t_corr"]))
+ok &= bool(np.array_equal(p, pu) and np.array_equal(a, au))
+ok &= bool(np.array_equal(smp["iter"], smp_u["iter"]) and np.array_equal(smp["vs"], smp_u["vs"]))
+print("comm_check_gibbs_f32 rank %d/%d (%s exchange, %d launches in the last run): equals the unsharded run: %s"
+      % (rank, world, os.environ.get("HTM_GIBBS_EXCHANGE", "p2p"), nl, ok))
+flag = torch.tensor([1 if ok else 0])
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if int(flag) == 1 else 1)
