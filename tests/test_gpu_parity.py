@@ -811,6 +811,12 @@ def test_event_sharded_gibbs_on_two_gpus(exchange):
                        cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("matches the unsharded oracle: True") == 2, r.stdout[-2000:]
+    # float32 (the persistent octet sweep with the exchange between two grid barriers) against the unsharded run
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), "tests/checks/comm_check_gibbs_f32.py"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("equals the unsharded run: True") == 2, r.stdout[-2000:]
 
 
 def test_blocked_gibbs_allreduce_path_is_step_exact(monkeypatch):
