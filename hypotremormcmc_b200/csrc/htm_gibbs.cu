@@ -225,13 +225,16 @@ __device__ void peer_allreduce(const PeerExchange& x, double* tot /* shared memo
     const uint32_t* mine = peer_flags(x.peer[me], n, W) + par * n + threadIdx.x;
     uint32_t seen = 0;
     long spins = 0;
-    do {
+    // once a peer has failed to answer the run is lost (htm_synchronize reports it): do not wait again
+    const bool dead = x.status && *reinterpret_cast<volatile int*>(x.status) != 0;
+    while (!dead) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      if (seen == x.epoch) break;
       if (++spins > (1L << 24)) {
-        if (x.status) *x.status = 1;
+        if (x.status) *reinterpret_cast<volatile int*>(x.status) = 1;
         break;
       }
-    } while (seen != x.epoch);
+    }
   }
   __syncthreads();
   for (int t = threadIdx.x; t < W; t += blockDim.x) {
