@@ -61,6 +61,29 @@ def test_loglik_float32_tolerance():
     assert rel(Lg, Lo) <= 1e-5
 
 
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("E,S,M", [(1, 10, 1), (77, 13, 2), (200, 50, 3), (95, 20, 5), (64, 7, 8), (131, 33, 9), (40, 1, 4)])
+def test_loglik_tile_and_warp_kernels_agree_with_oracle(monkeypatch, precision, E, S, M):
+    """htm_loglik has two kernels (32-event tiles with TMA-staged rows; one warp per (model, event)): both against
+    the oracle, for every models-per-CTA / station-slice split of the tile kernel and ragged tiles."""
+    syn = H.Synthetic(E, S, 11)
+    args = models(syn, np.random.default_rng(5), M)
+    cfg = H.default_config(n_sta=S, n_events=E, mode=H.MODE_FACTORISED, precision=precision, **NOSOLVE)
+    Lo, po_ = Oracle(cfg, syn).loglik(*args, per_event=True)
+    out = {}
+    for kern in ("tile", "warp"):
+        monkeypatch.setenv("HTM_LOGLIK_KERNEL", kern)
+        with H.HypoTremorB200(cfg) as g:
+            g.load(syn)
+            out[kern] = g.loglik(*args, per_event=True)
+    for kern, (Lg, pg) in out.items():
+        if precision == 64:
+            assert np.max(np.abs(pg - po_) / np.maximum(1.0, np.abs(po_))) <= 1e-12, kern
+            assert rel(Lg, Lo) <= 1e-12, kern
+        else:
+            assert np.max(np.abs(pg - po_)) <= 2e-3 and rel(Lg, Lo) <= 1e-5, kern
+
+
 def test_loglik_golden_and_degenerate_sigma():
     import os
     import types
