@@ -28,6 +28,19 @@ def test_library_exports_every_declared_symbol():
     assert sorted(H.api.EXPORTS) == names
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 (what cgo / ISO_C_BINDING tooling reads) and as C++."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "htm_b200.h")
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    for lang, std in (("c", "c99"), ("c++", "c++11")):
+        r = subprocess.run(["gcc", "-x", lang, "-std=" + std, "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", hdr],
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+
+
 def test_config_struct_matches_c_defaults():
     lib = H.load_library()
     c = H.HtmConfig()
