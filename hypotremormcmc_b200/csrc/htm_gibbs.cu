@@ -25,486 +25,17 @@
 #include <cstdlib>
 #include <string>
 
-#include "htm_forward.cuh"
-#include "htm_kernels.hpp"
+#include "htm_gibbs_step.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace htm {
-
-constexpr int kTile = 32;   // events per CTA
-constexpr int kCW = 8;      // chains (warps) per CTA
-
-template <typename real>
-struct GibbsParams {
-  typedef typename M<real>::real4 real4;
-  const real4* sta4;
-  const real4* obs4;  // raw: no station terms folded
-  const real4* evc4;
-  const void* prior_xy;  // real2 [E]
-  const float4* obsx;    // float32 only: expanded station-pair rows [E][xrow] (htm_forward.cuh)
-  int xrow;
-  real *hx, *hy, *hz, *hLe, *hLp;  // [J][E]
-  double *g_vs, *g_qs, *g_tc, *g_ac, *g_T, *g_L;  // [J], [J][S]
-  int* prop_which;
-  int* prop_idx;
-  double* prop_xnew;
-  double* prop_lpr;
-  int* a_prev;
-  int* slot_of;
-  double *part_cur, *part_prop;  // [J][n_tiles]
-  int E, S, J, K, n_tiles, n_cool_total;
-  int it, n_burn, n_interval;
-  PhiloxKeys rk;
-  uint32_t event_offset;
-  uint32_t chain_offset, J_total;  // Philox ids are global: shards of virtual ranks draw distinct streams
-  real prior_z, width_z, width_xy, step_xy, step_z;
-  unsigned long long* counts;
-  real4* hypo_rec;  // [cap][n_cool_total][E]
-  int rec_slot;     // ring slot of this iteration, or -1
-  htm_step_trace* trace;  // this iteration's [E+1][J] block, or null
-  htm_swap_trace* swap;   // this iteration's record, or null
-};
-
-template <typename real>
-__device__ __forceinline__ bool gibbs_is_cold(double T) {
-  return T < 1.0 + kEps64;
-}
-
-// one thread, sequential over stations; obs row and station terms in shared memory
-template <typename real>
-__device__ __forceinline__ real event_loglik_corr(const typename M<real>::real4* s_sta,
-                                                  const typename M<real>::real4* s_obs_row,
-                                                  const typename M<real>::real4 evc, int S, real px, real py,
-                                                  real pz, const Glob<real>& g, const real* s_tc, const real* s_ac,
-                                                  int ov_which, int ov_idx, real ov_val) {
-  typedef typename M<real>::real4 real4;
-  real ct = 0, ca = 0, S1t = 0, S1a = 0, S2 = 0;
-#pragma unroll 2
-  for (int j = 0; j < S; ++j) {
-    const real4 st = s_sta[j];
-    const real4 ob = s_obs_row[j];
-    real tc = s_tc[j], ac = s_ac[j];
-    if (j == ov_idx) {
-      if (ov_which == 2) tc = ov_val;
-      if (ov_which == 4) ac = ov_val;
-    }
-    real rt, ra;
-    station_resid(px, py, pz, g, st, ob, tc, ac, rt, ra);
-    if (j == 0) {
-      ct = rt;
-      ca = ra;
-    }
-    const real et = rt - ct, ea = ra - ca;
-    const real qt = ob.y * et, qa = ob.w * ea;
-    S1t += qt;
-    S1a += qa;
-    S2 += qt * et;
-    S2 += qa * ea;
-  }
-  return finish_loglik<real>(S1t, S2, S1a, static_cast<real>(0), evc);
-}
-
-// ---- chain-level bookkeeping -----------------------------------------------------------------------
-struct GibbsDecide {
-  double *g_vs, *g_qs, *g_tc, *g_ac, *g_T, *g_L;
-  int* prop_which;
-  int* prop_idx;
-  double* prop_xnew;
-  double* prop_lpr;
-  int* a_prev;
-  int* slot_of;
-  const double *part_cur, *part_prop;
-  int S, J, K, n_tiles, n_cool_total;
-  int it;       // iteration being decided; 0 = prepare only (no decision, no swap)
-  int it_next;  // iteration to propose for
-  PhiloxKeys rk;
-  uint32_t chain_offset, swap_stream;
-  int n_solved;
-  int solved[4];
-  double prior[4], width[4], step[4];  // indexed by type-1: vs, t_corr, qs, a_corr
-  unsigned long long* counts;
-  int count_globals;  // 0 on shards > 0 of an event-sharded run (the decisions are replicated)
-  PeerExchange xch;   // event shards: sums of all shards through peer memory (n <= 1: off)
-  // shared-parameter records of the cold chains: [cap][n_cool_total]
-  int rec_slot;
-  int* rec_chain;
-  double *rec_vs, *rec_qs, *rec_L, *rec_tc, *rec_ac;
-  htm_step_trace* trace;  // [J] (row E of this iteration's block) or null
-  htm_swap_trace* swap;
-};
-
-__device__ __forceinline__ double gauss64(uint32_t wa, uint32_t wb) { return M<double>::gauss(wa, wb); }
-
-// Chain-level state staged in shared memory: the serial parts of the decide step (swap, cold-slot numbering)
-// never wait on global memory, and the persistent kernel keeps it there for the whole launch.
-struct ChainSm {
-  double *T, *L, *vs, *qs, *xnew, *lpr, *tot, *tc, *ac;  // tot: [2][J]; tc, ac: [J][S]
-  int *which, *idx, *aprev, *slot;
-};
-__host__ __device__ inline size_t chain_sm_bytes(int J, int S) {
-  return static_cast<size_t>(J) * (2 * S + 8) * sizeof(double) + static_cast<size_t>(J) * 4 * sizeof(int);
-}
-__device__ __forceinline__ ChainSm carve_chain_sm(unsigned char* base, int J, int S) {
-  ChainSm c;
-  double* d = reinterpret_cast<double*>(base);
-  c.T = d; d += J;
-  c.L = d; d += J;
-  c.vs = d; d += J;
-  c.qs = d; d += J;
-  c.xnew = d; d += J;
-  c.lpr = d; d += J;
-  c.tot = d; d += 2 * J;
-  c.tc = d; d += static_cast<size_t>(J) * S;
-  c.ac = d; d += static_cast<size_t>(J) * S;
-  int* i = reinterpret_cast<int*>(d);
-  c.which = i; i += J;
-  c.idx = i; i += J;
-  c.aprev = i; i += J;
-  c.slot = i;
-  return c;
-}
-__device__ void chain_load(const GibbsDecide& d, const ChainSm& cs) {
-  for (int c = threadIdx.x; c < d.J; c += blockDim.x) {
-    cs.T[c] = d.g_T[c];
-    cs.L[c] = d.g_L[c];
-    cs.vs[c] = d.g_vs[c];
-    cs.qs[c] = d.g_qs[c];
-    cs.xnew[c] = d.prop_xnew[c];
-    cs.lpr[c] = d.prop_lpr[c];
-    cs.which[c] = d.prop_which[c];
-    cs.idx[c] = d.prop_idx[c];
-    cs.aprev[c] = d.a_prev[c];
-    cs.slot[c] = d.slot_of[c];
-  }
-  for (int i = threadIdx.x; i < d.J * d.S; i += blockDim.x) {
-    cs.tc[i] = d.g_tc[i];
-    cs.ac[i] = d.g_ac[i];
-  }
-}
-__device__ void chain_store(const GibbsDecide& d, const ChainSm& cs) {
-  for (int c = threadIdx.x; c < d.J; c += blockDim.x) {
-    d.g_T[c] = cs.T[c];
-    d.g_L[c] = cs.L[c];
-    d.g_vs[c] = cs.vs[c];
-    d.g_qs[c] = cs.qs[c];
-    d.prop_xnew[c] = cs.xnew[c];
-    d.prop_lpr[c] = cs.lpr[c];
-    d.prop_which[c] = cs.which[c];
-    d.prop_idx[c] = cs.idx[c];
-    d.a_prev[c] = cs.aprev[c];
-    d.slot_of[c] = cs.slot[c];
-  }
-  for (int i = threadIdx.x; i < d.J * d.S; i += blockDim.x) {
-    d.g_tc[i] = cs.tc[i];
-    d.g_ac[i] = cs.ac[i];
-  }
-}
-
-// ---- event shards: all-reduce of the per-chain sums over NVLink peer memory --------------------------------
-// Called by every thread of ONE CTA per shard (the last CTA of the sweep).  Each shard stores its W sums into
-// slot [parity][rank] of every shard's buffer, publishes the exchange number with a system-scope release, waits
-// for the numbers of all shards, and adds the n slots of its own buffer in shard order -- the same operands in
-// the same order everywhere, so every shard takes bit-identical decisions.  Two parities: a shard can be at most
-// one exchange ahead of the slowest one (it cannot pass exchange e+1 before everyone has published e+1, i.e.
-// has finished reading e).  The wait is bounded: a missing peer raises *status instead of hanging the GPU.
-__device__ __forceinline__ uint32_t* peer_flags(double* base, int n, int W) {
-  return reinterpret_cast<uint32_t*>(base + static_cast<size_t>(2) * n * W);
-}
-__device__ void peer_allreduce(const PeerExchange& x, double* tot /* shared memory, W values, in/out */, const int W) {
-  const int n = x.n, me = x.rank, par = static_cast<int>(x.epoch & 1u);
-  for (int i = threadIdx.x; i < n * W; i += blockDim.x) {
-    const int r = i / W, t = i - r * W;
-    x.peer[r][(static_cast<size_t>(par) * n + me) * W + t] = tot[t];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < static_cast<unsigned>(n)) {
-    uint32_t* theirs = peer_flags(x.peer[threadIdx.x], n, W) + par * n + me;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(x.epoch) : "memory");
-    const uint32_t* mine = peer_flags(x.peer[me], n, W) + par * n + threadIdx.x;
-    uint32_t seen = 0;
-    long spins = 0;
-    // once a peer has failed to answer the run is lost (htm_synchronize reports it): do not wait again
-    const bool dead = x.status && *reinterpret_cast<volatile int*>(x.status) != 0;
-    while (!dead) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-      if (seen == x.epoch) break;
-      if (++spins > (1L << 24)) {
-        if (x.status) *reinterpret_cast<volatile int*>(x.status) = 1;
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < W; t += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < n; ++r) s += __ldcg(x.peer[me] + (static_cast<size_t>(par) * n + r) * W + t);
-    tot[t] = s;
-  }
-  __syncthreads();
-}
-
-// Per-chain sums of the per-tile (or per-CTA) partial sums, in a fixed order; every thread of the CTA calls it
-// (no barrier inside: the caller synchronises before reading tot).
-__device__ void sum_partials(const int n_tiles, const double* part_cur, const double* part_prop, const int J, double* tot) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly.  With fewer than
-  // 32 partials per chain a warp serves 32/g chains at once (g = lanes per chain, a power of two): the
-  // butterfly levels it skips would only have added the zeros of lanes that hold no partial, so the sums
-  // are the same bits as with one chain per warp.
-  if (n_tiles <= 16) {
-    int g = 16;
-    while (g > 1 && (g >> 1) >= n_tiles) g >>= 1;
-    const int per_warp = 32 / g, sub = lane / g, l = lane - sub * g;
-    for (int c0 = warp * per_warp; c0 < J; c0 += nw * per_warp) {
-      const int c = c0 + sub;
-      double a = 0.0, b = 0.0;
-      if (c < J && l < n_tiles) {  // g >= n_tiles: at most one partial per lane
-        a = __ldcg(part_cur + static_cast<size_t>(c) * n_tiles + l);
-        b = __ldcg(part_prop + static_cast<size_t>(c) * n_tiles + l);
-      }
-      for (int o = g >> 1; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-      }
-      if (l == 0 && c < J) {
-        tot[c] = a;
-        tot[J + c] = b;
-      }
-    }
-  } else {
-    // four chains per pass, so that eight independent loads are in flight per lane instead of two
-    constexpr int kCh = 4;
-    for (int c0 = warp * kCh; c0 < J; c0 += nw * kCh) {
-      double a[kCh], b[kCh];
-#pragma unroll
-      for (int q = 0; q < kCh; ++q) a[q] = b[q] = 0.0;
-      for (int t = lane; t < n_tiles; t += 32) {
-#pragma unroll
-        for (int q = 0; q < kCh; ++q) {
-          const int c = min(c0 + q, J - 1);
-          a[q] += __ldcg(part_cur + static_cast<size_t>(c) * n_tiles + t);
-          b[q] += __ldcg(part_prop + static_cast<size_t>(c) * n_tiles + t);
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < kCh; ++q) {
-        const double sa = warp_sum<double>(a[q]), sb = warp_sum<double>(b[q]);
-        if (lane == 0 && c0 + q < J) {
-          tot[c0 + q] = sa;
-          tot[J + c0 + q] = sb;
-        }
-      }
-    }
-  }
-}
-
-// The decide step on the staged state.  Every thread of the CTA takes part; a CTA that is not the
-// `writer` computes exactly the same values but leaves counters, records and traces alone (the
-// persistent kernel runs this redundantly on every CTA so that one grid barrier per iteration suffices).
-// Ends with a block barrier.
-__device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int it, const int it_next,
-                            const double* part_cur, const double* part_prop, const int rec_slot,
-                            htm_step_trace* trace, htm_swap_trace* swap, const bool writer,
-                            const bool summed = false /* part_* are already the sums over all tiles and shards */) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int J = d.J, S = d.S;
-  if (it > 0) {
-    sum_partials(summed ? 1 : d.n_tiles, part_cur, part_prop, J, cs.tot);
-    __syncthreads();
-    if (!summed && d.xch.n > 1) peer_allreduce(d.xch, cs.tot, 2 * J);
-    // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----
-    for (int c = threadIdx.x; c < J; c += blockDim.x) {
-      const int which = cs.which[c];
-      const double T = cs.T[c];
-      const bool cold = T < 1.0 + kEps64;
-      const double Lcur = cs.tot[c], Lprop = cs.tot[J + c];
-      bool acc = false;
-      if (which != 0) {
-        const u32x4 wb = philox4x32_10(d.rk, static_cast<uint32_t>(it), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 1u);
-        const double ratio = (Lprop - Lcur) / T + cs.lpr[c];
-        const double r = M<double>::u_co(wb.v[0]);
-        if (r >= kEps64 && ::log(r) <= ratio) acc = true;
-        if (writer && cold && d.counts && d.count_globals) {
-          atomicAdd(d.counts + (which - 1), 1ull);
-          if (acc) atomicAdd(d.counts + 7 + (which - 1), 1ull);
-        }
-        if (acc) {
-          const double xn = cs.xnew[c];
-          const int idx = cs.idx[c];
-          if (which == 1) cs.vs[c] = xn;
-          if (which == 2) cs.tc[static_cast<size_t>(c) * S + idx] = xn;
-          if (which == 3) cs.qs[c] = xn;
-          if (which == 4) cs.ac[static_cast<size_t>(c) * S + idx] = xn;
-        }
-      }
-      cs.aprev[c] = acc ? 1 : 0;
-      cs.L[c] = acc ? Lprop : Lcur;
-      if (writer && trace) {
-        htm_step_trace t;
-        t.proposal_type = which;
-        t.index = which ? cs.idx[c] + 1 : 0;
-        t.prior_ok = 1;
-        t.accepted = acc ? 1 : 0;
-        t.log_likelihood = cs.L[c];
-        trace[c] = t;
-      }
-    }
-    __syncthreads();
-    // ---- record the cold chains' shared parameters (src/hypo_tremor_mcmc.f90:270-280) ----
-    if (writer && rec_slot >= 0 && d.rec_chain) {
-      for (int c = warp; c < J; c += nw) {
-        const int sl = cs.slot[c];
-        if (sl < 0) continue;
-        const size_t o = static_cast<size_t>(rec_slot) * d.n_cool_total + sl;
-        if (lane == 0) {
-          d.rec_chain[o] = c;
-          d.rec_vs[o] = cs.vs[c];
-          d.rec_qs[o] = cs.qs[c];
-          d.rec_L[o] = cs.L[c];
-        }
-        for (int j = lane; j < S; j += 32) {
-          d.rec_tc[o * S + j] = cs.tc[static_cast<size_t>(c) * S + j];
-          d.rec_ac[o * S + j] = cs.ac[static_cast<size_t>(c) * S + j];
-        }
-      }
-    }
-    // ---- one swap attempt over all J chains (src/cls_parallel.f90:220-240, 285-302) ----
-    if (threadIdx.x == 0 && J >= 2) {
-      const u32x4 w = philox4x32_10(d.rk, static_cast<uint32_t>(it), d.swap_stream, PHX_SWAP, 1u);
-      const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(J)));
-      int i2 = i1 + 1 + static_cast<int>(below(w.v[1], static_cast<uint32_t>(J - 1)));
-      if (i2 >= J) i2 -= J;
-      const double T1 = cs.T[i1], T2 = cs.T[i2], L1 = cs.L[i1], L2 = cs.L[i2];
-      const double del_s = (L2 - L1) * (1.0 / T1 - 1.0 / T2);
-      const double r = M<double>::u_co(w.v[2]);
-      const bool sacc = r >= kEps64 && ::log(r) <= del_s;
-      if (sacc) {
-        cs.T[i1] = T2;
-        cs.T[i2] = T1;
-      }
-      if (writer && swap) {
-        htm_swap_trace t;
-        t.rank1 = i1 / d.K;
-        t.chain1 = i1 % d.K + 1;
-        t.rank2 = i2 / d.K;
-        t.chain2 = i2 % d.K + 1;
-        t.accepted = sacc ? 1 : 0;
-        t.reserved = 0;
-        *swap = t;
-      }
-    }
-    __syncthreads();
-  }
-  // ---- slots of the cold chains (in chain order) for the next iteration's records ----
-  {
-    __shared__ int s_cold_in_warp[32];
-    int before = 0;  // cold chains in earlier passes
-    for (int base = 0; base < J; base += blockDim.x) {
-      const int c = base + threadIdx.x;
-      const bool cold = c < J && cs.T[c] < 1.0 + kEps64;
-      const uint32_t m = __ballot_sync(0xffffffffu, cold);
-      if (lane == 0) s_cold_in_warp[warp] = __popc(m);
-      __syncthreads();
-      int off = before, all = 0;
-      for (int w = 0; w < nw; ++w) {
-        const int n = s_cold_in_warp[w];
-        off += w < warp ? n : 0;
-        all += n;
-      }
-      if (c < J) cs.slot[c] = cold ? off + __popc(m & ((1u << lane) - 1u)) : -1;
-      before += all;
-      __syncthreads();
-    }
-  }
-  // ---- next shared-parameter proposal (src/cls_mcmc.f90:134-157 restricted to the solved ones) ----
-  for (int c = threadIdx.x; c < J; c += blockDim.x) {
-    if (d.n_solved == 0) {
-      cs.which[c] = 0;
-      continue;
-    }
-    const u32x4 wa = philox4x32_10(d.rk, static_cast<uint32_t>(it_next), d.chain_offset + static_cast<uint32_t>(c), PHX_GLOBAL, 0u);
-    const int which = d.solved[below(wa.v[0], static_cast<uint32_t>(d.n_solved))];
-    const int idx = (which == 2 || which == 4) ? static_cast<int>(below(wa.v[1], static_cast<uint32_t>(S))) : 0;
-    const double gs = gauss64(wa.v[2], wa.v[3]);
-    double x_old;
-    if (which == 1) x_old = cs.vs[c];
-    else if (which == 2) x_old = cs.tc[static_cast<size_t>(c) * S + idx];
-    else if (which == 3) x_old = cs.qs[c];
-    else x_old = cs.ac[static_cast<size_t>(c) * S + idx];
-    const double mu = d.prior[which - 1], sg = d.width[which - 1];
-    const double x_new = __dadd_rn(x_old, __dmul_rn(gs, d.step[which - 1]));
-    const double dn = x_new - mu, dl = x_old - mu;
-    cs.which[c] = which;
-    cs.idx[c] = idx;
-    cs.xnew[c] = x_new;
-    cs.lpr[c] = -(__dmul_rn(dn, dn) - __dmul_rn(dl, dl)) / (2.0 * sg * sg);
-  }
-  __syncthreads();
-}
-
-// one CTA: global -> shared, decide, shared -> global.  smem: chain_sm_bytes(J, S)
-__device__ void gibbs_decide(const GibbsDecide& d, unsigned char* smem) {
-  const ChainSm cs = carve_chain_sm(smem, d.J, d.S);
-  chain_load(d, cs);
-  __syncthreads();
-  decide_core(d, cs, d.it, d.it_next, d.part_cur, d.part_prop, d.rec_slot, d.trace, d.swap, true);
-  chain_store(d, cs);
-}
 
 __global__ void __launch_bounds__(256) gibbs_decide_kernel(const GibbsDecide d) {
   extern __shared__ __align__(16) unsigned char s_decide_dyn[];
   gibbs_decide(d, s_decide_dyn);
 }
 
-// ---- float32 packed evaluation (lane = event, warp = chain) --------------------------------------------
-// Row of one event in the expanded table: [0] = A of station 0, [1] = {t_obs0, a_obs0, 0, 0}, then 4 float4
-// per station pair (htm_forward.cuh: store_station_pair).  cp[m] = {-tc_j0, -tc_j1, -ac_j0, -ac_j1} are the
-// chain's station terms of pair m (warp-broadcast), ntc0/nac0 those of station 0.
-__device__ __forceinline__ int gibbs_xrow(int S) { return 2 + 4 * (S / 2); }
-constexpr int kGibbsPairUnroll = 2;
-__device__ __forceinline__ float eval_pairs_f32(const float4* __restrict__ row, const int n_pairs, const float hx,
-                                                const float hy, const float hz, const Glob<float>& g,
-                                                const float4* __restrict__ cp, const float ntc0, const float nac0,
-                                                const float4 evc) {
-  const float kC = 0.34657359027997264f;
-  const float4 A0 = row[0], h1 = row[1];
-  const float h2 = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
-  float2 nct, nca;
-  {
-    const float d2 = fmaf(hx, A0.x, fmaf(hy, A0.y, fmaf(hz, A0.z, A0.w + h2)));
-    const float d = d2 * mufu_rsq(d2);
-    const float l2 = mufu_lg2(d2);
-    const float ct = -(fmaf(d, g.ivs, ntc0) - h1.x);
-    const float ca = -(fmaf(-kC, l2, fmaf(-g.B, d, nac0)) - h1.y);
-    nct = f2(ct, ct);
-    nca = f2(ca, ca);
-  }
-  const float2 px = f2(hx, hx), py = f2(hy, hy), pz = f2(hz, hz), hh = f2(h2, h2);
-  const float2 ivs2 = f2(g.ivs, g.ivs), nB2 = f2(-g.B, -g.B), nc2 = f2(-kC, -kC);
-  float2 a1t = f2(0.f, 0.f), a1a = f2(0.f, 0.f), a2 = f2(0.f, 0.f);
-  const float4* r = row + 2;
-#pragma unroll kGibbsPairUnroll
-  for (int m = 0; m < n_pairs; ++m) {
-    const float4 r0 = r[4 * m], r1 = r[4 * m + 1], r2 = r[4 * m + 2], r3 = r[4 * m + 3];
-    const float4 c4 = cp[m];
-    const float2 swt = f2(r2.x, r2.y), swa = f2(r3.x, r3.y);
-    const float2 d2 = __ffma2_rn(px, f2(r0.x, r0.y),
-                                 __ffma2_rn(py, f2(r0.z, r0.w), __ffma2_rn(pz, f2(r1.x, r1.y), __fadd2_rn(f2(r1.z, r1.w), hh))));
-    const float2 d = __fmul2_rn(d2, f2(mufu_rsq(d2.x), mufu_rsq(d2.y)));
-    const float2 l2 = f2(mufu_lg2(d2.x), mufu_lg2(d2.y));
-    const float2 at = __fadd2_rn(__ffma2_rn(d, ivs2, nct), f2(c4.x, c4.y));
-    const float2 ut = __ffma2_rn(swt, at, f2(r2.z, r2.w));
-    const float2 aa = __fadd2_rn(__ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, nca)), f2(c4.z, c4.w));
-    const float2 ua = __ffma2_rn(swa, aa, f2(r3.z, r3.w));
-    a2 = __ffma2_rn(ut, ut, a2);
-    a1t = __ffma2_rn(swt, ut, a1t);
-    a2 = __ffma2_rn(ua, ua, a2);
-    a1a = __ffma2_rn(swa, ua, a1a);
-  }
-  return finish_loglik<float>(a1t.x + a1t.y, a2.x + a2.y, a1a.x + a1a.y, 0.f, evc);
-}
 
 // builds the expanded rows once per table upload: one thread per (event, pair) and one per event header
 __global__ void expand_obs_kernel(const float4* __restrict__ sta4, const float4* __restrict__ obs4,
@@ -538,94 +69,6 @@ cudaError_t launch_expand_obs(const Tables& tab, int E, int S, void* obsx, cudaS
       static_cast<const float4*>(tab.sta4), static_cast<const float4*>(tab.obs4_raw),
       static_cast<const float2*>(tab.prior_xy), E, S, static_cast<float4*>(obsx));
   return cudaGetLastError();
-}
-
-// ---- per-thread step shared by the per-iteration sweep and the persistent kernel ---------------------
-template <typename real>
-struct StepIn {
-  real T, iT, vs, qs, pval;
-  bool cold;
-  int which, pidx;
-  int S, n_pairs;
-  const typename M<real>::real4* obs_row;  // this lane's event row in shared memory
-  // float32 operands (station terms per pair: current / proposed; station 0: {-tc0, -ac0, -tc0', -ac0'})
-  const float4* cp;
-  const float4* cpP;
-  float4 c0;
-  // float64 operands
-  const typename M<real>::real4* s_sta;
-  const real* tc;
-  const real* ac;
-};
-
-// 1. one hypocentre coordinate proposed and judged on the event's own log-likelihood with the chain's
-//    temperature; 2. the chain's pending shared-parameter proposal evaluated for this event (-> Lp).
-template <typename real, bool TRACE>
-__device__ __forceinline__ void gibbs_thread_step(const GibbsParams<real>& p, const int it, const StepIn<real>& in,
-                                                  const int c, const int e, const int ee, const bool ev_ok,
-                                                  const typename M<real>::real4 evc, const real mux, const real muy,
-                                                  real& x, real& y, real& z, real& Le, real& Lp, int& icmp, bool& acc,
-                                                  htm_step_trace* trace) {
-  constexpr bool kF32 = sizeof(real) == 4;
-  const Glob<real> g = make_glob<real>(in.vs, in.qs);
-  const uint32_t gid = (static_cast<uint32_t>(ee) + p.event_offset) * p.J_total + p.chain_offset + static_cast<uint32_t>(c);
-  const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(it), gid, PHX_STEP, 0u);
-  icmp = static_cast<int>(below(w.v[0], 3u));
-  const real gs = M<real>::gauss(w.v[1], w.v[2]);
-  const bool isz = icmp == 0;
-  const real x_old = isz ? z : (icmp == 1 ? y : x);
-  const real mu = isz ? p.prior_z : (icmp == 1 ? muy : mux);
-  const real sigma = isz ? p.width_z : p.width_xy;
-  const real step = isz ? p.step_z : p.step_xy;
-  const real x_new = x_old + gs * step;
-  const real dn = x_new - mu, dl = x_old - mu;
-  real lpr = -(dn * dn - dl * dl) / (static_cast<real>(2) * sigma * sigma);
-  bool ok = true;
-  if (isz) {
-    if (x_new <= mu)
-      ok = false;
-    else
-      lpr = lpr + M<real>::log(dn) - M<real>::log(dl);
-  }
-  const real nx = icmp == 2 ? x_new : x, ny = icmp == 1 ? x_new : y, nz = isz ? x_new : z;
-  real Lnew;
-  if constexpr (kF32) {
-    Lnew = eval_pairs_f32(reinterpret_cast<const float4*>(in.obs_row), in.n_pairs, nx - mux, ny - muy, nz, g, in.cp,
-                          in.c0.x, in.c0.y, evc);
-  } else {
-    Lnew = event_loglik_corr<real>(in.s_sta, in.obs_row, evc, in.S, nx, ny, nz, g, in.tc, in.ac, 0, -1, 0);
-  }
-  const real ratio = M<real>::div(Lnew - Le, in.T, in.iT) + lpr;
-  const real ru = M<real>::u_co(w.v[3]);
-  acc = ok && (ru > static_cast<real>(0)) && (M<real>::log(ru) <= ratio);
-  if (acc) {
-    x = nx;
-    y = ny;
-    z = nz;
-    Le = Lnew;
-  }
-  if (TRACE) {
-    if (ev_ok && trace) {
-      htm_step_trace t;
-      t.proposal_type = 5 + icmp;
-      t.index = 3 * (e + 1) - icmp;
-      t.prior_ok = ok ? 1 : 0;
-      t.accepted = acc ? 1 : 0;
-      t.log_likelihood = static_cast<double>(Le);
-      trace[static_cast<size_t>(e) * p.J + c] = t;
-    }
-  }
-  Lp = Le;
-  if (in.which != 0) {
-    const Glob<real> gp = make_glob<real>(in.which == 1 ? in.pval : in.vs, in.which == 3 ? in.pval : in.qs);
-    if constexpr (kF32) {
-      Lp = eval_pairs_f32(reinterpret_cast<const float4*>(in.obs_row), in.n_pairs, x - mux, y - muy, z, gp, in.cpP,
-                          in.c0.z, in.c0.w, evc);
-    } else {
-      Lp = event_loglik_corr<real>(in.s_sta, in.obs_row, evc, in.S, x, y, z, gp, in.tc, in.ac, in.which,
-                                   (in.which == 2 || in.which == 4) ? in.pidx : -1, in.pval);
-    }
-  }
 }
 
 // shared-memory carve-up common to both kernels
