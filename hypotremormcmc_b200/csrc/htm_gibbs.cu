@@ -861,9 +861,7 @@ __global__ void __launch_bounds__(kCW * 32, 2) gibbs_persist_oq_kernel(const Gib
       if (writer) {
         sum_partials(d.n_tiles, part_cur, part_prop, J, cs.tot);
         __syncthreads();
-        PeerExchange x = d.xch;
-        x.epoch = d.xch.epoch + static_cast<uint32_t>(it - iter_first);
-        peer_allreduce(x, cs.tot, 2 * J);
+        peer_allreduce(d.xch, d.xch.epoch + static_cast<uint32_t>(it - iter_first), cs.tot, 2 * J);
         for (int t = threadIdx.x; t < 2 * J; t += blockDim.x) totals[t] = cs.tot[t];
         __threadfence();
       }

@@ -153,8 +153,9 @@ __device__ void chain_store(const GibbsDecide& d, const ChainSm& cs) {
 __device__ __forceinline__ uint32_t* peer_flags(double* base, int n, int W) {
   return reinterpret_cast<uint32_t*>(base + static_cast<size_t>(2) * n * W);
 }
-__device__ void peer_allreduce(const PeerExchange& x, double* tot /* shared memory, W values, in/out */, const int W) {
-  const int n = x.n, me = x.rank, par = static_cast<int>(x.epoch & 1u);
+__device__ void peer_allreduce(const PeerExchange& x, const uint32_t epoch, double* tot /* shared memory, W values, in/out */,
+                               const int W) {
+  const int n = x.n, me = x.rank, par = static_cast<int>(epoch & 1u);
   for (int i = threadIdx.x; i < n * W; i += blockDim.x) {
     const int r = i / W, t = i - r * W;
     x.peer[r][(static_cast<size_t>(par) * n + me) * W + t] = tot[t];
@@ -163,7 +164,7 @@ __device__ void peer_allreduce(const PeerExchange& x, double* tot /* shared memo
   __syncthreads();
   if (threadIdx.x < static_cast<unsigned>(n)) {
     uint32_t* theirs = peer_flags(x.peer[threadIdx.x], n, W) + par * n + me;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(x.epoch) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
     const uint32_t* mine = peer_flags(x.peer[me], n, W) + par * n + threadIdx.x;
     uint32_t seen = 0;
     long spins = 0;
@@ -171,7 +172,7 @@ __device__ void peer_allreduce(const PeerExchange& x, double* tot /* shared memo
     const bool dead = x.status && *reinterpret_cast<volatile int*>(x.status) != 0;
     while (!dead) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-      if (seen == x.epoch) break;
+      if (seen == epoch) break;
       if (++spins > (1L << 24)) {
         if (x.status) *reinterpret_cast<volatile int*>(x.status) = 1;
         break;
@@ -255,7 +256,7 @@ __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int i
   if (it > 0) {
     sum_partials(summed ? 1 : d.n_tiles, part_cur, part_prop, J, cs.tot);
     __syncthreads();
-    if (!summed && d.xch.n > 1) peer_allreduce(d.xch, cs.tot, 2 * J);
+    if (!summed && d.xch.n > 1) peer_allreduce(d.xch, d.xch.epoch, cs.tot, 2 * J);
     // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----
     for (int c = threadIdx.x; c < J; c += blockDim.x) {
       const int which = cs.which[c];
