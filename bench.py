@@ -319,6 +319,17 @@ def run_b200(a):
                 traffic = json.load(open(tp)).get("fact_lane_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # why the bound is not HBM: the kernel's measured DRAM traffic per launch against the measured copy bandwidth
+        hbm = None
+        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if traffic and os.path.exists(mp):
+            try:
+                peak_gbs = float(json.load(open(mp))["hbm_gbs"])
+                gbs = traffic / (dev_ms / a.steps * 1e-3) / 1e9
+                hbm = {"achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+                       "peak_source": "MEASURED_PEAKS.json hbm_gbs"}
+            except Exception:
+                hbm = None
         cpu = None
         if not a.no_cpu:
             from oracle import pyoracle
@@ -346,7 +357,7 @@ def run_b200(a):
                          "peak_source": "own-measured FFMA microbenchmark (htm_measure_fp32_peak); "
                                         "MEASURED_PEAKS.json has no FP32 vector peak",
                          "flop_per_proposal": flop_per_prop, "mufu_gops_measured": mufu,
-                         "kernel": "fact_lane_kernel" if a.kernel != 1 else "fact_warp_kernel"},
+                         "kernel": "fact_lane_kernel" if a.kernel != 1 else "fact_warp_kernel", "hbm": hbm},
         }
         if gathered:
             line["nccl_gather"] = gathered
