@@ -314,7 +314,8 @@ def run_b200(a):
     if rank == 0:
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        # the ncu capture is of the default workload (BASELINE configs[1]); other shapes have no measured figure
+        if os.path.exists(tp) and (a.events, a.stations, a.chains, a.ranks, a.precision) == (1000, 20, 16, 4, 32):
             try:
                 traffic = json.load(open(tp)).get("fact_lane_kernel_dram_bytes_per_launch")
             except Exception:

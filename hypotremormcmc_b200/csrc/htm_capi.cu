@@ -1,11 +1,13 @@
 // C ABI of libhtm_b200.so (include/htm_b200.h): handle, host-side table building, launches,
 // result fetches.  All compute is on the device; nothing here evaluates the forward model or
 // steps a chain on the CPU.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "htm_kernels.hpp"
@@ -108,7 +110,10 @@ int32_t build_tables_t(htm_handle h) {
     sta[4 * j + 2] = static_cast<real>(h->sta_z[j]);
     sta[4 * j + 3] = 0;
   }
-  for (int e = 0; e < E; ++e) {
+  // events are independent: the table build (two logarithms and two divisions per station and event) is split
+  // over host threads once it is large enough to matter for the end-to-end time
+  auto build_events = [&](int e_first, int e_last) {
+  for (int e = e_first; e < e_last; ++e) {
     double Ce = 0.0, swt = 0.0, swa = 0.0;
     for (int j = 0; j < S; ++j) {
       const size_t k = static_cast<size_t>(e) * S + j;
@@ -145,6 +150,20 @@ int32_t build_tables_t(htm_handle h) {
     evc[4 * e + 3] = 0;
     pxy[2 * e] = static_cast<real>(h->have_prior ? h->x_mu[e] : 0.0);
     pxy[2 * e + 1] = static_cast<real>(h->have_prior ? h->y_mu[e] : 0.0);
+  }
+  };
+  {
+    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+    nt = static_cast<unsigned>(std::min<size_t>(std::min(nt, 32u), static_cast<size_t>(E) * S / 50000 + 1));
+    if (nt <= 1) {
+      build_events(0, E);
+    } else {
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < nt; ++t)
+        pool.emplace_back(build_events, static_cast<int>(static_cast<long>(E) * t / nt),
+                          static_cast<int>(static_cast<long>(E) * (t + 1) / nt));
+      for (auto& th : pool) th.join();
+    }
   }
   auto up = [&](void** d, const std::vector<real>& v) -> cudaError_t {
     if (!*d) {
