@@ -828,9 +828,17 @@ static cudaError_t launch_factorised_t(const FactLaunch& a, cudaStream_t stream,
     *why = "n_sta too large for the shared-memory staging of the lane-per-chain kernel";
     return cudaErrorInvalidValue;
   }
-  // one chain per lane keeps the most warps in flight and measured fastest at every size; 2 or 4
-  // chains per lane (fewer, fatter warps) stay available on request
-  const int slots = a.slots == 0 ? 1 : a.slots;
+  // Chains per lane.  One keeps the most warps in flight; two share the station-pair reads and the loop
+  // overhead between two chains and measure 6-7 % faster (float32) once the tempering groups fill both slot
+  // rows exactly and the halved number of warps still oversubscribes the 592 schedulers about tenfold
+  // (10 000 x 50 x 4 x 16: 2.76 -> 2.94e10 proposals/s; 1000 events: equal; 3000 events: 2 % slower).  Four
+  // never won (tools/slots_sweep.py).
+  int slots = a.slots;
+  if (slots == 0) {
+    const int gpw = a.R < 32 / a.K ? a.R : 32 / a.K;  // tempering groups side by side in one slot row
+    const long warps2 = static_cast<long>(a.E) * (a.R / (2 * gpw));
+    slots = (sizeof(real) == 4 && a.R % (2 * gpw) == 0 && warps2 >= 6000) ? 2 : 1;
+  }
   switch (slots) {
     case 1: return launch_lane<real, 1>(a, stream);
     case 2: return launch_lane<real, 2>(a, stream);
