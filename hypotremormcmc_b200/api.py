@@ -23,7 +23,7 @@ EXPORTS = [
     "htm_synchronize", "htm_replay", "htm_fetch_samples", "htm_fetch_likelihood",
     "htm_discard_samples", "htm_get_counts", "htm_get_histograms", "htm_device_ptr",
     "htm_last_run_stats", "htm_measure_fp32_peak", "htm_comm_unique_id", "htm_comm_init", "htm_gather",
-    "htm_comm_p2p_export", "htm_comm_p2p_import",
+    "htm_comm_p2p_export", "htm_comm_p2p_import", "htm_gather_samples",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library():
         "htm_comm_unique_id": [ctypes.c_char_p],
         "htm_comm_init": [vp, ctypes.c_char_p],
         "htm_gather": [vp, ctypes.POINTER(ctypes.c_uint32), lp, lp],
+        "htm_gather_samples": [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), dp, dp, dp, dp, dp],
         "htm_comm_p2p_export": [vp, ctypes.c_char_p],
         "htm_comm_p2p_import": [vp, ctypes.c_char_p],
     }
@@ -312,6 +313,21 @@ class HypoTremorB200:
 
     def comm_init(self, unique_id):
         self._ck(self.lib.htm_comm_init(self._h, ctypes.create_string_buffer(unique_id, 128)))
+
+    def gather_samples(self, rank, max_records=1 << 20):
+        """Collective fetch_samples (event-sharded factorised mode): hypocentres of ALL events on every shard."""
+        E_tot, S = self.cfg.n_events, self.n_sta
+        n = ctypes.c_int32()
+        cap = min(max_records, max(1, self.cfg.max_samples) * self.cfg.n_cool * self.n_procs)
+        it = np.empty(cap, dtype=np.int32)
+        vs, qs = np.empty(cap), np.empty(cap)
+        hypo = np.empty((cap, 3 * E_tot))
+        tc, ac = np.empty((cap, S)), np.empty((cap, S))
+        self._ck(self.lib.htm_gather_samples(self._h, rank, cap, ctypes.byref(n),
+                                             it.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                             _dptr(vs), _dptr(qs), _dptr(hypo), _dptr(tc), _dptr(ac)))
+        k = n.value
+        return dict(iter=it[:k], vs=vs[:k], qs=qs[:k], hypo=hypo[:k], t_corr=tc[:k], a_corr=ac[:k])
 
     def comm_p2p_export(self):
         """64-byte CUDA IPC handle of this shard's exchange buffer (event-sharded blocked Gibbs)."""

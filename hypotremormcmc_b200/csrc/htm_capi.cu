@@ -1352,6 +1352,60 @@ int32_t htm_gather(htm_handle h, uint32_t* hist_all, int64_t n_propose[7], int64
   return HTM_OK;
 }
 
+int32_t htm_gather_samples(htm_handle h, int32_t rank, int32_t max_records, int32_t* n_records, int32_t* iter,
+                           double* vs, double* qs, double* hypo_all, double* t_corr, double* a_corr) {
+  if (!h || !n_records) return fail(h, HTM_ERR_ARG, "null argument");
+  if (!h->comm) return fail(h, HTM_ERR_STATE, "htm_comm_init was not called");
+  if (h->cfg.mode != HTM_MODE_FACTORISED)
+    return fail(h, HTM_ERR_UNSUPPORTED, "sample gather serves the event-sharded factorised mode (the other modes hold every event on every shard)");
+  const int W = h->cfg.shard_count, E = h->E;
+  int biggest = 0;
+  for (int r = 0; r < W; ++r) {
+    int lo, hi;
+    shard_bounds(h->E_total, r, W, &lo, &hi);
+    if (hi - lo > biggest) biggest = hi - lo;
+  }
+  // this shard's block, exactly as htm_fetch_samples delivers it (the cursors advance identically on every
+  // shard because the recorded iterations are the same everywhere)
+  std::vector<double> mine(hypo_all ? static_cast<size_t>(max_records > 0 ? max_records : 0) * 3 * E : 0);
+  const int32_t rc = htm_fetch_samples(h, rank, max_records, n_records, iter, vs, qs, hypo_all ? mine.data() : nullptr,
+                                       t_corr, a_corr);
+  if (rc != HTM_OK || !hypo_all) return rc;
+  const int n = *n_records;
+  if (n == 0) return HTM_OK;
+  // all-gather of the [n][3*E_shard] blocks, padded to the largest shard, over NVLink
+  const size_t blk = static_cast<size_t>(n) * 3 * biggest;  // doubles per shard
+  double *d_send = nullptr, *d_recv = nullptr;
+  std::vector<double> send(blk, 0.0), recv(blk * W);
+  for (int k = 0; k < n; ++k)
+    std::memcpy(send.data() + static_cast<size_t>(k) * 3 * biggest, mine.data() + static_cast<size_t>(k) * 3 * E, sizeof(double) * 3 * E);
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  HTM_CK(h, cudaMalloc(&d_send, blk * sizeof(double)));
+  cudaError_t e = cudaMalloc(&d_recv, blk * W * sizeof(double));
+  if (e != cudaSuccess) {
+    free_dev(d_send);
+    HTM_CK(h, e);
+  }
+  std::string why;
+  e = cudaMemcpyAsync(d_send, send.data(), blk * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  const bool ok = e == cudaSuccess && nccl_allgather_u32(h->comm, d_send, d_recv, blk * 2, h->stream, &why);
+  if (ok) e = cudaMemcpyAsync(recv.data(), d_recv, blk * W * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (ok && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  free_dev(d_send);
+  free_dev(d_recv);
+  if (!ok && !why.empty()) return fail(h, HTM_ERR_CUDA, why);
+  HTM_CK(h, e);
+  for (int r = 0; r < W; ++r) {
+    int lo, hi;
+    shard_bounds(h->E_total, r, W, &lo, &hi);
+    for (int k = 0; k < n; ++k)
+      std::memcpy(hypo_all + static_cast<size_t>(k) * 3 * h->E_total + static_cast<size_t>(3) * lo,
+                  recv.data() + static_cast<size_t>(r) * blk + static_cast<size_t>(k) * 3 * biggest,
+                  sizeof(double) * 3 * (hi - lo));
+  }
+  return HTM_OK;
+}
+
 int32_t htm_device_ptr(htm_handle h, int32_t what, void** ptr, int64_t* n_bytes) {
   if (!h || !ptr || !n_bytes) return fail(h, HTM_ERR_ARG, "null argument");
   if (what == 0) {

@@ -274,6 +274,17 @@ module htm_b200_binding
        integer(c_int32_t) :: rc
      end function htm_gather
 
+     function htm_gather_samples(h, rank, max_records, n_records, iter, vs, qs, hypo_all, t_corr, a_corr) &
+          & bind(c, name="htm_gather_samples") result(rc)
+       import
+       type(c_ptr), value :: h
+       integer(c_int32_t), value :: rank, max_records
+       integer(c_int32_t), intent(out) :: n_records
+       integer(c_int32_t), intent(out) :: iter(*)
+       real(c_double), intent(out) :: vs(*), qs(*), hypo_all(*), t_corr(*), a_corr(*)
+       integer(c_int32_t) :: rc
+     end function htm_gather_samples
+
      ! handles of all shards, 64 bytes each, in shard order (MPI_Allgather of the exported one)
      function htm_comm_p2p_export(h, handle) bind(c, name="htm_comm_p2p_export") result(rc)
        import

@@ -279,6 +279,14 @@ int32_t htm_comm_unique_id(char id[128]);
 int32_t htm_comm_init(htm_handle h, const char id[128]);
 int32_t htm_gather(htm_handle h, uint32_t* hist_all, int64_t n_propose[7], int64_t n_accept[7]);
 
+/* Collective form of htm_fetch_samples for the event-sharded factorised mode: every shard receives the records
+ * of virtual rank `rank` with the hypocentres of ALL events, hypo_all: [n][3*n_events_total] (all-gather of the
+ * shards' blocks over NVLink), so that one process can write the reference's hypo.RR.out records
+ * (src/hypo_tremor_mcmc.f90:272-274 writes all 3E values per record).  Every shard must call with the same
+ * arguments; it consumes the pending records exactly as htm_fetch_samples does. */
+int32_t htm_gather_samples(htm_handle h, int32_t rank, int32_t max_records, int32_t* n_records, int32_t* iter,
+                           double* vs, double* qs, double* hypo_all, double* t_corr, double* a_corr);
+
 /* Event-sharded blocked Gibbs (cfg.gibbs_shard_events): the one exchange step of the path -- the sum over
  * ALL events of every joint chain's log-likelihood, needed for each shared-parameter move (the reference
  * recomputes it with forward%calc_log_likelihood, src/cls_forward.f90:268-303, on one rank) -- done inside

@@ -815,6 +815,25 @@ def test_abi_level_nccl_gather_single_shard():
         assert np.array_equal(p, p0) and np.array_equal(a, a0)
 
 
+def test_event_sharded_factorised_gathers_on_two_gpus():
+    """Mode B, events sharded over two processes / GPUs: htm_gather (histograms, counters) and htm_gather_samples
+    (records with the hypocentres of all events) equal the unsharded run."""
+    import subprocess, sys, os, socket
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), "tools/comm_check.py"],
+                       cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("gathered samples == unsharded samples: True") == 2 and "gathered == unsharded: True" in r.stdout
+
+
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 def test_event_sharded_gibbs_on_two_gpus(exchange):
     """Event-sharded joint chains, one process per GPU: the per-iteration exchange of the per-chain sums (fused

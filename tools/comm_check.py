@@ -1,6 +1,7 @@
 """Multi-GPU check of the ABI-level gather (run under torchrun, one rank per GPU):
 every rank runs ITS shard of events, then htm_gather (NCCL inside the library) must reproduce the
-histograms and counters of the unsharded run that rank 0 also does."""
+histograms and counters of the unsharded run that rank 0 also does, and htm_gather_samples must deliver, on
+every rank, the records of each virtual rank with the hypocentres of ALL events."""
 import os
 import sys
 
@@ -17,7 +18,7 @@ dist.init_process_group("gloo")     # only to hand the NCCL id around (the host 
 E, S, R, K = 1003, 20, 4, 16
 syn = H.Synthetic(E, S, 9)
 base = dict(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=300, n_burn=0, n_interval=10,
-            mode=H.MODE_FACTORISED, precision=32, hist_bins=32, solve_vs=0, solve_t_corr=0, solve_qs=0, solve_a_corr=0)
+            mode=H.MODE_FACTORISED, precision=32, hist_bins=32, max_samples=40, solve_vs=0, solve_t_corr=0, solve_qs=0, solve_a_corr=0)
 ids = [H.HypoTremorB200.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 cfg = H.default_config(device=local, shard_rank=rank, shard_count=world, **base)
@@ -27,6 +28,18 @@ with H.HypoTremorB200(cfg) as g:
     g.run(1, 300)
     g.comm_init(ids[0])
     hist, p, a = g.gather()
+    smp = [g.gather_samples(r) for r in range(R)]
+ok_s = True
+with H.HypoTremorB200(H.default_config(device=local, **base)) as g:  # the unsharded run, on every rank
+    g.load(syn)
+    g.init_chains()
+    g.run(1, 300)
+    for r in range(R):
+        s0 = g.fetch_samples(r)
+        ok_s &= bool(np.array_equal(s0["iter"], smp[r]["iter"]) and np.array_equal(s0["hypo"], smp[r]["hypo"]))
+        ok_s &= len(s0["iter"]) == 30 and smp[r]["hypo"].shape == (30, 3 * E)
+print("comm_check rank %d/%d: gathered samples == unsharded samples: %s" % (rank, world, ok_s))
+assert ok_s
 if rank == 0:
     with H.HypoTremorB200(H.default_config(device=local, **base)) as g:
         g.load(syn)
