@@ -508,7 +508,8 @@ def gibbs_path(request, monkeypatch):
 
 
 @pytest.mark.parametrize("E,S,R,K,solve", [(5, 9, 2, 3, (1, 1, 1, 1)), (40, 20, 3, 4, (1, 0, 1, 0)), (3, 33, 1, 2, (0, 1, 0, 1)),
-                                            (70, 12, 5, 2, (1, 1, 1, 1)), (4, 8, 2, 3, (0, 0, 0, 0))])
+                                            (70, 12, 5, 2, (1, 1, 1, 1)), (4, 8, 2, 3, (0, 0, 0, 0)),
+                                            (1, 10, 4, 5, (1, 1, 1, 1))])  # the last: the shape of BASELINE configs[0]
 def test_blocked_gibbs_float64_step_exact(gibbs_path, E, S, R, K, solve):
     syn = H.Synthetic(E, S, 40 + E)
     cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=60, n_burn=12, n_interval=6,
