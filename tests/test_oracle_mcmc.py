@@ -227,3 +227,39 @@ def test_factorised_sharding_is_invariant():
     for f in ("proposal_type", "prior_ok", "accepted", "log_likelihood"):
         assert np.array_equal(tf[f][:, lo:lo + sh.n_events], tp[f])
     assert np.array_equal(sf[:, lo:lo + sh.n_events], sp)
+
+
+def test_blocked_gibbs_oracle_bookkeeping():
+    """Mode C statement: per iteration every cold chain proposes one hypocentre coordinate PER EVENT and one shared
+    parameter; records follow the reference's rules; temperatures only move; chunked == single run."""
+    syn, cfg = small(mode=H.MODE_BLOCKED_GIBBS, n_iter=300, n_burn=100, n_interval=10, n_chains=3, E=4)
+    R, K, E = cfg.n_procs, cfg.n_chains, syn.n_events
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    temps0 = sorted(o.get_chain_state(r, k)["temp"] for r in range(R) for k in range(K))
+    tr, sw = o.run(1, 300)
+    p, a = o.get_counts()
+    n_cold = R * cfg.n_cool
+    assert p[4:].sum() == 300 * E * n_cold and p[:4].sum() == 300 * n_cold and (a <= p).all()
+    # trace: [iteration][event 0..E-1, then the shared-parameter row][chain]
+    assert tr["proposal_type"].shape == (300, E + 1, R, K)
+    assert set(np.unique(tr["proposal_type"][:, :E])) <= {5, 6, 7} and set(np.unique(tr["proposal_type"][:, E])) <= {1, 2, 3, 4}
+    smp = [o.fetch_samples(r) for r in range(R)]
+    lik = [o.fetch_likelihood(r) for r in range(R)]
+    assert sum(len(s["iter"]) for s in smp) == 20 * n_cold        # iterations 101, 111, ..., 291
+    assert sum(len(l[0]) for l in lik) == 30 * n_cold             # the likelihood file includes the burn-in
+    assert sorted(o.get_chain_state(r, k)["temp"] for r in range(R) for k in range(K)) == temps0
+    # the carried total is the likelihood of the state
+    for r in range(R):
+        for k in range(K):
+            st = o.get_chain_state(r, k)
+            L = o.loglik(st["hypo"][None], st["t_corr"][None], st["a_corr"][None], [st["vs"]], [st["qs"]])[0]
+            assert abs(L - st["log_likelihood"]) <= 1e-9 * max(1.0, abs(L))
+    # chunking does not change anything
+    o2 = Oracle(cfg, syn)
+    o2.init_chains()
+    t1, s1 = o2.run(1, 77)
+    t2, s2 = o2.run(78, 300)
+    for f in ("proposal_type", "index", "prior_ok", "accepted", "log_likelihood"):
+        assert np.array_equal(np.concatenate([t1[f], t2[f]]), tr[f]), f
+    assert np.array_equal(np.concatenate([s1, s2]), sw)
