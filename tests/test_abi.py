@@ -100,3 +100,35 @@ def test_product_does_not_touch_the_oracle():
                     txt = open(os.path.join(dp, f), errors="ignore").read()
                     assert "htm_oracle" not in txt and "pyoracle" not in txt and "libhtm_oracle" not in txt, \
                         "%s references the oracle" % os.path.join(dp, f)
+
+
+def _build_c_client(tmp_path):
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "minimal_c_client")
+    libdir = os.path.join(ROOT, "hypotremormcmc_b200", "csrc")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-O2", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "minimal_c_client.c"), "-L" + libdir, "-lhtm_b200",
+                        "-Wl,-rpath," + libdir, "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+    return exe
+
+
+def test_plain_c_client_links_and_fails_loudly_without_a_device(tmp_path):
+    """examples/minimal_c_client.c: the ABI is usable from plain C; with no GPU the first compute call stops it."""
+    import subprocess
+    if have_gpu():
+        pytest.skip("GPU present: covered by the gpu-marked twin")
+    r = subprocess.run([_build_c_client(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_client_runs_on_the_gpu(tmp_path):
+    import subprocess
+    r = subprocess.run([_build_c_client(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("15 records of virtual rank 0; last: iteration 1901"), r.stdout
+    assert "cold x/y/z proposals 256000" in r.stdout   # 2000 iterations x 64 events x 2 cold chains
