@@ -74,6 +74,13 @@ void hto_set_rank_shard(void* h, uint32_t chain_offset, uint32_t j_total, uint32
   o->swap_stream = swap_stream;
 }
 
+// event shards of one joint ensemble (blocked Gibbs): see Oracle::sum_hook
+void hto_set_sum_hook(void* h, void (*hook)(double*, void*), void* user) {
+  Oracle* o = static_cast<Oracle*>(h);
+  o->sum_hook = hook;
+  o->sum_hook_user = user;
+}
+
 void hto_set_globals(void* h, double vs, double qs, const double* tc, const double* ac) {
   Oracle* o = static_cast<Oracle*>(h);
   o->fixed_vs = vs;

@@ -601,6 +601,14 @@ struct Oracle {
       tr->log_likelihood = g.Le[e];
     }
   }
+  // Event shards of ONE joint ensemble (cfg.gibbs_shard_events on the device): this oracle holds a slice of
+  // the events of every chain; the two sums over events that judge a shared-parameter move must then cover
+  // all shards.  The hook receives this shard's {sum of L_e, sum of L_e under the proposal} of one chain and
+  // returns the sums over all shards (the host test all-gathers them and adds in shard order, as the device's
+  // peer-memory exchange does).  Null = single shard.
+  typedef void (*SumHook)(double* two, void* user);
+  SumHook sum_hook = nullptr;
+  void* sum_hook_user = nullptr;
   void global_step_gibbs(int32_t c, int32_t it, htm_step_trace* tr) {
     GibbsChain& g = gc[c];
     g.L = sum_events(g.Le);
@@ -644,7 +652,13 @@ struct Oracle {
       const double xyz[3] = {g.x[e], g.y[e], g.z[e]};
       Lp[e] = fwd.event_log_likelihood(e, xyz, g.tc.data(), g.vs, g.ac.data(), g.qs);
     }
-    const double L_new = sum_events(Lp);
+    double L_new = sum_events(Lp);
+    if (sum_hook) {
+      double two[2] = {g.L, L_new};
+      sum_hook(two, sum_hook_user);
+      g.L = two[0];
+      L_new = two[1];
+    }
     const double ratio = (L_new - g.L) / g.temp + lpr;
     const double rr = Philox::u_co(wb[0]);
     bool acc = false;

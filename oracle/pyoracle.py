@@ -103,6 +103,19 @@ class Oracle:
         self.L.hto_set_rank_shard(self.h, ctypes.c_uint32(chain_offset), ctypes.c_uint32(j_total),
                                   ctypes.c_uint32(swap_stream))
 
+    def set_sum_hook(self, fn):
+        """blocked-Gibbs mode, event shards of one joint ensemble: fn(cur, prop) -> (cur, prop) summed over all
+        shards; called once per chain and iteration, in chain order (so a collective inside fn lines up)"""
+        proto = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_double), ctypes.c_void_p)
+
+        def tramp(two, _user):
+            a, b = fn(two[0], two[1])
+            two[0], two[1] = a, b
+
+        self._sum_hook = proto(tramp)  # keep the trampoline alive
+        self.L.hto_set_sum_hook.argtypes = [ctypes.c_void_p, proto, ctypes.c_void_p]
+        self.L.hto_set_sum_hook(self.h, self._sum_hook, None)
+
     def set_globals(self, vs, qs, t_corr, a_corr):
         tc = np.ascontiguousarray(t_corr, dtype=np.float64)
         ac = np.ascontiguousarray(a_corr, dtype=np.float64)

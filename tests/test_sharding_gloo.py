@@ -96,3 +96,74 @@ def test_shard_bounds_cover_everything():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- blocked Gibbs with the events of every joint chain sharded (the one exchange step of the path) --------------
+GE, GS, GR, GK, G_IT = 9, 6, 2, 3, 80
+
+
+def gibbs_cfg(**kw):
+    return H.default_config(n_sta=GS, n_events=GE, n_procs=GR, n_chains=GK, n_cool=1, n_iter=G_IT, n_burn=10,
+                            n_interval=5, mode=H.MODE_BLOCKED_GIBBS, precision=64, **kw)
+
+
+def gibbs_worker(rank, world, port, out):
+    """One rank = one event shard of ALL joint chains.  Per chain and iteration the two sums over events (current,
+    proposed) are all-gathered and added in shard order -- what peer_allreduce (csrc/htm_gibbs_decide.cuh) does on
+    the device -- so every rank takes the same decisions."""
+    from oracle.pyoracle import Oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    syn = H.Synthetic(GE, GS, 78)
+    sh = syn.shard(rank, world)
+    o = Oracle(gibbs_cfg(shard_rank=rank, shard_count=world, gibbs_shard_events=1), sh, event_offset=sh.event_offset)
+    o.init_chains()
+
+    def exchange(cur, prop):
+        mine = torch.tensor([cur, prop], dtype=torch.float64)
+        parts = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        a = b = 0.0
+        for p in parts:  # shard order: the same operands in the same order on every rank
+            a += float(p[0])
+            b += float(p[1])
+        return a, b
+
+    o.set_sum_hook(exchange)
+    tr, sw = o.run(1, G_IT)
+    out[rank] = dict(lo=sh.event_offset, n=sh.n_events, tr={k: np.array(tr[k]) for k in tr.dtype.names}, sw=np.array(sw),
+                     state=o.get_chain_state(1, 1), samples=o.fetch_samples(0), lik=o.fetch_likelihood(0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_event_sharded_blocked_gibbs_equals_unsharded(world):
+    from oracle.pyoracle import Oracle
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(gibbs_worker, args=(world, free_port(), out), nprocs=world, join=True)
+    syn = H.Synthetic(GE, GS, 78)
+    u = Oracle(gibbs_cfg(), syn)
+    u.init_chains()
+    tr_u, sw_u = u.run(1, G_IT)
+    st_u, smp_u, lik_u = u.get_chain_state(1, 1), u.fetch_samples(0), u.fetch_likelihood(0)
+    covered = 0
+    for rank in range(world):
+        r = out[rank]
+        lo, n = r["lo"], r["n"]
+        covered += n
+        for f in ("proposal_type", "prior_ok", "accepted"):
+            assert np.array_equal(r["tr"][f][:, :n], tr_u[f][:, lo:lo + n]), (rank, f)      # this shard's events
+            assert np.array_equal(r["tr"][f][:, n], tr_u[f][:, GE]), (rank, f)               # shared-parameter row
+        assert np.array_equal(r["tr"]["index"][:, :n] + 3 * lo, tr_u["index"][:, lo:lo + n])  # indices are shard-local
+        assert np.array_equal(r["sw"], sw_u)                                                # every rank: the same swaps
+        assert np.allclose(r["tr"]["log_likelihood"][:, n], tr_u["log_likelihood"][:, GE], rtol=1e-12, atol=0)
+        assert abs(r["state"]["vs"] - st_u["vs"]) < 1e-13 and r["state"]["temp"] == st_u["temp"]
+        assert np.allclose(r["state"]["hypo"], st_u["hypo"][3 * lo:3 * (lo + n)], rtol=1e-12, atol=1e-12)
+        assert np.array_equal(r["samples"]["iter"], smp_u["iter"])
+        assert np.allclose(r["samples"]["hypo"], smp_u["hypo"][:, 3 * lo:3 * (lo + n)], rtol=1e-12, atol=1e-12)
+        assert np.allclose(r["samples"]["t_corr"], smp_u["t_corr"], atol=1e-13)
+        assert np.array_equal(r["lik"][0], lik_u[0]) and np.allclose(r["lik"][1], lik_u[1], rtol=1e-12)
+    assert covered == GE
