@@ -14,7 +14,10 @@ Numbers on the JSON line:
             (htm_set_observations H2D -> htm_init_chains -> htm_run -> fetch samples, likelihood,
             histograms, counts D2H), host wall clock
   roofline  achieved algorithmic FLOP/s ((30*S+64) per proposal) of the
-            dominant kernel / own-measured FFMA peak (no driver-measured FP32 peak exists)
+            dominant kernel / own-measured FFMA peak (no driver-measured FP32 peak exists);
+            roofline.traffic = DRAM bytes per launch from the committed ncu capture (default workload only)
+            and roofline.hbm = that traffic per launch time against MEASURED_PEAKS.json's copy bandwidth
+            (the evidence that the kernel is not HBM-bound)
   cpu_baseline  the C++ restatement of the reference algorithm (oracle/, mode A: joint chain, one
             scalar per iteration, one swap per iteration), one thread per virtual rank, on a
             bounded sample of the same workload.  The real Fortran/MPI binary cannot be built in
