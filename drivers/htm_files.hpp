@@ -8,7 +8,8 @@
 //   selected_win.dat `id  time` per line                              (src/hypo_tremor_mcmc.f90:75-87)
 //   opt_data.NNNNNN.dat  n_sta lines: X Y Z t t_stdv a a_stdv          (src/cls_obs_data.f90:83-112)
 //   *.RR.out         stream records int32 iter + float64[...]          (src/hypo_tremor_mcmc.f90:216-233,270-280)
-//   proposal_count.txt  '(A,2I10)' of '"label"', n_propose, n_accept   (src/cls_parallel.f90:270-278)
+//   proposal_count.txt  '(A,2I20)' of '"label"', n_propose, n_accept   (src/cls_parallel.f90:270-278 uses 2I10: the
+//                       batched modes count every event and cold chain, so 10 digits overflow -- both drivers widen it)
 #pragma once
 #include <algorithm>
 #include <cctype>
@@ -169,7 +170,9 @@ struct Observations {
           size_t got;
           while ((got = std::fread(chunk, 1, sizeof(chunk), f)) > 0) buf.append(chunk, got);
           std::fclose(f);
-          // list-directed reals: 7 per station, separated by blanks, commas or line ends
+          // one list-directed read per station record, as `read(io,*)` of 7 items does (src/cls_obs_data.f90:92-99):
+          // the 7 items may continue over following lines; whatever follows the 7th on its line is skipped, and
+          // the next station starts on a new line
           size_t pos = 0;
           auto next = [&]() -> bool {
             while (pos < buf.size() && (std::isspace(static_cast<unsigned char>(buf[pos])) || buf[pos] == ',')) ++pos;
@@ -181,13 +184,25 @@ struct Observations {
           };
           for (int j = 0; j < n_sta; ++j) {
             const size_t k = i * n_sta + j;
-            for (int c = 0; c < 7; ++c) {
+            int c = 0;
+            while (c < 7) {
               if (!next()) throw std::runtime_error(std::string("short obs file ") + fname);
-              if (c == 3) t_obs[k] = parse_real("t_obs", tok);
-              if (c == 4) t_stdv[k] = parse_real("t_stdv", tok);
-              if (c == 5) a_obs[k] = parse_real("a_obs", tok);
-              if (c == 6) a_stdv[k] = parse_real("a_stdv", tok);
+              // r*c repeat form of list-directed input (e.g. 2*0.0)
+              int rep = 1;
+              std::string val = tok;
+              const size_t star = tok.find('*');
+              if (star != std::string::npos && star > 0 && tok.find_first_not_of("0123456789") == star) {
+                rep = std::atoi(tok.substr(0, star).c_str());
+                val = tok.substr(star + 1);
+              }
+              for (int q = 0; q < rep && c < 7; ++q, ++c) {
+                if (c == 3) t_obs[k] = parse_real("t_obs", val);
+                if (c == 4) t_stdv[k] = parse_real("t_stdv", val);
+                if (c == 5) a_obs[k] = parse_real("a_obs", val);
+                if (c == 6) a_stdv[k] = parse_real("a_stdv", val);
+              }
             }
+            while (pos < buf.size() && buf[pos] != '\n') ++pos;  // rest of the record's last line
           }
         } catch (const std::exception& e) {
           std::lock_guard<std::mutex> g(err_lock);

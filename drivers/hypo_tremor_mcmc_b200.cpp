@@ -167,7 +167,7 @@ int main(int argc, char** argv) {
     check(h, htm_get_counts(h, np, na), "htm_get_counts");
     static const char* label[7] = {"vs   ", "t_cor", "qs   ", "a_cor", "x    ", "y    ", "z    "};  // character(5)
     FILE* pc = std::fopen("proposal_count.txt", "w");
-    for (int k = 0; k < 7; ++k) std::fprintf(pc, "\"%s\"%10lld%10lld\n", label[k], static_cast<long long>(np[k]), static_cast<long long>(na[k]));
+    for (int k = 0; k < 7; ++k) std::fprintf(pc, "\"%s\"%20lld%20lld\n", label[k], static_cast<long long>(np[k]), static_cast<long long>(na[k]));
     std::fclose(pc);
     for (int r = 0; r < R; ++r) {
       f_hypo[r].close();

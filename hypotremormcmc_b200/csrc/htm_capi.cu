@@ -26,7 +26,18 @@ struct htm_handle_s {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool have_sta = false, have_obs = false, have_prior = false, tables_ok = false, chains_ready = false;
-  std::vector<double> sta_x, sta_y, sta_z, t_obs, t_stdv, a_obs, a_stdv, x_mu, y_mu;
+  // raw float64 inputs: pinned host staging (the library copies inputs during the call and keeps no caller
+  // pointer) -> ONE async H2D per set_* call -> device-side table build (htm_tables.cu).  Layout in doubles:
+  // obs [4][E][S] | sta [3][S] | xy_mu [2][E] | fixed station terms [2][S]
+  double* pin_in = nullptr;
+  double* d_in = nullptr;
+  bool pin_in_pinned = false;
+  cudaEvent_t ev_in = nullptr;  // last H2D out of pin_in: the next set_* call waits for it before overwriting
+  size_t off_obs() const { return 0; }
+  size_t off_sta() const { return static_cast<size_t>(4) * E * S; }
+  size_t off_xy() const { return off_sta() + static_cast<size_t>(3) * S; }
+  size_t off_g() const { return off_xy() + static_cast<size_t>(2) * E; }
+  size_t n_in() const { return off_g() + static_cast<size_t>(2) * S; }
   double g_vs = 0, g_qs = 0;
   std::vector<double> g_tc, g_ac;
   // device tables
@@ -40,7 +51,13 @@ struct htm_handle_s {
   void* d_samples = nullptr;
   int rec_cap = 0, rec_origin = 0, rec_pending = 0;
   std::vector<int> cur_samp, cur_lik;  // per rank, in recorded iterations consumed
-  std::vector<char> host_samples;      // host copy of the pending part of the ring
+  // Sample output: every htm_run queues, on a second stream behind its kernel, the device-to-host copy of the
+  // ring slots it fills into a pinned host mirror of the ring -- the copy overlaps the next htm_run chunk and
+  // htm_fetch_* only wait for the copy event.
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t ev_run = nullptr, ev_copy = nullptr;
+  char* pin_samples = nullptr;  // mode B: mirror of d_samples; mode C: mirror of the seven record arrays
+  bool pin_samples_pinned = false;
   bool host_samples_valid = false;
   // mode A state
   double *d_hypo = nullptr, *d_tc = nullptr, *d_ac = nullptr, *d_vs = nullptr, *d_qs = nullptr, *d_temp = nullptr,
@@ -52,9 +69,9 @@ struct htm_handle_s {
   GibbsLaunch gl;
   std::vector<void*> gibbs_bufs;
   int n_cold_total = 0;
-  std::vector<char> host_hypo_rec;
-  std::vector<int> host_rec_chain;
-  std::vector<double> host_rec_vs, host_rec_qs, host_rec_L, host_rec_tc, host_rec_ac;
+  char* host_hypo_rec = nullptr;  // carved out of pin_samples (alloc_state)
+  int* host_rec_chain = nullptr;
+  double *host_rec_vs = nullptr, *host_rec_qs = nullptr, *host_rec_L = nullptr, *host_rec_tc = nullptr, *host_rec_ac = nullptr;
   // multi-GPU (event shards): NCCL communicator, created by htm_comm_init
   void* comm = nullptr;
   // event-sharded blocked Gibbs: per-iteration exchange through peer memory (htm_comm_p2p_export / _import)
@@ -94,100 +111,81 @@ void shard_bounds(int n, int rank, int count, int* lo, int* hi) {
   *hi = *lo + base + (rank < rem ? 1 : 0);
 }
 
-// Build and upload sta4 / obs4 / obs4_raw / evc4 / prior_xy (layouts: htm_forward.cuh).
-// init_forward's rule for degenerate sigmas is applied here (src/cls_forward.f90:78-90):
-// the branch looks at t_stdv only; the "else" sets precision 1 and log sigma := 1.0.
-template <typename real>
-int32_t build_tables_t(htm_handle h) {
-  const int E = h->E, S = h->S;
-  const double l2ph = 0.5 * std::log(2.0 * std::acos(-1.0));
-  const bool ut = h->cfg.use_time != 0, ua = h->cfg.use_amp != 0;
-  std::vector<real> sta(4 * static_cast<size_t>(S)), obs(4 * static_cast<size_t>(E) * S),
-      raw(4 * static_cast<size_t>(E) * S), evc(4 * static_cast<size_t>(E)), pxy(2 * static_cast<size_t>(E));
-  for (int j = 0; j < S; ++j) {
-    sta[4 * j] = static_cast<real>(h->sta_x[j]);
-    sta[4 * j + 1] = static_cast<real>(h->sta_y[j]);
-    sta[4 * j + 2] = static_cast<real>(h->sta_z[j]);
-    sta[4 * j + 3] = 0;
+// Event-sharded blocked Gibbs: after a peer failed to answer an exchange (htm_gibbs_decide.cuh: peer_allreduce)
+// the kernels stop taking decisions and the shards have diverged -- every entry point that returns results
+// calls this after synchronising the stream and fails hard instead of handing out stale numbers.
+int32_t check_exchange(htm_handle h) {
+  if (!h->d_xch_status) return HTM_OK;
+  int st = 0;
+  HTM_CK(h, cudaMemcpy(&st, h->d_xch_status, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st != 0)
+    return fail(h, HTM_ERR_CUDA,
+                "peer-memory exchange timed out: a shard did not reach the same iteration (results of this run are "
+                "invalid on every shard; raise HTM_XCH_TIMEOUT_S if the shards are legitimately that far apart)");
+  return HTM_OK;
+}
+
+// pinned when possible (asynchronous copies), plain host memory otherwise (copies still work, just synchronously)
+void* host_alloc(size_t bytes, bool* pinned) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocDefault) == cudaSuccess) {
+    *pinned = true;
+    return p;
   }
-  // events are independent: the table build (two logarithms and two divisions per station and event) is split
-  // over host threads once it is large enough to matter for the end-to-end time
-  auto build_events = [&](int e_first, int e_last) {
-  for (int e = e_first; e < e_last; ++e) {
-    double Ce = 0.0, swt = 0.0, swa = 0.0;
-    for (int j = 0; j < S; ++j) {
-      const size_t k = static_cast<size_t>(e) * S + j;
-      double wt, wa, lt, la;
-      if (h->t_stdv[k] > 1.e-16) {
-        lt = std::log(h->t_stdv[k]);
-        wt = 1.0 / (h->t_stdv[k] * h->t_stdv[k]);
-        la = std::log(h->a_stdv[k]);
-        wa = 1.0 / (h->a_stdv[k] * h->a_stdv[k]);
-      } else {
-        lt = 1.0;
-        wt = 1.0;
-        la = 1.0;
-        wa = 1.0;
-      }
-      if (!ut) wt = 0.0;
-      if (!ua) wa = 0.0;
-      if (ut) Ce += l2ph + lt;
-      if (ua) Ce += l2ph + la;
-      swt += wt;
-      swa += wa;
-      raw[4 * k] = static_cast<real>(h->t_obs[k]);
-      raw[4 * k + 1] = static_cast<real>(wt);
-      raw[4 * k + 2] = static_cast<real>(h->a_obs[k]);
-      raw[4 * k + 3] = static_cast<real>(wa);
-      obs[4 * k] = static_cast<real>(h->t_obs[k] + h->g_tc[j]);
-      obs[4 * k + 1] = static_cast<real>(wt);
-      obs[4 * k + 2] = static_cast<real>(h->a_obs[k] + h->g_ac[j]);
-      obs[4 * k + 3] = static_cast<real>(wa);
-    }
-    evc[4 * e] = static_cast<real>(Ce);
-    evc[4 * e + 1] = static_cast<real>(swt > 0 ? 1.0 / swt : 0.0);
-    evc[4 * e + 2] = static_cast<real>(swa > 0 ? 1.0 / swa : 0.0);
-    evc[4 * e + 3] = 0;
-    pxy[2 * e] = static_cast<real>(h->have_prior ? h->x_mu[e] : 0.0);
-    pxy[2 * e + 1] = static_cast<real>(h->have_prior ? h->y_mu[e] : 0.0);
+  (void)cudaGetLastError();
+  *pinned = false;
+  return std::malloc(bytes ? bytes : 8);
+}
+void host_free(void* p, bool pinned) {
+  if (!p) return;
+  if (pinned)
+    cudaFreeHost(p);
+  else
+    std::free(p);
+}
+
+// Stage `n` doubles of one input segment: caller memory -> pinned staging -> device, asynchronously.  The
+// previous copy out of the staging buffer must have finished before it is overwritten.
+int32_t stage_input(htm_handle h, size_t off, const double* const* src, const size_t* len, int n_src) {
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  HTM_CK(h, cudaEventSynchronize(h->ev_in));
+  size_t o = off;
+  for (int i = 0; i < n_src; ++i) {
+    std::memcpy(h->pin_in + o, src[i], len[i] * sizeof(double));
+    o += len[i];
   }
-  };
-  {
-    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
-    nt = static_cast<unsigned>(std::min<size_t>(std::min(nt, 32u), static_cast<size_t>(E) * S / 50000 + 1));
-    if (nt <= 1) {
-      build_events(0, E);
-    } else {
-      std::vector<std::thread> pool;
-      for (unsigned t = 0; t < nt; ++t)
-        pool.emplace_back(build_events, static_cast<int>(static_cast<long>(E) * t / nt),
-                          static_cast<int>(static_cast<long>(E) * (t + 1) / nt));
-      for (auto& th : pool) th.join();
-    }
-  }
-  auto up = [&](void** d, const std::vector<real>& v) -> cudaError_t {
-    if (!*d) {
-      cudaError_t e = cudaMalloc(d, v.size() * sizeof(real));
-      if (e != cudaSuccess) return e;
-    }
-    return cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(real), cudaMemcpyHostToDevice, h->stream);
-  };
-  HTM_CK(h, up(&h->d_sta4, sta));
-  HTM_CK(h, up(&h->d_obs4, obs));
-  HTM_CK(h, up(&h->d_obs4_raw, raw));
-  HTM_CK(h, up(&h->d_evc4, evc));
-  HTM_CK(h, up(&h->d_prior_xy, pxy));
-  if (h->cfg.mode == HTM_MODE_REPLAY) {
-    std::vector<double> p64(2 * static_cast<size_t>(E));
-    for (int e = 0; e < E; ++e) {
-      p64[2 * e] = h->have_prior ? h->x_mu[e] : 0.0;
-      p64[2 * e + 1] = h->have_prior ? h->y_mu[e] : 0.0;
-    }
-    if (!h->d_prior_xy64) HTM_CK(h, cudaMalloc(&h->d_prior_xy64, p64.size() * sizeof(double)));
-    HTM_CK(h, cudaMemcpyAsync(h->d_prior_xy64, p64.data(), p64.size() * sizeof(double), cudaMemcpyHostToDevice,
-                              h->stream));
-  }
-  HTM_CK(h, cudaStreamSynchronize(h->stream));  // the staging vectors die here
+  HTM_CK(h, cudaMemcpyAsync(h->d_in + off, h->pin_in + off, (o - off) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  HTM_CK(h, cudaEventRecord(h->ev_in, h->stream));
+  h->tables_ok = false;
+  return HTM_OK;
+}
+
+Tables tables_of(htm_handle h);
+
+// sta4 / obs4 / obs4_raw / evc4 / prior_xy (layouts: htm_forward.cuh) are built ON THE DEVICE from the raw
+// float64 arrays (htm_tables.cu: init_forward's rules, src/cls_forward.f90:71-92, in float64): no host pass
+// over the observations, no synchronisation.
+int32_t build_tables(htm_handle h) {
+  const double* gsrc[2] = {h->g_tc.data(), h->g_ac.data()};
+  const size_t glen[2] = {static_cast<size_t>(h->S), static_cast<size_t>(h->S)};
+  const int32_t rc = stage_input(h, h->off_g(), gsrc, glen, 2);
+  if (rc != HTM_OK) return rc;
+  TableBuild b;
+  b.E = h->E;
+  b.S = h->S;
+  b.use_time = h->cfg.use_time != 0;
+  b.use_amp = h->cfg.use_amp != 0;
+  b.obs_in = h->d_in + h->off_obs();
+  b.sta_xyz = h->d_in + h->off_sta();
+  b.xy_mu = h->have_prior ? h->d_in + h->off_xy() : nullptr;
+  b.g_tc_ac = h->d_in + h->off_g();
+  b.sta4 = h->d_sta4;
+  b.obs4 = h->d_obs4;
+  b.obs4_raw = h->d_obs4_raw;
+  b.evc4 = h->d_evc4;
+  b.prior_xy = h->d_prior_xy;
+  b.prior_xy64 = h->d_prior_xy64;
+  HTM_CK(h, launch_build_tables(h->cfg.precision, b, h->stream));
   h->tables_ok = true;
   return HTM_OK;
 }
@@ -198,12 +196,11 @@ int32_t ensure_tables(htm_handle h) {
   if (h->tables_ok) return HTM_OK;
   if (!h->have_sta) return fail(h, HTM_ERR_STATE, "stations not set (htm_set_stations)");
   if (!h->have_obs) return fail(h, HTM_ERR_STATE, "observations not set (htm_set_observations)");
-  const int32_t rc = h->cfg.precision == HTM_PRECISION_F64 ? build_tables_t<double>(h) : build_tables_t<float>(h);
+  const int32_t rc = build_tables(h);
   if (rc != HTM_OK) return rc;
   if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS && h->cfg.precision == HTM_PRECISION_F32) {
     // expanded station-pair rows for the float32 joint-chain sweep (layout: htm_forward.cuh)
     const int xrow = 2 + 4 * (h->S / 2);
-    if (!h->d_obsx) HTM_CK(h, cudaMalloc(&h->d_obsx, static_cast<size_t>(h->E) * xrow * 16));
     HTM_CK(h, launch_expand_obs(tables_of(h), h->E, h->S, h->d_obsx, h->stream));
     h->gl.obsx = h->d_obsx;
     h->gl.xrow = xrow;
@@ -261,6 +258,21 @@ FactLaunch fact_launch_of(htm_handle h) {
 
 int32_t alloc_state(htm_handle h) {
   const size_t nB = static_cast<size_t>(h->E) * h->R * h->K;
+  {  // input staging + device tables (sizes are fixed by the configuration)
+    const size_t ES = static_cast<size_t>(h->E) * h->S, r4 = 4 * h->rs;
+    h->pin_in = static_cast<double*>(host_alloc(h->n_in() * sizeof(double), &h->pin_in_pinned));
+    if (!h->pin_in) return fail(h, HTM_ERR_CUDA, "out of host memory for the input staging buffer");
+    HTM_CK(h, cudaMalloc(&h->d_in, h->n_in() * sizeof(double)));
+    HTM_CK(h, cudaMalloc(&h->d_sta4, h->S * r4));
+    HTM_CK(h, cudaMalloc(&h->d_obs4_raw, ES * r4));
+    // the table with the fixed station terms folded in serves the factorised mode only
+    if (h->cfg.mode == HTM_MODE_FACTORISED) HTM_CK(h, cudaMalloc(&h->d_obs4, ES * r4));
+    HTM_CK(h, cudaMalloc(&h->d_evc4, h->E * r4));
+    HTM_CK(h, cudaMalloc(&h->d_prior_xy, h->E * 2 * h->rs));
+    if (h->cfg.mode == HTM_MODE_REPLAY) HTM_CK(h, cudaMalloc(&h->d_prior_xy64, h->E * 2 * sizeof(double)));
+    if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS && h->cfg.precision == HTM_PRECISION_F32)
+      HTM_CK(h, cudaMalloc(&h->d_obsx, static_cast<size_t>(h->E) * (2 + 4 * (h->S / 2)) * 16));
+  }
   if (h->cfg.mode == HTM_MODE_FACTORISED) {
     for (void** p : {&h->d_x, &h->d_y, &h->d_z, &h->d_L, &h->d_T}) {
       HTM_CK(h, cudaMalloc(p, nB * h->rs));
@@ -275,6 +287,8 @@ int32_t alloc_state(htm_handle h) {
       h->rec_cap = h->cfg.max_samples;
       const size_t ns = static_cast<size_t>(h->rec_cap) * h->R * h->cfg.n_cool * h->E * 4 * h->rs;
       HTM_CK(h, cudaMalloc(&h->d_samples, ns));
+      h->pin_samples = static_cast<char*>(host_alloc(ns, &h->pin_samples_pinned));
+      if (!h->pin_samples) return fail(h, HTM_ERR_CUDA, "out of host memory for the sample ring mirror");
     }
     h->cur_samp.assign(h->R, 0);
     h->cur_lik.assign(h->R, 0);
@@ -340,6 +354,18 @@ int32_t alloc_state(htm_handle h) {
       HTM_CK(h, grab(reinterpret_cast<void**>(&g.rec_L), n * 8));
       HTM_CK(h, grab(reinterpret_cast<void**>(&g.rec_tc), n * S * 8));
       HTM_CK(h, grab(reinterpret_cast<void**>(&g.rec_ac), n * S * 8));
+      // host mirror (pinned): hypo records, then the 8-byte arrays, then the chain ids
+      const size_t b_h = n * E * 4 * h->rs, b_d = n * 8, b_s = n * S * 8;
+      h->pin_samples = static_cast<char*>(host_alloc(b_h + 3 * b_d + 2 * b_s + n * 4, &h->pin_samples_pinned));
+      if (!h->pin_samples) return fail(h, HTM_ERR_CUDA, "out of host memory for the sample ring mirror");
+      char* q = h->pin_samples;
+      h->host_hypo_rec = q; q += b_h;
+      h->host_rec_vs = reinterpret_cast<double*>(q); q += b_d;
+      h->host_rec_qs = reinterpret_cast<double*>(q); q += b_d;
+      h->host_rec_L = reinterpret_cast<double*>(q); q += b_d;
+      h->host_rec_tc = reinterpret_cast<double*>(q); q += b_s;
+      h->host_rec_ac = reinterpret_cast<double*>(q); q += b_s;
+      h->host_rec_chain = reinterpret_cast<int*>(q);
     }
     h->cur_samp.assign(h->R, 0);
     h->cur_lik.assign(h->R, 0);
@@ -396,6 +422,10 @@ void gibbs_launch_of(htm_handle h) {
     g.xch.n = h->cfg.shard_count;
     g.xch.rank = h->cfg.shard_rank;
     g.xch.status = h->d_xch_status;
+    if (const char* ts = std::getenv("HTM_XCH_TIMEOUT_S")) {  // wall-clock budget of one wait (default 120 s)
+      const double sec = std::atof(ts);
+      if (sec > 0.0) g.xch.timeout_ns = static_cast<unsigned long long>(sec * 1e9);
+    }
   }
   g.xch_epoch0 = h->xch_epoch;
 }
@@ -411,46 +441,45 @@ bool record_ids(int first, int last, int n_interval, int* m_lo, int* m_hi) {
   return true;
 }
 
-int32_t pull_samples_gibbs(htm_handle h) {
-  if (h->host_samples_valid) return HTM_OK;
-  const size_t n = static_cast<size_t>(h->rec_pending) * h->n_cold_total, E = h->E, S = h->S;
-  h->host_hypo_rec.resize(n * E * 4 * h->rs);
-  h->host_rec_chain.resize(n);
-  h->host_rec_vs.resize(n);
-  h->host_rec_qs.resize(n);
-  h->host_rec_L.resize(n);
-  h->host_rec_tc.resize(n * S);
-  h->host_rec_ac.resize(n * S);
-  if (n > 0) {
-    HTM_CK(h, cudaStreamSynchronize(h->stream));
-    HTM_CK(h, cudaMemcpy(h->host_hypo_rec.data(), h->gl.hypo_rec, h->host_hypo_rec.size(), cudaMemcpyDeviceToHost));
-    HTM_CK(h, cudaMemcpy(h->host_rec_chain.data(), h->gl.rec_chain, n * 4, cudaMemcpyDeviceToHost));
-    HTM_CK(h, cudaMemcpy(h->host_rec_vs.data(), h->gl.rec_vs, n * 8, cudaMemcpyDeviceToHost));
-    HTM_CK(h, cudaMemcpy(h->host_rec_qs.data(), h->gl.rec_qs, n * 8, cudaMemcpyDeviceToHost));
-    HTM_CK(h, cudaMemcpy(h->host_rec_L.data(), h->gl.rec_L, n * 8, cudaMemcpyDeviceToHost));
-    HTM_CK(h, cudaMemcpy(h->host_rec_tc.data(), h->gl.rec_tc, n * S * 8, cudaMemcpyDeviceToHost));
-    HTM_CK(h, cudaMemcpy(h->host_rec_ac.data(), h->gl.rec_ac, n * S * 8, cudaMemcpyDeviceToHost));
+// Queue, behind the kernel(s) just launched on h->stream, the device-to-host copy of ring slots [first, end)
+// into the pinned mirror, on the copy stream: it overlaps whatever htm_run queues next.
+int32_t queue_sample_copy(htm_handle h, int first, int end) {
+  if (end <= first) return HTM_OK;
+  HTM_CK(h, cudaEventRecord(h->ev_run, h->stream));
+  HTM_CK(h, cudaStreamWaitEvent(h->cstream, h->ev_run, 0));
+  auto cp = [&](void* dst, const void* src, size_t per_slot) -> cudaError_t {
+    return cudaMemcpyAsync(static_cast<char*>(dst) + first * per_slot, static_cast<const char*>(src) + first * per_slot,
+                           (end - first) * per_slot, cudaMemcpyDeviceToHost, h->cstream);
+  };
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
+    const size_t nc = h->n_cold_total, E = h->E, S = h->S;
+    HTM_CK(h, cp(h->host_hypo_rec, h->gl.hypo_rec, nc * E * 4 * h->rs));
+    HTM_CK(h, cp(h->host_rec_chain, h->gl.rec_chain, nc * 4));
+    HTM_CK(h, cp(h->host_rec_vs, h->gl.rec_vs, nc * 8));
+    HTM_CK(h, cp(h->host_rec_qs, h->gl.rec_qs, nc * 8));
+    HTM_CK(h, cp(h->host_rec_L, h->gl.rec_L, nc * 8));
+    HTM_CK(h, cp(h->host_rec_tc, h->gl.rec_tc, nc * S * 8));
+    HTM_CK(h, cp(h->host_rec_ac, h->gl.rec_ac, nc * S * 8));
+  } else {
+    HTM_CK(h, cp(h->pin_samples, h->d_samples, static_cast<size_t>(h->R) * h->cfg.n_cool * h->E * 4 * h->rs));
   }
-  h->host_samples_valid = true;
+  HTM_CK(h, cudaEventRecord(h->ev_copy, h->cstream));
   return HTM_OK;
 }
 
+// the pending records are in the pinned mirror once the last queued copy has completed
 int32_t pull_samples(htm_handle h) {
   if (h->host_samples_valid) return HTM_OK;
-  const size_t per_rec = static_cast<size_t>(h->R) * h->cfg.n_cool * h->E * 4 * h->rs;
-  h->host_samples.resize(per_rec * h->rec_pending);
-  if (h->rec_pending > 0) {
-    HTM_CK(h, cudaMemcpyAsync(h->host_samples.data(), h->d_samples, h->host_samples.size(), cudaMemcpyDeviceToHost,
-                              h->stream));
-    HTM_CK(h, cudaStreamSynchronize(h->stream));
-  }
+  HTM_CK(h, cudaEventSynchronize(h->ev_copy));
+  if (const int32_t rcx = check_exchange(h)) return rcx;
   h->host_samples_valid = true;
   return HTM_OK;
 }
+int32_t pull_samples_gibbs(htm_handle h) { return pull_samples(h); }
 inline double sample_at(htm_handle h, int rec, int rank, int m, int e, int comp) {
   const size_t i = (((static_cast<size_t>(rec) * h->R + rank) * h->cfg.n_cool + m) * h->E + e) * 4 + comp;
-  return h->rs == 8 ? reinterpret_cast<const double*>(h->host_samples.data())[i]
-                    : static_cast<double>(reinterpret_cast<const float*>(h->host_samples.data())[i]);
+  return h->rs == 8 ? reinterpret_cast<const double*>(h->pin_samples)[i]
+                    : static_cast<double>(reinterpret_cast<const float*>(h->pin_samples)[i]);
 }
 
 }  // namespace
@@ -571,8 +600,12 @@ int32_t htm_create(htm_handle* out, const htm_config* cfg) {
     return fail(nullptr, HTM_ERR_ARG, "this shard holds no events / no virtual ranks");
   }
   ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&h->ev1);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_run, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming);
   if (ce != cudaSuccess) {
     g_create_error = cudaGetErrorString(ce);
     delete h;
@@ -592,6 +625,13 @@ int32_t htm_destroy(htm_handle h) {
   if (!h) return HTM_OK;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->cstream) cudaStreamSynchronize(h->cstream);
+  free_dev(h->d_in);
+  host_free(h->pin_in, h->pin_in_pinned);
+  host_free(h->pin_samples, h->pin_samples_pinned);
+  for (cudaEvent_t ev : {h->ev_in, h->ev_run, h->ev_copy})
+    if (ev) cudaEventDestroy(ev);
+  if (h->cstream) cudaStreamDestroy(h->cstream);
   for (void* p : {h->d_sta4, h->d_obs4, h->d_obs4_raw, h->d_evc4, h->d_prior_xy, static_cast<void*>(h->d_prior_xy64),
                   h->d_x, h->d_y, h->d_z, h->d_L, h->d_T, static_cast<void*>(h->d_counts),
                   static_cast<void*>(h->d_hist), h->d_samples, static_cast<void*>(h->d_hypo),
@@ -623,34 +663,31 @@ int32_t htm_last_error(htm_handle h, char* buf, int32_t len) {
 
 int32_t htm_set_stations(htm_handle h, const double* sx, const double* sy, const double* sz) {
   if (!h || !sx || !sy || !sz) return fail(h, HTM_ERR_ARG, "null argument");
-  h->sta_x.assign(sx, sx + h->S);
-  h->sta_y.assign(sy, sy + h->S);
-  h->sta_z.assign(sz, sz + h->S);
-  h->have_sta = true;
-  h->tables_ok = false;
-  return HTM_OK;
+  const double* src[3] = {sx, sy, sz};
+  const size_t len[3] = {static_cast<size_t>(h->S), static_cast<size_t>(h->S), static_cast<size_t>(h->S)};
+  const int32_t rc = stage_input(h, h->off_sta(), src, len, 3);
+  if (rc == HTM_OK) h->have_sta = true;
+  return rc;
 }
 
 int32_t htm_set_observations(htm_handle h, const double* t_obs, const double* t_stdv, const double* a_obs,
                              const double* a_stdv) {
   if (!h || !t_obs || !t_stdv || !a_obs || !a_stdv) return fail(h, HTM_ERR_ARG, "null argument");
   const size_t n = static_cast<size_t>(h->E) * h->S;
-  h->t_obs.assign(t_obs, t_obs + n);
-  h->t_stdv.assign(t_stdv, t_stdv + n);
-  h->a_obs.assign(a_obs, a_obs + n);
-  h->a_stdv.assign(a_stdv, a_stdv + n);
-  h->have_obs = true;
-  h->tables_ok = false;
-  return HTM_OK;
+  const double* src[4] = {t_obs, t_stdv, a_obs, a_stdv};
+  const size_t len[4] = {n, n, n, n};
+  const int32_t rc = stage_input(h, h->off_obs(), src, len, 4);
+  if (rc == HTM_OK) h->have_obs = true;
+  return rc;
 }
 
 int32_t htm_set_xy_prior(htm_handle h, const double* x_mu, const double* y_mu) {
   if (!h || !x_mu || !y_mu) return fail(h, HTM_ERR_ARG, "null argument");
-  h->x_mu.assign(x_mu, x_mu + h->E);
-  h->y_mu.assign(y_mu, y_mu + h->E);
-  h->have_prior = true;
-  h->tables_ok = false;
-  return HTM_OK;
+  const double* src[2] = {x_mu, y_mu};
+  const size_t len[2] = {static_cast<size_t>(h->E), static_cast<size_t>(h->E)};
+  const int32_t rc = stage_input(h, h->off_xy(), src, len, 2);
+  if (rc == HTM_OK) h->have_prior = true;
+  return rc;
 }
 
 int32_t htm_set_globals(htm_handle h, double vs, double qs, const double* t_corr, const double* a_corr) {
@@ -729,6 +766,7 @@ int32_t htm_get_chain_state(htm_handle h, int32_t rank, int32_t chain, double* h
   if (!h->chains_ready) return fail(h, HTM_ERR_STATE, "chains not initialised");
   HTM_CK(h, cudaSetDevice(h->cfg.device));
   HTM_CK(h, cudaStreamSynchronize(h->stream));
+  if (const int32_t rcx = check_exchange(h)) return rcx;
   if (h->cfg.mode == HTM_MODE_REPLAY) {
     const size_t c = static_cast<size_t>(rank) * h->K + chain;
     if (hypo) HTM_CK(h, cudaMemcpy(hypo, h->d_hypo + c * 3 * h->E, 3 * h->E * sizeof(double), cudaMemcpyDeviceToHost));
@@ -845,36 +883,53 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
   HTM_CK(h, cudaSetDevice(h->cfg.device));
   int32_t rc = ensure_tables(h);
   if (rc != HTM_OK) return rc;
-  // sample ring bookkeeping
+  // sample ring bookkeeping: computed here, COMMITTED only after the launch went through (a failed launch must
+  // not leave pending records that were never written, nor -- on event shards -- an exchange number that no
+  // longer matches the peers')
   int m_lo = 0, m_hi = -1;
   const bool recs = record_ids(iter_first, iter_last, h->cfg.n_interval, &m_lo, &m_hi);
   const bool have_ring = h->cfg.mode == HTM_MODE_BLOCKED_GIBBS ? h->gl.hypo_rec != nullptr : h->d_samples != nullptr;
+  int new_origin = h->rec_origin, new_pending = h->rec_pending;
+  bool reset_cursors = false;
   if (have_ring && recs) {
     bool all_consumed = true;
     for (int r = 0; r < h->R; ++r)
       if (h->cur_samp[r] < h->rec_pending || h->cur_lik[r] < h->rec_pending) all_consumed = false;
     if (h->rec_pending == 0 || all_consumed) {
-      h->rec_origin = m_lo;
-      h->rec_pending = 0;
-      h->cur_samp.assign(h->R, 0);
-      h->cur_lik.assign(h->R, 0);
+      new_origin = m_lo;
+      new_pending = 0;
+      reset_cursors = true;
     }
-    if (m_lo != h->rec_origin + h->rec_pending)
+    if (m_lo != new_origin + new_pending)
       return fail(h, HTM_ERR_STATE, "iterations must continue where the previous htm_run stopped while samples are pending");
-    if (m_hi - h->rec_origin + 1 > h->rec_cap)
+    if (m_hi - new_origin + 1 > h->rec_cap)
       return fail(h, HTM_ERR_STATE,
                   "sample ring full: fetch samples and likelihood of every rank (or htm_discard_samples) "
                   "before running further, or raise max_samples");
-    h->rec_pending = m_hi - h->rec_origin + 1;
-    h->host_samples_valid = false;
+    new_pending = m_hi - new_origin + 1;
   }
+  // the ring restarts at slot 0: copies of the previous contents must have left the device first
+  if (have_ring && recs && reset_cursors) HTM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+  const int copy_first = (have_ring && recs) ? new_pending - (m_hi - m_lo + 1) : 0;
+  auto commit = [&]() {
+    if (!(have_ring && recs)) return;
+    if (reset_cursors) {
+      h->cur_samp.assign(h->R, 0);
+      h->cur_lik.assign(h->R, 0);
+    }
+    h->rec_origin = new_origin;
+    h->rec_pending = new_pending;
+    h->host_samples_valid = false;
+  };
   if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
     if (h->cfg.gibbs_shard_events && h->cfg.shard_count > 1 && !h->comm && !h->xch_on)
       return fail(h, HTM_ERR_STATE,
                   "event-sharded blocked-Gibbs run needs htm_comm_p2p_export/_import or htm_comm_init first "
                   "(one exchange of the per-chain sums per iteration)");
+    const int keep_origin = h->rec_origin;
+    h->rec_origin = new_origin;  // the launch description reads the ring origin
     gibbs_launch_of(h);
-    if (h->gl.xch.n > 1) h->xch_epoch += static_cast<uint32_t>(iter_last - iter_first + 1);
+    h->rec_origin = keep_origin;
     h->gl.iter_first = iter_first;
     h->gl.iter_last = iter_last;
     h->gl.trace = d_trace;
@@ -892,12 +947,19 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
       HTM_CK(h, eg);
     }
     HTM_CK(h, cudaEventRecord(h->ev1, h->stream));
+    commit();
+    if (have_ring && recs) {
+      const int32_t rcq = queue_sample_copy(h, copy_first, new_pending);
+      if (rcq != HTM_OK) return rcq;
+    }
+    if (h->gl.xch.n > 1) h->xch_epoch += static_cast<uint32_t>(iter_last - iter_first + 1);
     h->timed = true;
     h->last_launches = nlg;
     h->last_proposals = static_cast<int64_t>(iter_last - iter_first + 1) * (static_cast<int64_t>(h->E) + 1) * h->C;
     return HTM_OK;
   }
   FactLaunch a = fact_launch_of(h);
+  a.rec_origin = new_origin;
   a.iter_first = iter_first;
   a.iter_last = iter_last;
   a.trace = d_trace;
@@ -910,6 +972,11 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
     return fail(h, e == cudaErrorInvalidValue && why[0] ? HTM_ERR_UNSUPPORTED : HTM_ERR_CUDA,
                 why[0] ? std::string(why) : std::string("launch_factorised: ") + cudaGetErrorString(e));
   HTM_CK(h, cudaEventRecord(h->ev1, h->stream));
+  commit();
+  if (have_ring && recs) {
+    const int32_t rcq = queue_sample_copy(h, copy_first, new_pending);
+    if (rcq != HTM_OK) return rcq;
+  }
   h->timed = true;
   h->last_launches = nl;
   h->last_proposals = static_cast<int64_t>(iter_last - iter_first + 1) * h->E * h->R * h->K;
@@ -935,13 +1002,19 @@ int32_t htm_run_traced(htm_handle h, int32_t iter_first, int32_t iter_last, htm_
   const size_t ns = gibbs ? n_it : n_it * h->E * h->R;
   htm_step_trace* d_t = nullptr;
   htm_swap_trace* d_s = nullptr;
+  cudaError_t ea = cudaSuccess;
   if (trace) {
-    HTM_CK(h, cudaMalloc(&d_t, nt * sizeof(htm_step_trace)));
-    HTM_CK(h, cudaMemset(d_t, 0, nt * sizeof(htm_step_trace)));
+    ea = cudaMalloc(&d_t, nt * sizeof(htm_step_trace));
+    if (ea == cudaSuccess) ea = cudaMemset(d_t, 0, nt * sizeof(htm_step_trace));
   }
-  if (swaps) {
-    HTM_CK(h, cudaMalloc(&d_s, ns * sizeof(htm_swap_trace)));
-    HTM_CK(h, cudaMemset(d_s, 0, ns * sizeof(htm_swap_trace)));
+  if (ea == cudaSuccess && swaps) {
+    ea = cudaMalloc(&d_s, ns * sizeof(htm_swap_trace));
+    if (ea == cudaSuccess) ea = cudaMemset(d_s, 0, ns * sizeof(htm_swap_trace));
+  }
+  if (ea != cudaSuccess) {
+    free_dev(d_t);
+    free_dev(d_s);
+    return fail(h, HTM_ERR_CUDA, std::string("htm_run_traced: ") + cudaGetErrorString(ea));
   }
   int32_t rc = run_impl(h, iter_first, iter_last, d_t, d_s);
   cudaError_t e = cudaSuccess;
@@ -954,19 +1027,14 @@ int32_t htm_run_traced(htm_handle h, int32_t iter_first, int32_t iter_last, htm_
   free_dev(d_s);
   if (rc != HTM_OK) return rc;
   if (e != cudaSuccess) return fail(h, HTM_ERR_CUDA, std::string("htm_run_traced: ") + cudaGetErrorString(e));
-  return HTM_OK;
+  return check_exchange(h);
 }
 
 int32_t htm_synchronize(htm_handle h) {
   if (!h) return HTM_ERR_ARG;
   HTM_CK(h, cudaSetDevice(h->cfg.device));
   HTM_CK(h, cudaStreamSynchronize(h->stream));
-  if (h->d_xch_status) {
-    int st = 0;
-    HTM_CK(h, cudaMemcpy(&st, h->d_xch_status, sizeof(int), cudaMemcpyDeviceToHost));
-    if (st != 0) return fail(h, HTM_ERR_CUDA, "peer-memory exchange timed out: a shard did not reach the same iteration");
-  }
-  return HTM_OK;
+  return check_exchange(h);
 }
 
 int32_t htm_replay(htm_handle h, int32_t iter_first, int32_t iter_last, const int32_t* const* draws,
@@ -1107,11 +1175,11 @@ int32_t htm_fetch_samples(htm_handle h, int32_t rank, int32_t max_records, int32
             for (int cc = 0; cc < 3; ++cc) {
               const size_t i = (o * E + e) * 4 + cc;
               hypo[static_cast<size_t>(n) * 3 * E + 3 * e + cc] =
-                  h->rs == 8 ? reinterpret_cast<const double*>(h->host_hypo_rec.data())[i]
-                             : static_cast<double>(reinterpret_cast<const float*>(h->host_hypo_rec.data())[i]);
+                  h->rs == 8 ? reinterpret_cast<const double*>(h->host_hypo_rec)[i]
+                             : static_cast<double>(reinterpret_cast<const float*>(h->host_hypo_rec)[i]);
             }
-        if (t_corr) std::memcpy(t_corr + static_cast<size_t>(n) * S, h->host_rec_tc.data() + o * S, S * sizeof(double));
-        if (a_corr) std::memcpy(a_corr + static_cast<size_t>(n) * S, h->host_rec_ac.data() + o * S, S * sizeof(double));
+        if (t_corr) std::memcpy(t_corr + static_cast<size_t>(n) * S, h->host_rec_tc + o * S, S * sizeof(double));
+        if (a_corr) std::memcpy(a_corr + static_cast<size_t>(n) * S, h->host_rec_ac + o * S, S * sizeof(double));
         ++n;
       }
     }
@@ -1211,6 +1279,7 @@ int32_t htm_get_counts(htm_handle h, int64_t n_propose[7], int64_t n_accept[7]) 
   if (!h || !n_propose || !n_accept) return fail(h, HTM_ERR_ARG, "null argument");
   HTM_CK(h, cudaSetDevice(h->cfg.device));
   HTM_CK(h, cudaStreamSynchronize(h->stream));
+  if (const int32_t rcx = check_exchange(h)) return rcx;
   for (int k = 0; k < 7; ++k) n_propose[k] = n_accept[k] = 0;
   if (h->cfg.mode == HTM_MODE_REPLAY) {
     std::vector<unsigned long long> c(static_cast<size_t>(h->C) * 14);
@@ -1349,7 +1418,7 @@ int32_t htm_gather(htm_handle h, uint32_t* hist_all, int64_t n_propose[7], int64
     if (!ok && !why.empty()) return fail(h, HTM_ERR_CUDA, why);
     HTM_CK(h, e);
   }
-  return HTM_OK;
+  return check_exchange(h);  // after the collectives, so that no shard is left waiting in them
 }
 
 int32_t htm_gather_samples(htm_handle h, int32_t rank, int32_t max_records, int32_t* n_records, int32_t* iter,
@@ -1358,51 +1427,78 @@ int32_t htm_gather_samples(htm_handle h, int32_t rank, int32_t max_records, int3
   if (!h->comm) return fail(h, HTM_ERR_STATE, "htm_comm_init was not called");
   if (h->cfg.mode != HTM_MODE_FACTORISED)
     return fail(h, HTM_ERR_UNSUPPORTED, "sample gather serves the event-sharded factorised mode (the other modes hold every event on every shard)");
-  const int W = h->cfg.shard_count, E = h->E;
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  const int W = h->cfg.shard_count, E = h->E, nc = h->cfg.n_cool;
   int biggest = 0;
   for (int r = 0; r < W; ++r) {
     int lo, hi;
     shard_bounds(h->E_total, r, W, &lo, &hi);
     if (hi - lo > biggest) biggest = hi - lo;
   }
-  // this shard's block, exactly as htm_fetch_samples delivers it (the cursors advance identically on every
-  // shard because the recorded iterations are the same everywhere)
-  std::vector<double> mine(hypo_all ? static_cast<size_t>(max_records > 0 ? max_records : 0) * 3 * E : 0);
-  const int32_t rc = htm_fetch_samples(h, rank, max_records, n_records, iter, vs, qs, hypo_all ? mine.data() : nullptr,
-                                       t_corr, a_corr);
-  if (rc != HTM_OK || !hypo_all) return rc;
-  const int n = *n_records;
-  if (n == 0) return HTM_OK;
-  // all-gather of the [n][3*E_shard] blocks, padded to the largest shard, over NVLink
-  const size_t blk = static_cast<size_t>(n) * 3 * biggest;  // doubles per shard
-  double *d_send = nullptr, *d_recv = nullptr;
-  std::vector<double> send(blk, 0.0), recv(blk * W);
-  for (int k = 0; k < n; ++k)
-    std::memcpy(send.data() + static_cast<size_t>(k) * 3 * biggest, mine.data() + static_cast<size_t>(k) * 3 * E, sizeof(double) * 3 * E);
-  HTM_CK(h, cudaSetDevice(h->cfg.device));
-  HTM_CK(h, cudaMalloc(&d_send, blk * sizeof(double)));
-  cudaError_t e = cudaMalloc(&d_recv, blk * W * sizeof(double));
-  if (e != cudaSuccess) {
-    free_dev(d_send);
-    HTM_CK(h, e);
-  }
+  // Which ring records go out is decided exactly as htm_fetch_samples does (the cursors advance identically on
+  // every shard because the recorded iterations are the same everywhere); the scalars come from that call, the
+  // hypocentres do NOT pass through the host: ring -> packed [n][3*biggest] doubles (pack_hypo_kernel) ->
+  // ncclAllGather over NVLink -> one strided device-to-host copy per shard block into hypo_all.
+  const int rec0 = (rank >= 0 && rank < h->R) ? h->cur_samp[rank] : 0;
+  int32_t rc = htm_fetch_samples(h, rank, max_records, n_records, iter, vs, qs, nullptr, t_corr, a_corr);
+  const int n = rc == HTM_OK ? *n_records : 0;
+  // every shard enters the collectives, whatever happened locally: first agree on (failure, record count)
+  unsigned long long st_host[2] = {rc == HTM_OK ? 0ull : 1ull, static_cast<unsigned long long>(n)};
+  unsigned long long* d_st = nullptr;
   std::string why;
-  e = cudaMemcpyAsync(d_send, send.data(), blk * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-  const bool ok = e == cudaSuccess && nccl_allgather_u32(h->comm, d_send, d_recv, blk * 2, h->stream, &why);
-  if (ok) e = cudaMemcpyAsync(recv.data(), d_recv, blk * W * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaMalloc(&d_st, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_st, st_host, sizeof(st_host), cudaMemcpyHostToDevice, h->stream);
+  bool ok = e == cudaSuccess && nccl_allreduce_u64(h->comm, d_st, d_st, 2, h->stream, &why);
+  if (ok) e = cudaMemcpyAsync(st_host, d_st, sizeof(st_host), cudaMemcpyDeviceToHost, h->stream);
   if (ok && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  free_dev(d_send);
-  free_dev(d_recv);
+  free_dev(d_st);
   if (!ok && !why.empty()) return fail(h, HTM_ERR_CUDA, why);
   HTM_CK(h, e);
-  for (int r = 0; r < W; ++r) {
+  if (rc != HTM_OK) return rc;
+  if (st_host[0] != 0) return fail(h, HTM_ERR_STATE, "htm_gather_samples: another shard failed to fetch its records");
+  if (st_host[1] != static_cast<unsigned long long>(n) * W)
+    return fail(h, HTM_ERR_STATE, "htm_gather_samples: the shards hold different numbers of records (call with the same arguments everywhere)");
+  if (!hypo_all || n == 0) return HTM_OK;
+  // ring slots of the n records just consumed: recorded iterations after burn-in, n_cool records each
+  std::vector<int> slots;
+  for (int rec = rec0; rec < h->cur_samp[rank]; ++rec) {
+    const int it = (h->rec_origin + rec) * h->cfg.n_interval + 1;
+    if (it <= h->cfg.n_burn) continue;
+    for (int m = 0; m < nc; ++m) slots.push_back(rec * nc + m);  // (ring record, cold slot) flattened
+  }
+  if (static_cast<int>(slots.size()) != n) return fail(h, HTM_ERR_STATE, "htm_gather_samples: record bookkeeping mismatch");
+  const size_t blk = static_cast<size_t>(n) * 3 * biggest;  // doubles per shard
+  double *d_send = nullptr, *d_recv = nullptr;
+  int* d_slots = nullptr;
+  auto cleanup = [&]() {
+    free_dev(d_send);
+    free_dev(d_recv);
+    free_dev(d_slots);
+  };
+  e = cudaMalloc(&d_send, blk * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_recv, blk * W * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_slots, n * sizeof(int));
+  // the flattened (record, cold slot) index addresses rows of E entries when the rank dimension is fixed:
+  // ring layout [slot][R][n_cool][E]  ->  row = (slot * R + rank) * n_cool + m
+  std::vector<int> rows(n);
+  for (int k = 0; k < n; ++k) rows[k] = (slots[k] / nc * h->R + rank) * nc + slots[k] % nc;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_slots, rows.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess && biggest != E) e = cudaMemsetAsync(d_send, 0, blk * sizeof(double), h->stream);
+  if (e == cudaSuccess)
+    e = launch_pack_hypo(h->cfg.precision, h->d_samples, d_slots, n, E, static_cast<size_t>(E), 0, d_send,
+                         static_cast<size_t>(3) * biggest, h->stream);
+  ok = e == cudaSuccess && nccl_allgather_u32(h->comm, d_send, d_recv, blk * 2, h->stream, &why);
+  for (int r = 0; r < W && ok && e == cudaSuccess; ++r) {
     int lo, hi;
     shard_bounds(h->E_total, r, W, &lo, &hi);
-    for (int k = 0; k < n; ++k)
-      std::memcpy(hypo_all + static_cast<size_t>(k) * 3 * h->E_total + static_cast<size_t>(3) * lo,
-                  recv.data() + static_cast<size_t>(r) * blk + static_cast<size_t>(k) * 3 * biggest,
-                  sizeof(double) * 3 * (hi - lo));
+    e = cudaMemcpy2DAsync(hypo_all + static_cast<size_t>(3) * lo, static_cast<size_t>(3) * h->E_total * sizeof(double),
+                          d_recv + static_cast<size_t>(r) * blk, static_cast<size_t>(3) * biggest * sizeof(double),
+                          static_cast<size_t>(3) * (hi - lo) * sizeof(double), n, cudaMemcpyDeviceToHost, h->stream);
   }
+  if (ok && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (!ok && !why.empty()) return fail(h, HTM_ERR_CUDA, why);
+  HTM_CK(h, e);
   return HTM_OK;
 }
 

@@ -861,11 +861,14 @@ __global__ void __launch_bounds__(kCW * 32, 2) gibbs_persist_oq_kernel(const Gib
       if (writer) {
         sum_partials(d.n_tiles, part_cur, part_prop, J, cs.tot);
         __syncthreads();
-        peer_allreduce(d.xch, d.xch.epoch + static_cast<uint32_t>(it - iter_first), cs.tot, 2 * J);
-        for (int t = threadIdx.x; t < 2 * J; t += blockDim.x) totals[t] = cs.tot[t];
+        if (peer_allreduce(d.xch, d.xch.epoch + static_cast<uint32_t>(it - iter_first), cs.tot, 2 * J))
+          for (int t = threadIdx.x; t < 2 * J; t += blockDim.x) totals[t] = cs.tot[t];
         __threadfence();
       }
       grid.sync();
+      // a peer that never answered ends the run here, on every CTA alike (only this shard's writer sets the
+      // flag, before the barrier): no decision is taken from partial sums; the host reports HTM_ERR_CUDA
+      if (*reinterpret_cast<volatile int*>(d.xch.status) != 0) break;
       decide_core(d, cs, it, it + 1, totals, totals + J, rec_slot, trace_g, swap_it, writer, true);
     } else {
       decide_core(d, cs, it, it + 1, part_cur, part_prop, rec_slot, trace_g, swap_it, writer);

@@ -149,13 +149,27 @@ __device__ void chain_store(const GibbsDecide& d, const ChainSm& cs) {
 // for the numbers of all shards, and adds the n slots of its own buffer in shard order -- the same operands in
 // the same order everywhere, so every shard takes bit-identical decisions.  Two parities: a shard can be at most
 // one exchange ahead of the slowest one (it cannot pass exchange e+1 before everyone has published e+1, i.e.
-// has finished reading e).  The wait is bounded: a missing peer raises *status instead of hanging the GPU.
+// has finished reading e).
+// The wait is bounded by WALL CLOCK (globaltimer; shards are separate host processes that may drain gigabytes
+// of samples between chunks, so a poll count would be a guess): x.timeout_ns per wait, minutes by default.
+// Returns false -- uniformly for the CTA -- when a peer did not answer now or in an earlier exchange; *status
+// is then set, the caller must take NO decision from `tot`, and every result-returning entry point of the C
+// ABI reports the failure (htm_capi.cu: check_exchange).
 __device__ __forceinline__ uint32_t* peer_flags(double* base, int n, int W) {
   return reinterpret_cast<uint32_t*>(base + static_cast<size_t>(2) * n * W);
 }
-__device__ void peer_allreduce(const PeerExchange& x, const uint32_t epoch, double* tot /* shared memory, W values, in/out */,
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ bool peer_allreduce(const PeerExchange& x, const uint32_t epoch, double* tot /* shared memory, W values, in/out */,
                                const int W) {
+  __shared__ int s_xch_fail;
   const int n = x.n, me = x.rank, par = static_cast<int>(epoch & 1u);
+  if (threadIdx.x == 0) s_xch_fail = (x.status && *reinterpret_cast<volatile int*>(x.status) != 0) ? 1 : 0;
+  __syncthreads();
+  if (s_xch_fail) return false;  // the run is lost already: neither publish nor wait
   for (int i = threadIdx.x; i < n * W; i += blockDim.x) {
     const int r = i / W, t = i - r * W;
     x.peer[r][(static_cast<size_t>(par) * n + me) * W + t] = tot[t];
@@ -167,25 +181,30 @@ __device__ void peer_allreduce(const PeerExchange& x, const uint32_t epoch, doub
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
     const uint32_t* mine = peer_flags(x.peer[me], n, W) + par * n + threadIdx.x;
     uint32_t seen = 0;
-    long spins = 0;
-    // once a peer has failed to answer the run is lost (htm_synchronize reports it): do not wait again
-    const bool dead = x.status && *reinterpret_cast<volatile int*>(x.status) != 0;
-    while (!dead) {
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int polls = 0;
+    for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
       if (seen == epoch) break;
-      if (++spins > (1L << 24)) {
+      if ((++polls & 1023u) == 0u && global_timer_ns() - t0 > x.timeout_ns) {
         if (x.status) *reinterpret_cast<volatile int*>(x.status) = 1;
+        s_xch_fail = 1;
         break;
       }
     }
   }
   __syncthreads();
+  if (s_xch_fail) {
+    __threadfence();  // the flag is visible to the rest of the grid before anyone acts on it
+    return false;
+  }
   for (int t = threadIdx.x; t < W; t += blockDim.x) {
     double s = 0.0;
     for (int r = 0; r < n; ++r) s += __ldcg(x.peer[me] + (static_cast<size_t>(par) * n + r) * W + t);
     tot[t] = s;
   }
   __syncthreads();
+  return true;
 }
 
 // Per-chain sums of the per-tile (or per-CTA) partial sums, in a fixed order; every thread of the CTA calls it
@@ -256,7 +275,8 @@ __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int i
   if (it > 0) {
     sum_partials(summed ? 1 : d.n_tiles, part_cur, part_prop, J, cs.tot);
     __syncthreads();
-    if (!summed && d.xch.n > 1) peer_allreduce(d.xch, d.xch.epoch, cs.tot, 2 * J);
+    // a failed exchange ends the run: no decision is taken from partial sums (uniform for the CTA)
+    if (!summed && d.xch.n > 1 && !peer_allreduce(d.xch, d.xch.epoch, cs.tot, 2 * J)) return;
     // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----
     for (int c = threadIdx.x; c < J; c += blockDim.x) {
       const int which = cs.which[c];

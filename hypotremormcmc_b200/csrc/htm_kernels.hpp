@@ -19,6 +19,21 @@ struct Tables {
   const void* prior_xy = nullptr;  // [E] real2 {x_mu, y_mu}
 };
 
+// device-side table build (htm_tables.cu): raw float64 inputs as the driver hands them over -> the tables above
+struct TableBuild {
+  int E = 0, S = 0, use_time = 1, use_amp = 1;
+  const double* obs_in = nullptr;    // [4][E][S]: t_obs, t_stdv, a_obs, a_stdv (station index fastest)
+  const double* sta_xyz = nullptr;   // [3][S]
+  const double* xy_mu = nullptr;     // [2][E] or null (no prior centre set: zeros)
+  const double* g_tc_ac = nullptr;   // [2][S] fixed station terms folded into obs4 (mode B)
+  void *sta4 = nullptr, *obs4 = nullptr, *obs4_raw = nullptr, *evc4 = nullptr, *prior_xy = nullptr;
+  double* prior_xy64 = nullptr;      // replay mode only
+};
+cudaError_t launch_build_tables(int precision, const TableBuild& b, cudaStream_t stream);
+// ring records {x, y, z, L_e} -> hypo[record][3E] doubles, device to device (sample gathers)
+cudaError_t launch_pack_hypo(int precision, const void* ring, const int* slot_of_rec, int n_rec, int E, size_t ring_stride,
+                             size_t row_offset, double* out, size_t out_stride, cudaStream_t stream);
+
 // everything a factorised-mode launch needs
 struct FactLaunch {
   int precision = 32;
@@ -90,6 +105,8 @@ struct PeerExchange {
   int n = 0, rank = 0;    // n <= 1: no exchange
   uint32_t epoch = 0;     // exchange number of this launch, the same on every shard, never reused
   int* status = nullptr;  // device flag: 1 = a peer never answered
+  unsigned long long timeout_ns = 120ull * 1000000000ull;  // wall-clock budget of ONE wait (globaltimer); the host
+                                                           // sets it from HTM_XCH_TIMEOUT_S
 };
 inline size_t peer_exchange_bytes(int n, int J) {
   return static_cast<size_t>(2) * n * 2 * J * sizeof(double) + static_cast<size_t>(2) * n * sizeof(uint32_t);

@@ -135,7 +135,7 @@ program hypo_tremor_mcmc_b200
   call htm_check(h, htm_get_counts(h, n_prop, n_acc), "htm_get_counts")
   open(newunit=io, file="proposal_count.txt", status="unknown")
   do k = 1, 7
-     write(io, '(A,2I10)') '"' // label(k) // '"', n_prop(k), n_acc(k)
+     write(io, '(A,2I20)') '"' // label(k) // '"', n_prop(k), n_acc(k)
   end do
   close(io)
   do r = 0, n_ranks - 1
