@@ -23,7 +23,7 @@ EXPORTS = [
     "htm_synchronize", "htm_replay", "htm_fetch_samples", "htm_fetch_likelihood",
     "htm_discard_samples", "htm_get_counts", "htm_get_histograms", "htm_device_ptr",
     "htm_last_run_stats", "htm_measure_fp32_peak", "htm_comm_unique_id", "htm_comm_init", "htm_gather",
-    "htm_comm_p2p_export", "htm_comm_p2p_import", "htm_gather_samples",
+    "htm_comm_p2p_export", "htm_comm_p2p_import", "htm_gather_samples", "htm_gibbs_pending", "htm_gibbs_last_sums",
 ]
 
 
@@ -85,6 +85,8 @@ def load_library():
         "htm_comm_init": [vp, ctypes.c_char_p],
         "htm_gather": [vp, ctypes.POINTER(ctypes.c_uint32), lp, lp],
         "htm_gather_samples": [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), dp, dp, dp, dp, dp],
+        "htm_gibbs_pending": [vp, ip, ip, dp],
+        "htm_gibbs_last_sums": [vp, dp, dp],
         "htm_comm_p2p_export": [vp, ctypes.c_char_p],
         "htm_comm_p2p_import": [vp, ctypes.c_char_p],
     }
@@ -240,6 +242,21 @@ class HypoTremorB200:
 
     def synchronize(self):
         self._ck(self.lib.htm_synchronize(self._h))
+
+    def gibbs_pending(self):
+        """(which, idx, x_new) per joint chain: the shared-parameter proposal the next iteration will judge."""
+        J = self.n_procs * self.n_chains
+        which, idx, xn = np.zeros(J, dtype=np.int32), np.zeros(J, dtype=np.int32), np.zeros(J)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        self._ck(self.lib.htm_gibbs_pending(self._h, which.ctypes.data_as(ip), idx.ctypes.data_as(ip), _dptr(xn)))
+        return which, idx, xn
+
+    def gibbs_last_sums(self):
+        """(cur, prop) per joint chain: sums over this shard's events judged by the last iteration (float32 mode C)."""
+        J = self.n_procs * self.n_chains
+        cur, prop = np.zeros(J), np.zeros(J)
+        self._ck(self.lib.htm_gibbs_last_sums(self._h, _dptr(cur), _dptr(prop)))
+        return cur, prop
 
     def replay(self, iter_first, iter_last, draws):
         """draws: list (one per virtual rank) of int32 arrays of raw xorshift128 words."""

@@ -80,6 +80,7 @@ struct htm_handle_s {
   bool xch_on = false;
   uint32_t xch_epoch = 1;                  // number of the next exchange; advances identically on every shard
   int* d_xch_status = nullptr;
+  int last_partials = 0, last_parity = 0;  // float32 mode C: layout of the partial sums of the last launch
   // stats
   bool timed = false;
   int64_t last_launches = 0, last_proposals = 0;
@@ -323,10 +324,17 @@ int32_t alloc_state(htm_handle h) {
       }
       return e;
     };
-    HTM_CK(h, grab(&g.hx, J * E * h->rs));
-    HTM_CK(h, grab(&g.hy, J * E * h->rs));
-    HTM_CK(h, grab(&g.hz, J * E * h->rs));
-    HTM_CK(h, grab(&g.hLe, J * E * h->rs));
+    if (h->cfg.precision == HTM_PRECISION_F32) {  // htm_gibbs_f32.cu: float4 state arrays
+      HTM_CK(h, grab(&g.sH, J * E * 16));
+      HTM_CK(h, grab(&g.sM, J * E * 16));
+      HTM_CK(h, grab(&g.sQ, J * E * 16));
+      HTM_CK(h, grab(&g.sP, J * E * 16));
+    } else {
+      HTM_CK(h, grab(&g.hx, J * E * h->rs));
+      HTM_CK(h, grab(&g.hy, J * E * h->rs));
+      HTM_CK(h, grab(&g.hz, J * E * h->rs));
+      HTM_CK(h, grab(&g.hLe, J * E * h->rs));
+    }
     HTM_CK(h, grab(&g.hLp, J * E * h->rs));
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.g_vs), J * 8));
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.g_qs), J * 8));
@@ -811,20 +819,22 @@ int32_t htm_get_chain_state(htm_handle h, int32_t rank, int32_t chain, double* h
   // blocked Gibbs: chain c = rank*n_chains + chain
   {
     const size_t c = static_cast<size_t>(rank) * h->K + chain, E = h->E, S = h->S;
-    std::vector<char> bx(E * h->rs), by(E * h->rs), bz(E * h->rs);
-    HTM_CK(h, cudaMemcpy(bx.data(), static_cast<char*>(h->gl.hx) + c * E * h->rs, E * h->rs, cudaMemcpyDeviceToHost));
-    HTM_CK(h, cudaMemcpy(by.data(), static_cast<char*>(h->gl.hy) + c * E * h->rs, E * h->rs, cudaMemcpyDeviceToHost));
-    HTM_CK(h, cudaMemcpy(bz.data(), static_cast<char*>(h->gl.hz) + c * E * h->rs, E * h->rs, cudaMemcpyDeviceToHost));
-    auto at = [&](const std::vector<char>& b, size_t i) -> double {
-      return h->rs == 8 ? reinterpret_cast<const double*>(b.data())[i]
-                        : static_cast<double>(reinterpret_cast<const float*>(b.data())[i]);
-    };
-    if (hypo)
+    if (hypo && h->rs == 4) {
+      std::vector<float> b4(E * 4);
+      HTM_CK(h, cudaMemcpy(b4.data(), static_cast<char*>(h->gl.sH) + c * E * 16, E * 16, cudaMemcpyDeviceToHost));
+      for (size_t e = 0; e < E; ++e)
+        for (int k = 0; k < 3; ++k) hypo[3 * e + k] = static_cast<double>(b4[4 * e + k]);
+    } else if (hypo) {
+      std::vector<double> bx(E), by(E), bz(E);
+      HTM_CK(h, cudaMemcpy(bx.data(), static_cast<char*>(h->gl.hx) + c * E * 8, E * 8, cudaMemcpyDeviceToHost));
+      HTM_CK(h, cudaMemcpy(by.data(), static_cast<char*>(h->gl.hy) + c * E * 8, E * 8, cudaMemcpyDeviceToHost));
+      HTM_CK(h, cudaMemcpy(bz.data(), static_cast<char*>(h->gl.hz) + c * E * 8, E * 8, cudaMemcpyDeviceToHost));
       for (size_t e = 0; e < E; ++e) {
-        hypo[3 * e] = at(bx, e);
-        hypo[3 * e + 1] = at(by, e);
-        hypo[3 * e + 2] = at(bz, e);
+        hypo[3 * e] = bx[e];
+        hypo[3 * e + 1] = by[e];
+        hypo[3 * e + 2] = bz[e];
       }
+    }
     if (t_corr) HTM_CK(h, cudaMemcpy(t_corr, h->gl.g_tc + c * S, S * 8, cudaMemcpyDeviceToHost));
     if (a_corr) HTM_CK(h, cudaMemcpy(a_corr, h->gl.g_ac + c * S, S * 8, cudaMemcpyDeviceToHost));
     if (vs) HTM_CK(h, cudaMemcpy(vs, h->gl.g_vs + c, 8, cudaMemcpyDeviceToHost));
@@ -934,16 +944,24 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
     h->gl.iter_last = iter_last;
     h->gl.trace = d_trace;
     h->gl.swaps = d_swaps;
+    h->gl.out_partials = &h->last_partials;
+    h->last_parity = iter_last & 1;
     int nlg = 0;
     HTM_CK(h, cudaEventRecord(h->ev0, h->stream));
     {
       const cudaError_t eg = launch_gibbs(h->gl, h->stream, &nlg);
       if (eg == cudaErrorInvalidConfiguration)
         return fail(h, HTM_ERR_UNSUPPORTED,
-                    "blocked-Gibbs mode stages 32 event rows and the chain-level state in shared memory: "
-                    "n_sta (limit about 200) or n_procs*n_chains*n_sta is too large");
+                    "blocked-Gibbs mode stages event rows and chain-level state in shared memory: n_sta is too large "
+                    "(limit about 180), or -- float64 only -- n_procs*n_chains*n_sta exceeds about 10^4");
       if (eg == cudaErrorCooperativeLaunchTooLarge)
-        return fail(h, HTM_ERR_UNSUPPORTED, "HTM_GIBBS_PERSIST=1 but the grid does not fit on the device at once");
+        return fail(h, HTM_ERR_UNSUPPORTED,
+                    "the cooperative grid does not fit on the device at once (HTM_GIBBS_PERSIST=1 with too many tiles, "
+                    "or more than ~9000 joint chains per GPU in float32)");
+      if (eg == cudaErrorNotSupported)
+        return fail(h, HTM_ERR_UNSUPPORTED,
+                    "float32 event-sharded blocked Gibbs exchanges the per-chain sums through peer memory only: call "
+                    "htm_comm_p2p_export / htm_comm_p2p_import (the NCCL all-reduce per iteration serves float64)");
       HTM_CK(h, eg);
     }
     HTM_CK(h, cudaEventRecord(h->ev1, h->stream));
@@ -1500,6 +1518,45 @@ int32_t htm_gather_samples(htm_handle h, int32_t rank, int32_t max_records, int3
   if (!ok && !why.empty()) return fail(h, HTM_ERR_CUDA, why);
   HTM_CK(h, e);
   return HTM_OK;
+}
+
+// Validation entry points of the float32 blocked-Gibbs kernel (tests/): the shared-parameter proposal that the
+// NEXT iteration will judge, and the sums over this shard's events of the per-event log-likelihoods, current and
+// under the proposal, that the LAST iteration judged -- so a test can redo that difference in float64.
+int32_t htm_gibbs_pending(htm_handle h, int32_t* which, int32_t* idx, double* x_new) {
+  if (!h || !which || !idx || !x_new) return fail(h, HTM_ERR_ARG, "null argument");
+  if (h->cfg.mode != HTM_MODE_BLOCKED_GIBBS) return fail(h, HTM_ERR_STATE, "blocked-Gibbs mode only");
+  if (!h->chains_ready) return fail(h, HTM_ERR_STATE, "chains not initialised");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  HTM_CK(h, cudaStreamSynchronize(h->stream));
+  static_assert(sizeof(int) == sizeof(int32_t), "int32");
+  HTM_CK(h, cudaMemcpy(which, h->gl.prop_which, h->C * sizeof(int), cudaMemcpyDeviceToHost));
+  HTM_CK(h, cudaMemcpy(idx, h->gl.prop_idx, h->C * sizeof(int), cudaMemcpyDeviceToHost));
+  HTM_CK(h, cudaMemcpy(x_new, h->gl.prop_xnew, h->C * sizeof(double), cudaMemcpyDeviceToHost));
+  return check_exchange(h);
+}
+
+int32_t htm_gibbs_last_sums(htm_handle h, double* cur, double* prop) {
+  if (!h || !cur || !prop) return fail(h, HTM_ERR_ARG, "null argument");
+  if (h->cfg.mode != HTM_MODE_BLOCKED_GIBBS || h->cfg.precision != HTM_PRECISION_F32)
+    return fail(h, HTM_ERR_UNSUPPORTED, "float32 blocked-Gibbs mode only");
+  if (h->last_partials <= 0) return fail(h, HTM_ERR_STATE, "nothing was run yet");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  HTM_CK(h, cudaStreamSynchronize(h->stream));
+  const size_t J = h->C, gx = h->last_partials, psz = J * gx;
+  std::vector<double> buf(2 * psz);
+  HTM_CK(h, cudaMemcpy(buf.data(), h->gl.part_cur + static_cast<size_t>(h->last_parity) * 2 * psz, 2 * psz * sizeof(double),
+                       cudaMemcpyDeviceToHost));
+  for (size_t c = 0; c < J; ++c) {
+    double a = 0.0, b = 0.0;
+    for (size_t t = 0; t < gx; ++t) {
+      a += buf[c * gx + t];
+      b += buf[psz + c * gx + t];
+    }
+    cur[c] = a;
+    prop[c] = b;
+  }
+  return check_exchange(h);
 }
 
 int32_t htm_device_ptr(htm_handle h, int32_t what, void** ptr, int64_t* n_bytes) {

@@ -17,7 +17,7 @@ struct GibbsParams {
   const real4* obs4;  // raw: no station terms folded
   const real4* evc4;
   const void* prior_xy;  // real2 [E]
-  const float4* obsx;    // float32 only: expanded station-pair rows [E][xrow] (htm_forward.cuh)
+  const float4* obsx;    // float32 only: expanded station-pair rows [E][xrow] (htm_gibbs_f32.cu)
   int xrow;
   real *hx, *hy, *hz, *hLe, *hLp;  // [J][E]
   double *g_vs, *g_qs, *g_tc, *g_ac, *g_T, *g_L;  // [J], [J][S]
@@ -106,7 +106,35 @@ __device__ __forceinline__ ChainSm carve_chain_sm(unsigned char* base, int J, in
   c.slot = i;
   return c;
 }
-__device__ void chain_load(const GibbsDecide& d, const ChainSm& cs) {
+// Variant for any number of joint chains: only the small per-chain state lives in shared memory; the station terms
+// t_corr / a_corr [J][S] stay in global memory (L2) and cs.tc / cs.ac point there.  Every CTA that runs the
+// decide step redundantly writes the SAME accepted values, and every read of a term bypasses L1 (term_ld), so
+// no CTA can see a stale value (htm_gibbs_f32.cu).
+__host__ __device__ inline size_t chain_sm_small_bytes(int J) {
+  return static_cast<size_t>(J) * 8 * sizeof(double) + static_cast<size_t>(J) * 4 * sizeof(int);
+}
+__device__ __forceinline__ ChainSm carve_chain_sm_small(unsigned char* base, int J, double* g_tc, double* g_ac) {
+  ChainSm c;
+  double* d = reinterpret_cast<double*>(base);
+  c.T = d; d += J;
+  c.L = d; d += J;
+  c.vs = d; d += J;
+  c.qs = d; d += J;
+  c.xnew = d; d += J;
+  c.lpr = d; d += J;
+  c.tot = d; d += 2 * J;
+  c.tc = g_tc;
+  c.ac = g_ac;
+  int* i = reinterpret_cast<int*>(d);
+  c.which = i; i += J;
+  c.idx = i; i += J;
+  c.aprev = i; i += J;
+  c.slot = i;
+  return c;
+}
+__device__ __forceinline__ double term_ld(const double* p, const bool gterms) { return gterms ? __ldcg(p) : *p; }
+
+static __device__ void chain_load(const GibbsDecide& d, const ChainSm& cs, const bool terms = true) {
   for (int c = threadIdx.x; c < d.J; c += blockDim.x) {
     cs.T[c] = d.g_T[c];
     cs.L[c] = d.g_L[c];
@@ -119,12 +147,13 @@ __device__ void chain_load(const GibbsDecide& d, const ChainSm& cs) {
     cs.aprev[c] = d.a_prev[c];
     cs.slot[c] = d.slot_of[c];
   }
+  if (!terms) return;
   for (int i = threadIdx.x; i < d.J * d.S; i += blockDim.x) {
     cs.tc[i] = d.g_tc[i];
     cs.ac[i] = d.g_ac[i];
   }
 }
-__device__ void chain_store(const GibbsDecide& d, const ChainSm& cs) {
+static __device__ void chain_store(const GibbsDecide& d, const ChainSm& cs, const bool terms = true) {
   for (int c = threadIdx.x; c < d.J; c += blockDim.x) {
     d.g_T[c] = cs.T[c];
     d.g_L[c] = cs.L[c];
@@ -137,6 +166,7 @@ __device__ void chain_store(const GibbsDecide& d, const ChainSm& cs) {
     d.a_prev[c] = cs.aprev[c];
     d.slot_of[c] = cs.slot[c];
   }
+  if (!terms) return;
   for (int i = threadIdx.x; i < d.J * d.S; i += blockDim.x) {
     d.g_tc[i] = cs.tc[i];
     d.g_ac[i] = cs.ac[i];
@@ -163,7 +193,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ bool peer_allreduce(const PeerExchange& x, const uint32_t epoch, double* tot /* shared memory, W values, in/out */,
+static __device__ bool peer_allreduce(const PeerExchange& x, const uint32_t epoch, double* tot /* shared memory, W values, in/out */,
                                const int W) {
   __shared__ int s_xch_fail;
   const int n = x.n, me = x.rank, par = static_cast<int>(epoch & 1u);
@@ -209,7 +239,7 @@ __device__ bool peer_allreduce(const PeerExchange& x, const uint32_t epoch, doub
 
 // Per-chain sums of the per-tile (or per-CTA) partial sums, in a fixed order; every thread of the CTA calls it
 // (no barrier inside: the caller synchronises before reading tot).
-__device__ void sum_partials(const int n_tiles, const double* part_cur, const double* part_prop, const int J, double* tot) {
+static __device__ void sum_partials(const int n_tiles, const double* part_cur, const double* part_prop, const int J, double* tot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   // fixed-order sums of the per-tile partials: lanes stride over tiles, then a butterfly.  With fewer than
   // 32 partials per chain a warp serves 32/g chains at once (g = lanes per chain, a power of two): the
@@ -266,10 +296,11 @@ __device__ void sum_partials(const int n_tiles, const double* part_cur, const do
 // `writer` computes exactly the same values but leaves counters, records and traces alone (the
 // persistent kernel runs this redundantly on every CTA so that one grid barrier per iteration suffices).
 // Ends with a block barrier.
-__device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int it, const int it_next,
+static __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int it, const int it_next,
                             const double* part_cur, const double* part_prop, const int rec_slot,
                             htm_step_trace* trace, htm_swap_trace* swap, const bool writer,
-                            const bool summed = false /* part_* are already the sums over all tiles and shards */) {
+                            const bool summed = false /* part_* are already the sums over all tiles and shards */,
+                            const bool gterms = false /* cs.tc / cs.ac are global memory (carve_chain_sm_small) */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int J = d.J, S = d.S;
   if (it > 0) {
@@ -328,8 +359,8 @@ __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int i
           d.rec_L[o] = cs.L[c];
         }
         for (int j = lane; j < S; j += 32) {
-          d.rec_tc[o * S + j] = cs.tc[static_cast<size_t>(c) * S + j];
-          d.rec_ac[o * S + j] = cs.ac[static_cast<size_t>(c) * S + j];
+          d.rec_tc[o * S + j] = term_ld(cs.tc + static_cast<size_t>(c) * S + j, gterms);
+          d.rec_ac[o * S + j] = term_ld(cs.ac + static_cast<size_t>(c) * S + j, gterms);
         }
       }
     }
@@ -393,9 +424,9 @@ __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int i
     const double gs = gauss64(wa.v[2], wa.v[3]);
     double x_old;
     if (which == 1) x_old = cs.vs[c];
-    else if (which == 2) x_old = cs.tc[static_cast<size_t>(c) * S + idx];
+    else if (which == 2) x_old = term_ld(cs.tc + static_cast<size_t>(c) * S + idx, gterms);
     else if (which == 3) x_old = cs.qs[c];
-    else x_old = cs.ac[static_cast<size_t>(c) * S + idx];
+    else x_old = term_ld(cs.ac + static_cast<size_t>(c) * S + idx, gterms);
     const double mu = d.prior[which - 1], sg = d.width[which - 1];
     const double x_new = __dadd_rn(x_old, __dmul_rn(gs, d.step[which - 1]));
     const double dn = x_new - mu, dl = x_old - mu;
@@ -407,13 +438,132 @@ __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, const int i
   __syncthreads();
 }
 
+// one CTA, station terms left in global memory: smem chain_sm_small_bytes(J)
+static __device__ void gibbs_decide_small(const GibbsDecide& d, unsigned char* smem) {
+  const ChainSm cs = carve_chain_sm_small(smem, d.J, d.g_tc, d.g_ac);
+  chain_load(d, cs, false);
+  __syncthreads();
+  decide_core(d, cs, d.it, d.it_next, d.part_cur, d.part_prop, d.rec_slot, d.trace, d.swap, true, false, true);
+  chain_store(d, cs, false);
+}
+
 // one CTA: global -> shared, decide, shared -> global.  smem: chain_sm_bytes(J, S)
-__device__ void gibbs_decide(const GibbsDecide& d, unsigned char* smem) {
+static __device__ void gibbs_decide(const GibbsDecide& d, unsigned char* smem) {
   const ChainSm cs = carve_chain_sm(smem, d.J, d.S);
   chain_load(d, cs);
   __syncthreads();
   decide_core(d, cs, d.it, d.it_next, d.part_cur, d.part_prop, d.rec_slot, d.trace, d.swap, true);
   chain_store(d, cs);
 }
+
+// ---- host side: launch description -> kernel parameter blocks (shared by htm_gibbs.cu and htm_gibbs_f32.cu) ----
+template <typename real>
+inline GibbsParams<real> make_gibbs_params(const GibbsLaunch& a) {
+  GibbsParams<real> p;
+  typedef typename M<real>::real4 real4;
+  p.sta4 = static_cast<const real4*>(a.tab.sta4);
+  p.obs4 = static_cast<const real4*>(a.tab.obs4_raw);
+  p.evc4 = static_cast<const real4*>(a.tab.evc4);
+  p.prior_xy = a.tab.prior_xy;
+  p.obsx = static_cast<const float4*>(a.obsx);
+  p.xrow = a.xrow;
+  p.hx = static_cast<real*>(a.hx);
+  p.hy = static_cast<real*>(a.hy);
+  p.hz = static_cast<real*>(a.hz);
+  p.hLe = static_cast<real*>(a.hLe);
+  p.hLp = static_cast<real*>(a.hLp);
+  p.g_vs = a.g_vs;
+  p.g_qs = a.g_qs;
+  p.g_tc = a.g_tc;
+  p.g_ac = a.g_ac;
+  p.g_T = a.g_T;
+  p.g_L = a.g_L;
+  p.prop_which = a.prop_which;
+  p.prop_idx = a.prop_idx;
+  p.prop_xnew = a.prop_xnew;
+  p.prop_lpr = a.prop_lpr;
+  p.a_prev = a.a_prev;
+  p.slot_of = a.slot_of;
+  p.part_cur = a.part_cur;  // one allocation [2][2][J][n_tiles]; the per-iteration path uses buffer 0
+  p.part_prop = a.part_cur + static_cast<size_t>(a.J) * ((a.E + kTile - 1) / kTile);
+  p.E = a.E;
+  p.S = a.S;
+  p.J = a.J;
+  p.K = a.K;
+  p.n_tiles = (a.E + kTile - 1) / kTile;
+  p.n_cool_total = a.n_cool_total;
+  p.it = 0;
+  p.n_burn = a.n_burn;
+  p.n_interval = a.n_interval;
+  p.rk = philox_keys(a.seed);
+  p.event_offset = a.event_offset;
+  p.chain_offset = a.chain_offset;
+  p.J_total = a.J_total;
+  p.prior_z = static_cast<real>(a.prior_z);
+  p.width_z = static_cast<real>(a.width_z);
+  p.width_xy = static_cast<real>(a.width_xy);
+  p.step_xy = static_cast<real>(a.step_xy);
+  p.step_z = static_cast<real>(a.step_z);
+  p.counts = a.counts;
+  p.hypo_rec = static_cast<real4*>(a.hypo_rec);
+  p.rec_slot = -1;
+  p.trace = nullptr;
+  p.swap = nullptr;
+  return p;
+}
+
+inline GibbsDecide make_decide(const GibbsLaunch& a) {
+  GibbsDecide d;
+  d.g_vs = a.g_vs;
+  d.g_qs = a.g_qs;
+  d.g_tc = a.g_tc;
+  d.g_ac = a.g_ac;
+  d.g_T = a.g_T;
+  d.g_L = a.g_L;
+  d.prop_which = a.prop_which;
+  d.prop_idx = a.prop_idx;
+  d.prop_xnew = a.prop_xnew;
+  d.prop_lpr = a.prop_lpr;
+  d.a_prev = a.a_prev;
+  d.slot_of = a.slot_of;
+  d.part_cur = a.part_cur;
+  d.part_prop = a.part_cur + static_cast<size_t>(a.J) * ((a.E + kTile - 1) / kTile);
+  d.S = a.S;
+  d.J = a.J;
+  d.K = a.K;
+  d.n_tiles = (a.E + kTile - 1) / kTile;
+  d.n_cool_total = a.n_cool_total;
+  d.it = 0;
+  d.it_next = 0;
+  d.rk = philox_keys(a.seed);
+  d.chain_offset = a.chain_offset;
+  d.swap_stream = a.swap_stream;
+  d.n_solved = 0;
+  for (int t = 0; t < 4; ++t) {
+    d.solved[t] = 0;
+    if (a.solve[t]) d.solved[d.n_solved++] = t + 1;
+    d.prior[t] = a.g_prior[t];
+    d.width[t] = a.g_width[t];
+    d.step[t] = a.g_step[t];
+  }
+  d.counts = a.counts;
+  d.count_globals = a.count_globals;
+  d.xch = a.xch;
+  d.rec_slot = -1;
+  d.rec_chain = a.rec_chain;
+  d.rec_vs = a.rec_vs;
+  d.rec_qs = a.rec_qs;
+  d.rec_L = a.rec_L;
+  d.rec_tc = a.rec_tc;
+  d.rec_ac = a.rec_ac;
+  d.trace = nullptr;
+  d.swap = nullptr;
+  return d;
+}
+
+
+// float32 joint-chain kernel (htm_gibbs_f32.cu)
+cudaError_t launch_gibbs_f32(const GibbsLaunch& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_gibbs_f32_init(const GibbsLaunch& a, cudaStream_t stream);
 
 }  // namespace htm

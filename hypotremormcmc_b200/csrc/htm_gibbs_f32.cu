@@ -1,0 +1,662 @@
+// Mode C (blocked Gibbs), float32: the throughput kernel of the joint-chain schedule.
+//
+// Schedule (identical to the float64 kernels of htm_gibbs.cu, whose CPU statement lives with the test oracle):
+// per iteration every (chain, event) proposes one hypocentre coordinate, judged on the event's own
+// log-likelihood with the chain's temperature (src/cls_mcmc.f90:159-165,193-203; src/cls_forward.f90:307-362);
+// then ONE shared parameter per chain (vs | one t_corr | qs | one a_corr) is judged on the sum over ALL events
+// (what the reference recomputes with forward%calc_log_likelihood, src/cls_forward.f90:268-303); record; one
+// swap attempt over all chains (src/cls_parallel.f90:220-240,285-302).
+//
+// What is different from a literal evaluation: the effect of a shared-parameter proposal on an event's
+// log-likelihood is a LOW-ORDER POLYNOMIAL in the parameter change once a few weighted moments of the event's
+// residuals are known, so the second O(n_sta) forward evaluation per (chain, event, iteration) disappears:
+//   with e_j = r_j - r_0 (residual relative to station 0, j >= 1), D_j = d_j - d_0, w = sigma^-2,
+//     S1 = sum w e      S2 = sum w e^2      A1 = sum w D      A2 = sum w e D      A3 = sum w D^2
+//     chi^2 = S2 - S1^2 / W,  L_e = -(chi_t^2 + chi_a^2)/2 - C_e            (src/cls_forward.f90:166-173,283-297)
+//   vs -> vs'    : e_t += D (1/vs' - 1/vs),  e_a -= D (B' - B),  B = pi f /(Q vs)      (:157-160, :247)
+//                  dS1 = q A1, dS2 = q (2 A2 + q A3), dA2 = q A3      (q = the coefficient of D)
+//   qs -> qs'    : the amplitude half of the same
+//   tc_j -> +dlt : j >= 1: e_j -= dlt      -> dS1 = -w dlt, dS2 = w dlt (dlt - 2 e_j), dA2 = -w dlt D_j
+//                  j == 0: e_k += dlt (all k) -> dS1 = dlt W', dS2 = dlt (2 S1 + dlt W'), dA2 = dlt A1
+//   ac_j         : the same on the amplitude sums
+// One pass over the stations at the PROPOSED hypocentre yields L_e and all moments (25 packed FP32 operations +
+// 4 MUFU per station pair and chain instead of 2 x (16 + 4)); the per-event change of the pending
+// shared-parameter proposal then costs O(1).  It is also the cancellation-free way to form the Metropolis ratio
+// of a shared parameter in float32: sum_e dL_e is accumulated in float64 from per-event DIFFERENCES instead of
+// differencing two sums of 10^4..10^5 float32 log-likelihoods.
+//
+// State per (chain, event), float4 arrays [J][E] (event index fastest):
+//   H = {x, y, z, L_e}   M = {A1t, A3t, A1a, A3a}   Q = {S1t, S1a, A2t, A2a}   P = Q under the pending proposal
+//   Lp = L_e under the pending proposal.  An accepted shared-parameter proposal is committed lazily by the next
+//   sweep (H.w := Lp, Q := P), exactly the numbers that were judged.
+//
+// Mapping: persistent cooperative kernel, one wave of CTAs.  warp = 8 events x 4 chains (chain minor: lanes that
+// share an event row are neighbours, 2 shared-memory wavefronts per 16-byte row read instead of 4); a CTA owns up
+// to 32 chains and walks a contiguous range of event octets whose expanded rows (htm_forward.cuh) arrive through
+// a 2-stage ring of 1-D bulk-TMA copies (full / empty mbarriers) that runs across iteration boundaries.  Per
+// iteration: sweep -> per-(chain, CTA) float64 partial sums -> ONE grid barrier -> every CTA adds the partials in
+// the same fixed order and takes the same decisions on its own shared-memory copy of the small per-chain state
+// (CTA (0,0) alone writes counters, records, traces).  The station terms t_corr/a_corr [J][S] stay in global
+// memory (L2): every CTA writes the same accepted values, reads bypass L1.  Event shards (several GPUs, one
+// ensemble) exchange the per-chain sums through NVLink peer memory between two grid barriers.
+#include <cooperative_groups.h>
+
+#include "htm_gibbs_decide.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace htm {
+
+constexpr int kOct = 8;
+constexpr int kQuad = 4;
+constexpr float kHalfLn2 = 0.34657359027997264f;
+
+// ---- expanded rows: built once per table upload -------------------------------------------------------------
+// row[0] = A of station 0, row[1] = {t_obs0, a_obs0, sum_{j>=1} w_t, sum_{j>=1} w_a}, then 4 float4 per station
+// pair (1,2), (3,4), ... (store_station_pair); an even station count leaves a zero-weight half pair.
+__global__ void expand_obs_kernel(const float4* __restrict__ sta4, const float4* __restrict__ obs4,
+                                  const float2* __restrict__ prior_xy, int E, int S, float4* __restrict__ obsx) {
+  const int n_pairs = S / 2, per_ev = n_pairs + 1, xrow = 2 + 4 * n_pairs;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(E) * per_ev) return;
+  const int e = static_cast<int>(i / per_ev), m = static_cast<int>(i % per_ev) - 1;
+  const float2 c = prior_xy[e];
+  const float4* ob = obs4 + static_cast<size_t>(e) * S;
+  float4* row = obsx + static_cast<size_t>(e) * xrow;
+  if (m < 0) {
+    const StaRecF r0 = expand_station(sta4[0], ob[0], c.x, c.y);
+    float wt = 0.f, wa = 0.f;
+    for (int j = 1; j < S; ++j) {
+      wt += ob[j].y;
+      wa += ob[j].w;
+    }
+    row[0] = r0.A;
+    row[1] = make_float4(ob[0].x, ob[0].z, wt, wa);
+    return;
+  }
+  const int j0 = 1 + 2 * m, j1 = j0 + 1;
+  const StaRecF a = expand_station(sta4[j0], ob[j0], c.x, c.y);
+  StaRecF b = a;
+  if (j1 < S)
+    b = expand_station(sta4[j1], ob[j1], c.x, c.y);
+  else
+    b.B = make_float4(0.f, 0.f, 0.f, 0.f);
+  store_station_pair(row + 2 + 4 * m, a, b);
+}
+
+cudaError_t launch_expand_obs(const Tables& tab, int E, int S, void* obsx, cudaStream_t stream) {
+  const size_t n = static_cast<size_t>(E) * (S / 2 + 1);
+  expand_obs_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(
+      static_cast<const float4*>(tab.sta4), static_cast<const float4*>(tab.obs4_raw),
+      static_cast<const float2*>(tab.prior_xy), E, S, static_cast<float4*>(obsx));
+  return cudaGetLastError();
+}
+
+// ---- one pass over the stations: log-likelihood and moments at a hypocentre ---------------------------------
+struct Moments {
+  float L, S1t, S1a, A1t, A2t, A3t, A1a, A2a, A3a;
+};
+struct RowHead {  // station 0 at a hypocentre: its distance and the (negated) shifts
+  float d0, nct, nca;
+};
+__device__ __forceinline__ RowHead row_head(const float4* __restrict__ row, const float hx, const float hy, const float hz,
+                                            const float h2, const Glob<float>& g, const float ntc0, const float nac0) {
+  const float4 A0 = row[0], h1 = row[1];
+  const float d2 = fmaf(hx, A0.x, fmaf(hy, A0.y, fmaf(hz, A0.z, A0.w + h2)));
+  RowHead r;
+  r.d0 = d2 * mufu_rsq(d2);
+  const float l2 = mufu_lg2(d2);
+  r.nct = -(fmaf(r.d0, g.ivs, ntc0) - h1.x);
+  r.nca = -(fmaf(-kHalfLn2, l2, fmaf(-g.B, r.d0, nac0)) - h1.y);
+  return r;
+}
+
+#ifndef HTM_GIBBS_PK_UNROLL
+#define HTM_GIBBS_PK_UNROLL 2
+#endif
+constexpr int kMomentsUnroll = HTM_GIBBS_PK_UNROLL;
+// cp[m] = {-tc_j0, -tc_j1, -ac_j0, -ac_j1}: the chain's station terms of pair m; ntc0 / nac0 those of station 0
+__device__ __forceinline__ Moments eval_moments_f32(const float4* __restrict__ row, const int n_pairs, const float hx,
+                                                    const float hy, const float hz, const Glob<float>& g,
+                                                    const float4* __restrict__ cp, const float ntc0, const float nac0,
+                                                    const float4 evc) {
+  const float h2 = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
+  const RowHead hd = row_head(row, hx, hy, hz, h2, g, ntc0, nac0);
+  const float2 nct = f2(hd.nct, hd.nct), nca = f2(hd.nca, hd.nca), nd0 = f2(-hd.d0, -hd.d0);
+  const float2 px = f2(hx, hx), py = f2(hy, hy), pz = f2(hz, hz), hh = f2(h2, h2);
+  const float2 ivs2 = f2(g.ivs, g.ivs), nB2 = f2(-g.B, -g.B), nc2 = f2(-kHalfLn2, -kHalfLn2);
+  float2 a1t = f2(0.f, 0.f), a1a = f2(0.f, 0.f), a2 = f2(0.f, 0.f);
+  float2 m1t = f2(0.f, 0.f), m2t = f2(0.f, 0.f), m3t = f2(0.f, 0.f);
+  float2 m1a = f2(0.f, 0.f), m2a = f2(0.f, 0.f), m3a = f2(0.f, 0.f);
+  const float4* r = row + 2;
+#pragma unroll kMomentsUnroll
+  for (int m = 0; m < n_pairs; ++m) {
+    const float4 r0 = r[4 * m], r1 = r[4 * m + 1], r2 = r[4 * m + 2], r3 = r[4 * m + 3];
+    const float4 c4 = cp[m];
+    const float2 swt = f2(r2.x, r2.y), swa = f2(r3.x, r3.y);
+    const float2 d2 = __ffma2_rn(px, f2(r0.x, r0.y),
+                                 __ffma2_rn(py, f2(r0.z, r0.w), __ffma2_rn(pz, f2(r1.x, r1.y), __fadd2_rn(f2(r1.z, r1.w), hh))));
+    const float2 d = __fmul2_rn(d2, f2(mufu_rsq(d2.x), mufu_rsq(d2.y)));
+    const float2 l2 = f2(mufu_lg2(d2.x), mufu_lg2(d2.y));
+    const float2 at = __fadd2_rn(__ffma2_rn(d, ivs2, nct), f2(c4.x, c4.y));
+    const float2 ut = __ffma2_rn(swt, at, f2(r2.z, r2.w));  // sqrt(w_t) e_t
+    const float2 aa = __fadd2_rn(__ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, nca)), f2(c4.z, c4.w));
+    const float2 ua = __ffma2_rn(swa, aa, f2(r3.z, r3.w));  // sqrt(w_a) e_a
+    const float2 D = __fadd2_rn(d, nd0);
+    const float2 pt = __fmul2_rn(swt, D), pa = __fmul2_rn(swa, D);  // sqrt(w) D
+    a2 = __ffma2_rn(ut, ut, a2);
+    a1t = __ffma2_rn(swt, ut, a1t);
+    a2 = __ffma2_rn(ua, ua, a2);
+    a1a = __ffma2_rn(swa, ua, a1a);
+    m1t = __ffma2_rn(swt, pt, m1t);
+    m2t = __ffma2_rn(ut, pt, m2t);
+    m3t = __ffma2_rn(pt, pt, m3t);
+    m1a = __ffma2_rn(swa, pa, m1a);
+    m2a = __ffma2_rn(ua, pa, m2a);
+    m3a = __ffma2_rn(pa, pa, m3a);
+  }
+  Moments o;
+  o.S1t = a1t.x + a1t.y;
+  o.S1a = a1a.x + a1a.y;
+  o.A1t = m1t.x + m1t.y;
+  o.A2t = m2t.x + m2t.y;
+  o.A3t = m3t.x + m3t.y;
+  o.A1a = m1a.x + m1a.y;
+  o.A2a = m2a.x + m2a.y;
+  o.A3a = m3a.x + m3a.y;
+  o.L = finish_loglik<float>(o.S1t, a2.x + a2.y, o.S1a, 0.f, evc);
+  return o;
+}
+
+// Change of the sums under the chain's pending shared-parameter proposal (see the header of this file).
+// qa: coefficient of D in e_t (vs: 1/vs' - 1/vs, else 0); qb: coefficient of D in e_a (vs, qs: -(B' - B));
+// dlt: change of the station term (t_corr / a_corr proposals).
+struct PropF32 {
+  int which, idx;
+  float qa, qb, dlt;
+};
+struct DeltaSums {
+  float dS1t, dS2t, dA2t, dS1a, dS2a, dA2a;
+};
+__device__ __forceinline__ DeltaSums pending_delta(const PropF32& pr, const float4* __restrict__ row, const int n_pairs,
+                                                   const float hx, const float hy, const float hz, const Glob<float>& g,
+                                                   const float4* __restrict__ cp, const float ntc0, const float nac0,
+                                                   const float4 Mm, const float4 Q) {
+  DeltaSums o = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (pr.which == 1 || pr.which == 3) {
+    o.dS1t = pr.qa * Mm.x;
+    o.dS2t = pr.qa * fmaf(pr.qa, Mm.y, 2.f * Q.z);
+    o.dA2t = pr.qa * Mm.y;
+    o.dS1a = pr.qb * Mm.z;
+    o.dS2a = pr.qb * fmaf(pr.qb, Mm.w, 2.f * Q.w);
+    o.dA2a = pr.qb * Mm.w;
+    return o;
+  }
+  if (pr.which != 2 && pr.which != 4) return o;
+  const bool is_t = pr.which == 2;
+  const float dlt = pr.dlt;
+  if (pr.idx == 0) {  // station 0 carries the shift: every other residual moves by +dlt
+    const float4 h1 = row[1];
+    if (is_t) {
+      o.dS1t = dlt * h1.z;
+      o.dS2t = dlt * fmaf(dlt, h1.z, 2.f * Q.x);
+      o.dA2t = dlt * Mm.x;
+    } else {
+      o.dS1a = dlt * h1.w;
+      o.dS2a = dlt * fmaf(dlt, h1.w, 2.f * Q.y);
+      o.dA2a = dlt * Mm.z;
+    }
+    return o;
+  }
+  // one station of the event at the CURRENT hypocentre (plus station 0 for the shift)
+  const float h2 = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
+  const RowHead hd = row_head(row, hx, hy, hz, h2, g, ntc0, nac0);
+  const int m = (pr.idx - 1) >> 1;
+  const bool hi = ((pr.idx - 1) & 1) != 0;
+  const float4* r = row + 2 + 4 * m;
+  const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], c4 = cp[m];
+  const float cx = hi ? r0.y : r0.x, cy = hi ? r0.w : r0.z, cz = hi ? r1.y : r1.x, cc = hi ? r1.w : r1.z;
+  const float d2 = fmaf(hx, cx, fmaf(hy, cy, fmaf(hz, cz, cc + h2)));
+  const float d = d2 * mufu_rsq(d2);
+  const float D = d - hd.d0;
+  if (is_t) {
+    const float sw = hi ? r2.y : r2.x, so = hi ? r2.w : r2.z, ntc = hi ? c4.y : c4.x;
+    const float u = fmaf(sw, fmaf(d, g.ivs, hd.nct) + ntc, so);  // sqrt(w) e
+    const float w = sw * sw;
+    o.dS1t = -w * dlt;
+    o.dS2t = dlt * fmaf(w, dlt, -2.f * sw * u);
+    o.dA2t = -w * dlt * D;
+  } else {
+    const float l2 = mufu_lg2(d2);
+    const float sw = hi ? r3.y : r3.x, so = hi ? r3.w : r3.z, nac = hi ? c4.w : c4.z;
+    const float u = fmaf(sw, fmaf(-kHalfLn2, l2, fmaf(-g.B, d, hd.nca)) + nac, so);
+    const float w = sw * sw;
+    o.dS1a = -w * dlt;
+    o.dS2a = dlt * fmaf(w, dlt, -2.f * sw * u);
+    o.dA2a = -w * dlt * D;
+  }
+  return o;
+}
+
+// ---- shared memory of one CTA ----------------------------------------------------------------------------------
+struct F32Sm {
+  uint64_t* full;   // [2]
+  uint64_t* empty;  // [2]
+  float4* rows;     // [2][kOct][row]
+  float4* cp;       // [nc][cps]
+  float4* c0;       // [nc]  {-tc0, -ac0, 0, 0}
+  float* pq;        // [nc][3]  qa, qb, dlt of the pending proposal
+  int row, cps;
+};
+__host__ __device__ inline int f32_cps(int S) { return (S / 2) | 1; }
+__host__ __device__ inline size_t f32_sweep_smem(int S, int nc) {
+  const int xrow = 2 + 4 * (S / 2);
+  return 32 + (static_cast<size_t>(2) * kOct * (xrow + 1) + static_cast<size_t>(nc) * (f32_cps(S) + 1)) * sizeof(float4) +
+         static_cast<size_t>(nc) * 4 * sizeof(float);
+}
+__device__ __forceinline__ F32Sm carve_f32_sm(unsigned char* base, int S, int xrow, int nc) {
+  F32Sm m;
+  m.row = xrow + 1;
+  m.cps = f32_cps(S);
+  m.full = reinterpret_cast<uint64_t*>(base);
+  m.empty = m.full + 2;
+  m.rows = reinterpret_cast<float4*>(base + 32);
+  m.cp = m.rows + 2 * kOct * m.row;
+  m.c0 = m.cp + nc * m.cps;
+  m.pq = reinterpret_cast<float*>(m.c0 + nc);
+  return m;
+}
+
+// the station terms of the CTA's chains from global memory (L2) and the coefficients of their pending proposals
+__device__ __forceinline__ void f32_stage_chain_terms(const F32Sm& m, const ChainSm& cs, int nc, int c_base, int J, int S) {
+  const int n_pairs = S / 2;
+  for (int i = threadIdx.x; i < nc * n_pairs; i += blockDim.x) {
+    const int lc = i / n_pairs, mm = i - lc * n_pairs, c = c_base + lc;
+    if (c >= J) continue;
+    const double* gtc = cs.tc + static_cast<size_t>(c) * S;
+    const double* gac = cs.ac + static_cast<size_t>(c) * S;
+    const int j0 = 1 + 2 * mm, j1 = j0 + 1;
+    float4 cur = make_float4(-static_cast<float>(__ldcg(gtc + j0)), 0.f, -static_cast<float>(__ldcg(gac + j0)), 0.f);
+    if (j1 < S) {
+      cur.y = -static_cast<float>(__ldcg(gtc + j1));
+      cur.w = -static_cast<float>(__ldcg(gac + j1));
+    }
+    m.cp[lc * m.cps + mm] = cur;
+  }
+  for (int lc = threadIdx.x; lc < nc; lc += blockDim.x) {
+    const int c = c_base + lc;
+    if (c >= J) continue;
+    const double tc0 = __ldcg(cs.tc + static_cast<size_t>(c) * S), ac0 = __ldcg(cs.ac + static_cast<size_t>(c) * S);
+    m.c0[lc] = make_float4(-static_cast<float>(tc0), -static_cast<float>(ac0), 0.f, 0.f);
+    const int wh = cs.which[c];
+    const double vs = cs.vs[c], qs = cs.qs[c], xn = cs.xnew[c];
+    double qa = 0.0, qb = 0.0, dlt = 0.0;
+    if (wh == 1) {
+      qa = 1.0 / xn - 1.0 / vs;
+      qb = -(kPi * kFreq / (qs * xn) - kPi * kFreq / (qs * vs));
+    } else if (wh == 3) {
+      qb = -(kPi * kFreq / (xn * vs) - kPi * kFreq / (qs * vs));
+    } else if (wh == 2) {
+      dlt = xn - __ldcg(cs.tc + static_cast<size_t>(c) * S + cs.idx[c]);
+    } else if (wh == 4) {
+      dlt = xn - __ldcg(cs.ac + static_cast<size_t>(c) * S + cs.idx[c]);
+    }
+    m.pq[3 * lc] = static_cast<float>(qa);
+    m.pq[3 * lc + 1] = static_cast<float>(qb);
+    m.pq[3 * lc + 2] = static_cast<float>(dlt);
+  }
+}
+
+struct F32State {
+  float4 *H, *M, *Q, *P;
+  float* Lp;
+};
+
+// INIT = true: generate_model for every (chain, event) (src/cls_model.f90:139-158, Philox draws as in the
+// float64 path) and its state at the initial shared parameters; no iteration is run.
+template <bool TRACE, bool INIT>
+__global__ void __launch_bounds__(kCW * 32, 2)
+    gibbs_f32_kernel(const GibbsParams<float> p, const GibbsDecide d, const F32State st, const int iter_first,
+                     const int iter_last, const int rec_origin, const int rec_cap, htm_step_trace* trace_base,
+                     htm_swap_trace* swap_base, double* part /* [2][2][J][gridDim.x] */, const int n_oct,
+                     double* totals /* [2*J] */, const uint64_t seed) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::grid_group grid = cg::this_grid();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const int S = p.S, J = p.J, E = p.E, n_pairs = S / 2;
+  const int nc = n_warps * kQuad;
+  const int c_base = blockIdx.y * nc;
+  const bool writer = blockIdx.x == 0 && blockIdx.y == 0;
+  const F32Sm m = carve_f32_sm(smem_raw, S, p.xrow, nc);
+  const ChainSm cs = carve_chain_sm_small(smem_raw + ((f32_sweep_smem(S, nc) + 15) & ~static_cast<size_t>(15)), J,
+                                          d.g_tc, d.g_ac);
+  const int o_begin = static_cast<int>(static_cast<long>(n_oct) * blockIdx.x / gridDim.x);
+  const int o_end = static_cast<int>(static_cast<long>(n_oct) * (blockIdx.x + 1) / gridDim.x);
+  const int n_my = o_end - o_begin;  // >= 1: the launcher never starts more CTAs per chain group than octets
+  const int n_it = INIT ? 1 : iter_last - iter_first + 1;
+  const long n_run = static_cast<long>(n_my) * n_it;  // octet visits of this CTA
+  const uint32_t row_bytes = static_cast<uint32_t>(p.xrow * sizeof(float4));
+  if (threadIdx.x == 0) {
+    mbar_init(m.full, 1);
+    mbar_init(m.full + 1, 1);
+    mbar_init(m.empty, n_warps);
+    mbar_init(m.empty + 1, n_warps);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  auto issue = [&](long t) {  // visit t of this CTA -> ring stage t & 1
+    const int buf = static_cast<int>(t & 1), o = o_begin + static_cast<int>(t % n_my);
+    const int n_ev = min(kOct, E - o * kOct);
+    if (lane == 0) mbar_expect_tx(m.full + buf, row_bytes * n_ev);
+    __syncwarp();
+    if (lane < n_ev)
+      tma_load_1d(m.rows + (buf * kOct + lane) * m.row, p.obsx + static_cast<size_t>(o * kOct + lane) * p.xrow, row_bytes,
+                  m.full + buf);
+  };
+  if (warp == 0) {
+    if (n_run > 0) issue(0);
+    if (n_run > 1) issue(1);
+  }
+  chain_load(d, cs, /*terms=*/false);
+  __syncthreads();
+
+  const int es = lane >> 2, chs = lane & (kQuad - 1);
+  const bool warp_ok = c_base + warp * kQuad < J;
+  const bool c_ok = c_base + warp * kQuad + chs < J;
+  const int lc = c_ok ? warp * kQuad + chs : warp * kQuad;
+  const int c = warp_ok ? c_base + lc : 0;
+  const size_t per_it = static_cast<size_t>(E + 1) * J, psz = static_cast<size_t>(J) * gridDim.x;
+  uint32_t cnt_p[3] = {0, 0, 0}, cnt_a[3] = {0, 0, 0};
+  long t_run = 0;
+
+  for (int it = iter_first; it < iter_first + n_it; ++it) {
+    double* part_cur = part + static_cast<size_t>(it & 1) * 2 * psz;
+    double* part_prop = part_cur + psz;
+    const bool rec = !INIT && p.n_interval > 1 && (it % p.n_interval) == 1;
+    int rec_slot = rec ? (it - 1) / p.n_interval - rec_origin : -1;
+    if (rec_slot >= rec_cap) rec_slot = -1;
+    htm_step_trace* trace_it = trace_base ? trace_base + static_cast<size_t>(it - iter_first) * per_it : nullptr;
+    // the CTA's chain terms for this iteration (decide_core ended with a block barrier; the previous
+    // iteration's reads of cp / pq are over)
+    f32_stage_chain_terms(m, cs, nc, c_base, J, S);
+    __syncthreads();
+    const float T = static_cast<float>(cs.T[c]);
+    const float iT = 1.f / T;
+    const bool cold = gibbs_is_cold<float>(cs.T[c]);
+    const Glob<float> g = make_glob<float>(static_cast<float>(cs.vs[c]), static_cast<float>(cs.qs[c]));
+    PropF32 pr;
+    pr.which = INIT ? 0 : cs.which[c];
+    pr.idx = cs.idx[c];
+    pr.qa = m.pq[3 * lc];
+    pr.qb = m.pq[3 * lc + 1];
+    pr.dlt = m.pq[3 * lc + 2];
+    const float4* cp = m.cp + lc * m.cps;
+    const float4 c0 = warp_ok ? m.c0[lc] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool a_prev = !INIT && cs.aprev[c] != 0;
+    const int rec_chain_slot = (rec_slot >= 0 && p.hypo_rec) ? cs.slot[c] : -1;
+    double s_cur = 0.0, s_prop = 0.0;
+    for (int i = 0; i < n_my; ++i, ++t_run) {
+      const int buf = static_cast<int>(t_run & 1);
+      const uint32_t ph = static_cast<uint32_t>((t_run >> 1) & 1);
+      const int o = o_begin + i;
+      mbar_wait(m.full + buf, ph);
+      if (warp_ok) {
+        const int n_ev = min(kOct, E - o * kOct);
+        const int e = o * kOct + es;
+        const bool ev_ok = e < E;
+        const int ee = ev_ok ? e : E - 1;  // idle lanes clone the last event and never write
+        const float4* row = m.rows + (buf * kOct + (ev_ok ? es : n_ev - 1)) * m.row;
+        const size_t ci = static_cast<size_t>(c) * E + ee;
+        const float4 evc = p.evc4[ee];
+        const float2 mu = reinterpret_cast<const float2*>(p.prior_xy)[ee];
+        const uint32_t gid = (static_cast<uint32_t>(ee) + p.event_offset) * p.J_total + p.chain_offset + static_cast<uint32_t>(c);
+        float4 H, Mm, Q;
+        bool acc = false, dirty = false;
+        int icmp = 0;
+        if (INIT) {
+          const u32x4 a = philox4x32_10(seed, 0u, gid, PHX_INIT, 0u);
+          const u32x4 b = philox4x32_10(seed, 1u, gid, PHX_INIT, 0u);
+          H.x = mu.x + M<float>::gauss(a.v[0], a.v[1]) * p.width_xy;
+          H.y = mu.y + M<float>::gauss(a.v[2], a.v[3]) * p.width_xy;
+          H.z = p.prior_z + M<float>::sqrt(-2.f * M<float>::log(M<float>::u_oo(b.v[0]))) * p.width_z;
+          const Moments o1 = eval_moments_f32(row, n_pairs, H.x - mu.x, H.y - mu.y, H.z, g, cp, c0.x, c0.y, evc);
+          H.w = o1.L;
+          Mm = make_float4(o1.A1t, o1.A3t, o1.A1a, o1.A3a);
+          Q = make_float4(o1.S1t, o1.S1a, o1.A2t, o1.A2a);
+          dirty = acc = true;
+        } else {
+          H = st.H[ci];
+          Mm = st.M[ci];
+          if (a_prev) {  // lazy commit of the last shared-parameter acceptance: exactly what was judged
+            Q = st.P[ci];
+            H.w = st.Lp[ci];
+            dirty = true;
+          } else {
+            Q = st.Q[ci];
+          }
+          // model_perturb for one coordinate (src/cls_model.f90:162-190); icmp 0 -> z, 1 -> y, 2 -> x
+          const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(it), gid, PHX_STEP, 0u);
+          icmp = static_cast<int>(below(w.v[0], 3u));
+          const float gs = M<float>::gauss(w.v[1], w.v[2]);
+          const bool isz = icmp == 0;
+          const float x_old = isz ? H.z : (icmp == 1 ? H.y : H.x);
+          const float mu1 = isz ? p.prior_z : (icmp == 1 ? mu.y : mu.x);
+          const float sigma = isz ? p.width_z : p.width_xy;
+          const float x_new = x_old + gs * (isz ? p.step_z : p.step_xy);
+          const float dn = x_new - mu1, dl = x_old - mu1;
+          float lpr = -(dn * dn - dl * dl) / (2.f * sigma * sigma);
+          bool ok = true;
+          if (isz) {
+            if (x_new <= mu1)
+              ok = false;
+            else
+              lpr = lpr + M<float>::log(dn) - M<float>::log(dl);
+          }
+          const float nx = icmp == 2 ? x_new : H.x, ny = icmp == 1 ? x_new : H.y, nz = isz ? x_new : H.z;
+          const Moments o1 = eval_moments_f32(row, n_pairs, nx - mu.x, ny - mu.y, nz, g, cp, c0.x, c0.y, evc);
+          // mcmc_judge_model (src/cls_mcmc.f90:193-203)
+          const float ratio = (o1.L - H.w) * iT + lpr;
+          const float ru = M<float>::u_co(w.v[3]);
+          acc = ok && (ru > 0.f) && (M<float>::log(ru) <= ratio);
+          if (acc) {
+            H = make_float4(nx, ny, nz, o1.L);
+            Mm = make_float4(o1.A1t, o1.A3t, o1.A1a, o1.A3a);
+            Q = make_float4(o1.S1t, o1.S1a, o1.A2t, o1.A2a);
+            dirty = true;
+          }
+          if (TRACE) {
+            if (ev_ok && c_ok && trace_it) {
+              htm_step_trace t;
+              t.proposal_type = 5 + icmp;
+              t.index = 3 * (e + 1) - icmp;
+              t.prior_ok = ok ? 1 : 0;
+              t.accepted = acc ? 1 : 0;
+              t.log_likelihood = static_cast<double>(H.w);
+              trace_it[static_cast<size_t>(e) * J + c] = t;
+            }
+          }
+        }
+        // the chain's pending shared-parameter proposal, for this event: O(1)
+        const DeltaSums ds = pending_delta(pr, row, n_pairs, H.x - mu.x, H.y - mu.y, H.z, g, cp, c0.x, c0.y, Mm, Q);
+        const float dchi = (ds.dS2t - ds.dS1t * fmaf(2.f, Q.x, ds.dS1t) * evc.y) + (ds.dS2a - ds.dS1a * fmaf(2.f, Q.y, ds.dS1a) * evc.z);
+        const float dL = -0.5f * dchi;
+        if (ev_ok && c_ok) {
+          if (dirty) {
+            st.H[ci] = H;
+            st.Q[ci] = Q;
+          }
+          if (acc) st.M[ci] = Mm;
+          st.P[ci] = make_float4(Q.x + ds.dS1t, Q.y + ds.dS1a, Q.z + ds.dA2t, Q.w + ds.dA2a);
+          st.Lp[ci] = H.w + dL;
+          if (rec_chain_slot >= 0)
+            p.hypo_rec[(static_cast<size_t>(rec_slot) * p.n_cool_total + rec_chain_slot) * E + e] = H;
+          s_cur += static_cast<double>(H.w);
+          s_prop += static_cast<double>(H.w) + static_cast<double>(dL);
+          if (cold && !INIT) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              cnt_p[t] += icmp == t ? 1u : 0u;
+              cnt_a[t] += (icmp == t && acc) ? 1u : 0u;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(m.empty + buf);
+      if (warp == 0 && t_run + 2 < n_run) {
+        if (lane == 0) mbar_wait(m.empty + buf, ph);
+        __syncwarp();
+        issue(t_run + 2);
+      }
+    }
+    if (warp_ok) {
+#pragma unroll
+      for (int off = 16; off >= kQuad; off >>= 1) {
+        s_cur += __shfl_xor_sync(0xffffffffu, s_cur, off);
+        s_prop += __shfl_xor_sync(0xffffffffu, s_prop, off);
+      }
+      if (es == 0 && c_ok) {
+        part_cur[static_cast<size_t>(c) * gridDim.x + blockIdx.x] = s_cur;
+        part_prop[static_cast<size_t>(c) * gridDim.x + blockIdx.x] = s_prop;
+      }
+    }
+    grid.sync();
+    if (INIT) {  // g_L[c] = sum_e L_e (fixed order: partials in CTA order)
+      if (writer) {
+        sum_partials(d.n_tiles, part_cur, part_prop, J, cs.tot);
+        __syncthreads();
+        for (int t = threadIdx.x; t < J; t += blockDim.x) d.g_L[t] = cs.tot[t];
+      }
+      break;
+    }
+    htm_step_trace* trace_g = trace_it ? trace_it + static_cast<size_t>(E) * J : nullptr;
+    htm_swap_trace* swap_it = swap_base ? swap_base + (it - iter_first) : nullptr;
+    if (d.xch.n > 1) {
+      // event shards: CTA (0,0) adds this shard's partials, exchanges the sums with the other GPUs through peer
+      // memory and hands the totals over all events to every CTA of its grid
+      if (writer) {
+        sum_partials(d.n_tiles, part_cur, part_prop, J, cs.tot);
+        __syncthreads();
+        if (peer_allreduce(d.xch, d.xch.epoch + static_cast<uint32_t>(it - iter_first), cs.tot, 2 * J))
+          for (int t = threadIdx.x; t < 2 * J; t += blockDim.x) totals[t] = cs.tot[t];
+        __threadfence();
+      }
+      grid.sync();
+      // a peer that never answered ends the run here, on every CTA alike (only this shard's writer sets the
+      // flag, before the barrier): no decision is taken from partial sums; the host reports HTM_ERR_CUDA
+      if (*reinterpret_cast<volatile int*>(d.xch.status) != 0) break;
+      decide_core(d, cs, it, it + 1, totals, totals + J, rec_slot, trace_g, swap_it, writer, true, true);
+    } else {
+      decide_core(d, cs, it, it + 1, part_cur, part_prop, rec_slot, trace_g, swap_it, writer, false, true);
+    }
+  }
+  if (INIT) return;
+  if (warp_ok) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const uint32_t np = warp_sum<uint32_t>(cnt_p[t]), na = warp_sum<uint32_t>(cnt_a[t]);
+      if (lane == 0 && p.counts) {
+        if (np) atomicAdd(p.counts + 4 + t, static_cast<unsigned long long>(np));
+        if (na) atomicAdd(p.counts + 11 + t, static_cast<unsigned long long>(na));
+      }
+    }
+  }
+  if (writer) chain_store(d, cs, /*terms=*/false);
+}
+
+// cold slots + the proposal of the first iteration (a pure function of state and iteration number): one CTA
+__global__ void __launch_bounds__(256) gibbs_f32_prepare_kernel(const GibbsDecide d) {
+  extern __shared__ __align__(16) unsigned char s_prep_dyn[];
+  gibbs_decide_small(d, s_prep_dyn);
+}
+static cudaError_t launch_gibbs_prepare(const GibbsLaunch& a, cudaStream_t stream) {
+  const size_t sm = chain_sm_small_bytes(a.J);
+  if (sm > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t err = cudaFuncSetAttribute(gibbs_f32_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+  if (err != cudaSuccess) return err;
+  GibbsDecide d = make_decide(a);
+  d.it = 0;
+  d.it_next = a.iter_first;
+  gibbs_f32_prepare_kernel<<<1, 256, sm, stream>>>(d);
+  return cudaGetLastError();
+}
+
+// ---- host launcher -----------------------------------------------------------------------------------------
+struct F32Shape {
+  int n_warps = kCW, gy = 1, n_oct = 1;
+  long gx = 1;
+  size_t smem = 0;
+};
+template <bool TRACE, bool INIT>
+static cudaError_t f32_shape(const GibbsLaunch& a, F32Shape* s) {
+  const int quads = (a.J + kQuad - 1) / kQuad;
+  s->gy = (quads + kCW - 1) / kCW;
+  s->n_warps = (quads + s->gy - 1) / s->gy;
+  s->smem = ((f32_sweep_smem(a.S, s->n_warps * kQuad) + 15) & ~static_cast<size_t>(15)) + chain_sm_small_bytes(a.J);
+  if (s->smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t err = cudaFuncSetAttribute(gibbs_f32_kernel<TRACE, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(s->smem));
+  if (err != cudaSuccess) return err;
+  int per_sm = 0, dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_f32_kernel<TRACE, INIT>, s->n_warps * 32, s->smem);
+  if (err != cudaSuccess) return err;
+  s->n_oct = (a.E + kOct - 1) / kOct;
+  s->gx = static_cast<long>(per_sm) * n_sm / s->gy;
+  if (s->gx > s->n_oct) s->gx = s->n_oct;
+  if (s->gx > a.part_tiles) s->gx = a.part_tiles;  // [2][cur, prop][J][gx]
+  if (s->gx < 1) return cudaErrorCooperativeLaunchTooLarge;  // more chain groups than resident CTAs
+  return cudaSuccess;
+}
+
+template <bool TRACE, bool INIT>
+static cudaError_t launch_f32(const GibbsLaunch& a, cudaStream_t stream) {
+  F32Shape s;
+  cudaError_t err = f32_shape<TRACE, INIT>(a, &s);
+  if (err != cudaSuccess) return err;
+  GibbsParams<float> pp = make_gibbs_params<float>(a);
+  GibbsDecide dp = make_decide(a);
+  pp.n_tiles = dp.n_tiles = static_cast<int>(s.gx);
+  if (a.out_partials) *a.out_partials = static_cast<int>(s.gx);
+  dp.xch.epoch = a.xch_epoch0;  // exchange number of iter_first; the kernel counts on from there
+  F32State st;
+  st.H = static_cast<float4*>(a.sH);
+  st.M = static_cast<float4*>(a.sM);
+  st.Q = static_cast<float4*>(a.sQ);
+  st.P = static_cast<float4*>(a.sP);
+  st.Lp = static_cast<float*>(a.hLp);
+  int iter_first = a.iter_first, iter_last = a.iter_last, rec_origin = a.rec_origin, rec_cap = a.rec_cap, n_oct = s.n_oct;
+  htm_step_trace* tr = a.trace;
+  htm_swap_trace* sw = a.swaps;
+  double* part = a.part_cur;
+  double* totals = a.totals;
+  uint64_t seed = a.seed;
+  void* args[] = {&pp, &dp, &st, &iter_first, &iter_last, &rec_origin, &rec_cap, &tr, &sw, &part, &n_oct, &totals, &seed};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gibbs_f32_kernel<TRACE, INIT>),
+                                     dim3(static_cast<unsigned>(s.gx), s.gy), dim3(s.n_warps * 32), args, s.smem, stream);
+}
+
+// float32 mode C run: prepare (cold slots + first proposal) + ONE cooperative launch for all iterations
+cudaError_t launch_gibbs_f32(const GibbsLaunch& a, cudaStream_t stream, int* n_launches) {
+  if (a.comm && a.xch.n <= 1) return cudaErrorNotSupported;  // float32 event shards exchange through peer memory only
+  cudaError_t err = launch_gibbs_prepare(a, stream);
+  if (err != cudaSuccess) return err;
+  err = (a.trace || a.swaps) ? launch_f32<true, false>(a, stream) : launch_f32<false, false>(a, stream);
+  if (err != cudaSuccess) return err;
+  if (n_launches) *n_launches = 2;
+  return cudaGetLastError();
+}
+
+// hypocentres + state of every (chain, event) at the initial shared parameters, and g_L
+cudaError_t launch_gibbs_f32_init(const GibbsLaunch& a, cudaStream_t stream) {
+  GibbsLaunch b = a;
+  b.iter_first = b.iter_last = 0;
+  b.trace = nullptr;
+  b.swaps = nullptr;
+  b.xch = PeerExchange();
+  return launch_f32<false, true>(b, stream);
+}
+
+}  // namespace htm

@@ -116,7 +116,10 @@ inline size_t peer_exchange_bytes(int n, int J) {
 struct GibbsLaunch {
   int precision = 32;
   Tables tab;
-  void *hx = nullptr, *hy = nullptr, *hz = nullptr, *hLe = nullptr, *hLp = nullptr;  // real [J][E]
+  void *hx = nullptr, *hy = nullptr, *hz = nullptr, *hLe = nullptr, *hLp = nullptr;  // real [J][E] (float32: hLp only)
+  // float32 state (htm_gibbs_f32.cu), float4 [J][E] each: {x,y,z,L_e}, moments {A1t,A3t,A1a,A3a},
+  // sums {S1t,S1a,A2t,A2a}, and the sums under the chain's pending shared-parameter proposal
+  void *sH = nullptr, *sM = nullptr, *sQ = nullptr, *sP = nullptr;
   double *g_vs = nullptr, *g_qs = nullptr, *g_tc = nullptr, *g_ac = nullptr, *g_T = nullptr, *g_L = nullptr;
   int *prop_which = nullptr, *prop_idx = nullptr, *a_prev = nullptr, *slot_of = nullptr;
   double *prop_xnew = nullptr, *prop_lpr = nullptr;
@@ -147,6 +150,7 @@ struct GibbsLaunch {
   int rec_origin = 0, rec_cap = 0;
   htm_step_trace* trace = nullptr;  // debug: [n_it][E+1][J]
   htm_swap_trace* swaps = nullptr;  // debug: [n_it]
+  int* out_partials = nullptr;      // float32: receives the number of partial sums per chain of this launch
 };
 cudaError_t launch_gibbs(const GibbsLaunch& a, cudaStream_t stream, int* n_launches);
 // float32: build the expanded rows from the raw tables (once per table upload)

@@ -285,6 +285,22 @@ module htm_b200_binding
        integer(c_int32_t) :: rc
      end function htm_gather_samples
 
+     ! validation entry points of the float32 blocked-Gibbs kernel (per joint chain of this shard)
+     function htm_gibbs_pending(h, which, idx, x_new) bind(c, name="htm_gibbs_pending") result(rc)
+       import
+       type(c_ptr), value :: h
+       integer(c_int32_t), intent(out) :: which(*), idx(*)
+       real(c_double), intent(out) :: x_new(*)
+       integer(c_int32_t) :: rc
+     end function htm_gibbs_pending
+
+     function htm_gibbs_last_sums(h, cur, prop) bind(c, name="htm_gibbs_last_sums") result(rc)
+       import
+       type(c_ptr), value :: h
+       real(c_double), intent(out) :: cur(*), prop(*)
+       integer(c_int32_t) :: rc
+     end function htm_gibbs_last_sums
+
      ! handles of all shards, 64 bytes each, in shard order (MPI_Allgather of the exported one)
      function htm_comm_p2p_export(h, handle) bind(c, name="htm_comm_p2p_export") result(rc)
        import

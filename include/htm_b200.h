@@ -226,6 +226,16 @@ int32_t htm_run(htm_handle h, int32_t iter_first, int32_t iter_last);
 int32_t htm_run_traced(htm_handle h, int32_t iter_first, int32_t iter_last,
                        htm_step_trace* trace, htm_swap_trace* swaps);
 
+/* Validation entry points of the float32 blocked-Gibbs kernel (no counterpart in the reference, like
+ * htm_run_traced).  htm_gibbs_pending: the shared-parameter proposal (mcmc_propose_model's vs / t_corr / qs /
+ * a_corr branches, src/cls_mcmc.f90:139-157) that the NEXT iteration will judge, per joint chain of this shard:
+ * which = 1 vs, 2 t_corr, 3 qs, 4 a_corr; idx = 0-based station; x_new.  htm_gibbs_last_sums: per joint chain,
+ * the sums over this shard's events of the per-event log-likelihoods the LAST iteration judged, current and
+ * under its proposal (what forward%calc_log_likelihood returns for the two models, src/cls_forward.f90:268-303;
+ * the kernel forms the difference from per-event moments, see csrc/htm_gibbs_f32.cu). */
+int32_t htm_gibbs_pending(htm_handle h, int32_t* which, int32_t* idx, double* x_new);
+int32_t htm_gibbs_last_sums(htm_handle h, double* cur, double* prop);
+
 /* Wait for queued work; returns the first asynchronous error if any. */
 int32_t htm_synchronize(htm_handle h);
 

@@ -548,72 +548,118 @@ def test_blocked_gibbs_float64_step_exact(gibbs_path, E, S, R, K, solve):
     assert rel(fin["log_likelihood"], fo["log_likelihood"]) < 1e-9
 
 
-def test_blocked_gibbs_persistent_and_per_iteration_paths_are_bit_identical(monkeypatch):
-    syn = H.Synthetic(300, 20, 8)
-    cfg = H.default_config(n_sta=20, n_events=300, n_procs=3, n_chains=4, n_iter=120, n_burn=20, n_interval=10,
-                           mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=16)
-    res = []
-    for persist in (0, 1):
-        monkeypatch.setenv("HTM_GIBBS_PERSIST", str(persist))
-        with H.HypoTremorB200(cfg) as g:
-            g.load(syn)
-            g.init_chains()
-            g.run(1, 70)
-            g.run(71, 120)
-            _, nl, _ = g.last_run_stats()
-            assert nl == (2 if persist else 51)
-            res.append(([g.get_chain_state(r, k) for r in range(3) for k in range(4)], g.get_counts(),
-                        [g.fetch_samples(r) for r in range(3)], [g.fetch_likelihood(r) for r in range(3)]))
-    for a, b in zip(res[0][0], res[1][0]):
-        assert np.array_equal(a["hypo"], b["hypo"]) and a["vs"] == b["vs"] and a["qs"] == b["qs"]
-        assert np.array_equal(a["t_corr"], b["t_corr"]) and a["temp"] == b["temp"] and a["log_likelihood"] == b["log_likelihood"]
-    assert np.array_equal(res[0][1][0], res[1][1][0]) and np.array_equal(res[0][1][1], res[1][1][1])
-    for a, b in zip(res[0][2], res[1][2]):
-        assert np.array_equal(a["iter"], b["iter"]) and np.array_equal(a["hypo"], b["hypo"]) and np.array_equal(a["vs"], b["vs"])
-    for a, b in zip(res[0][3], res[1][3]):
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-
-
-@pytest.mark.parametrize("E,S,R,K", [(300, 20, 3, 4), (77, 13, 5, 5), (33, 50, 1, 3), (200, 8, 9, 8), (10, 1, 2, 2)])
-def test_blocked_gibbs_sweep_layouts_are_bit_identical(monkeypatch, E, S, R, K):
-    """HTM_GIBBS_SWEEP = layout of the float32 sweep: chain (warp = chain, lane = event) or octet (warp = 8 events
-    x 4 chains, the CTA walks event octets through a TMA ring); HTM_GIBBS_PERSIST = one launch per iteration (0)
-    or one cooperative launch per run (1).  All four kernels must agree bit for bit."""
+def test_blocked_gibbs_float32_first_iteration_follows_the_float64_kernel():
+    """The float32 kernel (htm_gibbs_f32.cu: one pass per event + moment-based shared-parameter deltas) draws the same
+    Philox words as the float64 kernels, so until rounding flips a decision the two runs coincide: at iteration 1
+    every per-event log-likelihood and every chain's summed log-likelihood after the shared-parameter step must
+    agree to float32 accuracy, and (almost) every accept flag must be the same."""
+    E, S, R, K = 400, 20, 3, 4
     syn = H.Synthetic(E, S, 8)
-    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_iter=60, n_burn=10, n_interval=10,
-                           mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=16)
-    res = []
-    for persist, layout in (("0", "chain"), ("0", "octet"), ("1", "octet"), ("1", "chain")):
-        monkeypatch.setenv("HTM_GIBBS_PERSIST", persist)
-        monkeypatch.setenv("HTM_GIBBS_SWEEP", layout)
-        with H.HypoTremorB200(cfg) as g:
+    base = dict(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_iter=10, n_burn=0, n_interval=5,
+                mode=H.MODE_BLOCKED_GIBBS, max_samples=4)
+    tr = {}
+    for prec in (64, 32):
+        with H.HypoTremorB200(H.default_config(precision=prec, **base)) as g:
             g.load(syn)
             g.init_chains()
-            tr, sw = g.run_traced(1, 25)
-            g.run(26, 47)
-            g.run(48, 60)
-            _, nl, _ = g.last_run_stats()
-            assert nl == (2 if persist == "1" else 14)
-            res.append(([g.get_chain_state(r, k) for r in range(R) for k in range(K)], g.get_counts(),
-                        [g.fetch_samples(r) for r in range(R)], [g.fetch_likelihood(r) for r in range(R)], tr, sw))
-    for other in res[1:]:
-        for a, b in zip(res[0][0], other[0]):
-            assert np.array_equal(a["hypo"], b["hypo"]) and a["vs"] == b["vs"] and a["qs"] == b["qs"]
-            assert np.array_equal(a["t_corr"], b["t_corr"]) and np.array_equal(a["a_corr"], b["a_corr"])
-            assert a["temp"] == b["temp"] and a["log_likelihood"] == b["log_likelihood"]
-        assert np.array_equal(res[0][1][0], other[1][0]) and np.array_equal(res[0][1][1], other[1][1])
-        for a, b in zip(res[0][2], other[2]):
-            assert np.array_equal(a["iter"], b["iter"]) and np.array_equal(a["hypo"], b["hypo"]) and np.array_equal(a["vs"], b["vs"])
-        for a, b in zip(res[0][3], other[3]):
-            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
-        for f in FLAGS:
-            assert np.array_equal(res[0][4][f], other[4][f]), f
-        assert np.array_equal(res[0][4]["log_likelihood"], other[4]["log_likelihood"])
-        assert np.array_equal(res[0][5], other[5])
+            tr[prec], _ = g.run_traced(1, 1)
+    a, b = tr[64][0], tr[32][0]
+    assert np.array_equal(a["proposal_type"], b["proposal_type"]) and np.array_equal(a["index"], b["index"])
+    assert (a["accepted"] != b["accepted"]).mean() < 2e-3
+    same = a["accepted"][:-1] == b["accepted"][:-1]
+    dL = np.abs(a["log_likelihood"][:-1] - b["log_likelihood"][:-1])[same]
+    assert dL.max() < 2e-3 * max(1.0, S / 20), dL.max()                       # per event
+    tot = np.abs(a["log_likelihood"][-1] - b["log_likelihood"][-1])            # per chain, after the shared step
+    agree = a["accepted"][-1] == b["accepted"][-1]
+    assert agree.mean() > 0.8
+    # (a flipped hypocentre decision somewhere moves the whole sum, so only a loose bound holds per chain)
+    assert np.median(tot[agree] / np.abs(a["log_likelihood"][-1][agree])) < 1e-5
+
+
+def test_blocked_gibbs_float32_shared_parameter_ratio_at_20000_events():
+    """The Metropolis ratio of a shared parameter is a sum over ALL events.  The float32 kernel accumulates it in
+    float64 from per-event DIFFERENCES (moment form, htm_gibbs_f32.cu); here the difference it judged is redone in
+    float64 (htm_loglik on the state and on the state with the proposal applied) for real pending proposals of
+    every kind at 20 000 events x 50 stations: |error| << 1 log-likelihood unit, however large the sums are."""
+    E, S, R, K = 20000, 50, 2, 4
+    J = R * K
+    syn = H.Synthetic(E, S, 77)
+    # small steps so that proposals of every kind stay in the range where they are sometimes accepted
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=100, n_burn=0, n_interval=50,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=32, step_size_vs=2e-4, step_size_qs=0.5,
+                           step_size_t_corr=2e-3, step_size_a_corr=1e-3)
+    worst, kinds = 0.0, set()
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        g.run(1, 30)
+        it = 31
+        for _ in range(6):
+            before = [g.get_chain_state(c // K, c % K) for c in range(J)]
+            which, idx, xn = g.gibbs_pending()
+            g.run(it, it)
+            cur32, prop32 = g.gibbs_last_sums()
+            after = [g.get_chain_state(c // K, c % K) for c in range(J)]
+            hypo = np.stack([s["hypo"] for s in after])           # hypocentres the shared step was judged on
+            tc = np.stack([s["t_corr"] for s in before])
+            ac = np.stack([s["a_corr"] for s in before])
+            vs = np.array([s["vs"] for s in before])
+            qs = np.array([s["qs"] for s in before])
+            tcp, acp, vsp, qsp = tc.copy(), ac.copy(), vs.copy(), qs.copy()
+            for c in range(J):
+                kinds.add(int(which[c]))
+                if which[c] == 1:
+                    vsp[c] = xn[c]
+                elif which[c] == 2:
+                    tcp[c, idx[c]] = xn[c]
+                elif which[c] == 3:
+                    qsp[c] = xn[c]
+                elif which[c] == 4:
+                    acp[c, idx[c]] = xn[c]
+            L_cur = g.loglik(hypo, tc, ac, vs, qs)
+            L_prop = g.loglik(hypo, tcp, acp, vsp, qsp)
+            err = np.abs((prop32 - cur32) - (L_prop - L_cur))
+            worst = max(worst, float(err.max()))
+            # the carried sums themselves are float32 accurate only: that is why differences are formed per event
+            assert np.all(np.abs(cur32 - L_cur) <= 2e-5 * np.abs(L_cur))
+            it += 1
+    assert kinds >= {1, 2, 3, 4} or len(kinds) >= 3, kinds
+    assert worst < 1e-2, worst
+
+
+def test_blocked_gibbs_float32_many_joint_chains():
+    """600 joint chains x 40 stations: the chain-level station terms (J x S x 2 doubles = 384 KB) no longer have to
+    fit a CTA's shared memory -- the float32 kernel keeps them in global memory.  Size-independent invariants."""
+    E, S, R, K, n_it = 500, 40, 100, 6, 40
+    syn = H.Synthetic(E, S, 5)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=n_it, n_burn=0, n_interval=10,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=8)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        temps0 = sorted(g.get_chain_state(r, k)["temp"] for r in range(0, R, 7) for k in range(K))
+        g.run(1, n_it)
+        p, a = g.get_counts()
+        states = [g.get_chain_state(r, k) for r in range(0, R, 17) for k in range(K)]
+        L64 = g.loglik(np.stack([s["hypo"] for s in states]), np.stack([s["t_corr"] for s in states]),
+                       np.stack([s["a_corr"] for s in states]), [s["vs"] for s in states], [s["qs"] for s in states])
+        smp = [g.fetch_samples(r) for r in range(R)]
+    assert len(temps0) == len(range(0, R, 7)) * K
+    assert p[4:7].sum() == n_it * E * R and p[:4].sum() == n_it * R and (a <= p).all()
+    assert a[:4].sum() > 0 and a[4:7].sum() > 0
+    for s, L in zip(states, L64):
+        assert abs(s["log_likelihood"] - L) <= 2e-5 * abs(L), (s["log_likelihood"], L)
+    assert sum(len(x["iter"]) for x in smp) == 4 * R      # iterations 1, 11, 21, 31: one cold chain per rank each
+    with pytest.raises(H.HtmError) as ei:                  # the float64 kernels keep that state in shared memory
+        with H.HypoTremorB200(H.copy_config(cfg, precision=64)) as g64:
+            g64.load(syn)
+            g64.init_chains()
+            g64.run(1, 2)
+    assert ei.value.code == H.config.HTM_ERR_UNSUPPORTED
 
 
 def test_blocked_gibbs_full_size_properties():
-    """20 000 events x 50 stations x 20 joint chains (the persistent octet sweep): size-independent invariants."""
+    """20 000 events x 50 stations x 20 joint chains (float32 kernel, one cooperative launch): size-independent invariants."""
     E, S, R, K, n_it, n_int = 20000, 50, 4, 5, 120, 20
     syn = H.Synthetic(E, S, 77)
     cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=2, n_iter=n_it, n_burn=40, n_interval=n_int,
@@ -854,7 +900,9 @@ def test_event_sharded_gibbs_on_two_gpus(exchange):
                        cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("matches the unsharded oracle: True") == 2, r.stdout[-2000:]
-    # float32 (the persistent octet sweep with the exchange between two grid barriers) against the unsharded run
+    if exchange == "nccl":
+        return  # float32 event shards exchange through peer memory only
+    # float32 (persistent kernel with the exchange between two grid barriers) against the unsharded run
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), "tests/checks/comm_check_gibbs_f32.py"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=300)
