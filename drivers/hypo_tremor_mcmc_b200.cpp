@@ -9,6 +9,7 @@
 // parameter file's station_file, selected_win.dat, opt_data.NNNNNN.dat.  Outputs: hypo.RR.out,
 // t_corr.RR.out, vs.RR.out, a_corr.RR.out, qs.RR.out, likelihoodRR.out per virtual rank RR, and
 // proposal_count.txt.  n_procs of the parameter file = number of virtual ranks (no MPI).
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -28,7 +29,7 @@ static void check(htm_handle h, int32_t rc, const char* where) {
 
 int main(int argc, char** argv) {
   std::string param_file;
-  int precision = 32, chunk = 64;
+  int precision = 32, chunk = 0;  // 0 = choose from the record size
   unsigned long long seed = 20231001ull;
   bool big_endian = true, dry = false;
   unsigned loader_threads = 0;  // 0 = all host cores
@@ -100,6 +101,12 @@ int main(int argc, char** argv) {
     const bool any_solve = cfg.solve_vs || cfg.solve_t_corr || cfg.solve_qs || cfg.solve_a_corr;
     cfg.mode = any_solve ? HTM_MODE_BLOCKED_GIBBS : HTM_MODE_FACTORISED;
     cfg.precision = precision;
+    if (chunk <= 0) {
+      // records drained per htm_run: 64, fewer when one hypo record (3 E doubles per cold chain) is large --
+      // the host buffers below stay within about 256 MB
+      const double per_rec = 24.0 * n_events * cfg.n_cool * cfg.n_procs;
+      chunk = static_cast<int>(std::max(1.0, std::min(64.0, 2.56e8 / per_rec - 1.0)));
+    }
     cfg.max_samples = chunk + 1;
 
     if (dry) {  // parse-only: what the driver understood, as JSON (used by the CPU tests)

@@ -720,7 +720,14 @@ int32_t htm_init_chains(htm_handle h) {
   if (rc != HTM_OK) return rc;
   if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS) {
     gibbs_launch_of(h);
-    HTM_CK(h, launch_gibbs_init(h->gl, h->cfg.temp_high, h->cfg.ladder, h->cfg.n_cool, h->stream));
+    {
+      const cudaError_t ei = launch_gibbs_init(h->gl, h->cfg.temp_high, h->cfg.ladder, h->cfg.n_cool, h->stream);
+      if (ei == cudaErrorInvalidConfiguration || ei == cudaErrorCooperativeLaunchTooLarge)
+        return fail(h, HTM_ERR_UNSUPPORTED,
+                    "blocked-Gibbs mode (float32) stages event rows and chain-level state in shared memory: n_sta is "
+                    "too large (limit about 180) or there are more than ~9000 joint chains per GPU");
+      HTM_CK(h, ei);
+    }
     HTM_CK(h, cudaMemsetAsync(h->gl.a_prev, 0, h->C * sizeof(int), h->stream));
     HTM_CK(h, cudaMemsetAsync(h->d_counts, 0, 14 * sizeof(unsigned long long), h->stream));
     h->rec_pending = 0;

@@ -33,7 +33,8 @@ __global__ void build_tables_kernel(const TableBuild b) {
   const double* t_stdv = b.obs_in + n;
   const double* a_obs = b.obs_in + 2 * n;
   const double* a_stdv = b.obs_in + 3 * n;
-  real4* obs = static_cast<real4*>(b.obs4) + static_cast<size_t>(e) * b.S;
+  // the table with the fixed station terms folded in exists in the factorised mode only
+  real4* obs = b.obs4 ? static_cast<real4*>(b.obs4) + static_cast<size_t>(e) * b.S : nullptr;
   real4* raw = static_cast<real4*>(b.obs4_raw) + static_cast<size_t>(e) * b.S;
   double Ce = 0.0, swt = 0.0, swa = 0.0;
   for (int j = 0; j < b.S; ++j) {
@@ -67,7 +68,7 @@ __global__ void build_tables_kernel(const TableBuild b) {
     o.z = static_cast<real>(a_obs[k] + b.g_tc_ac[b.S + j]);
     o.w = r.w;
     raw[j] = r;
-    obs[j] = o;
+    if (obs) obs[j] = o;
   }
   real4 c;
   c.x = static_cast<real>(Ce);

@@ -567,8 +567,9 @@ def test_blocked_gibbs_float32_first_iteration_follows_the_float64_kernel():
     assert np.array_equal(a["proposal_type"], b["proposal_type"]) and np.array_equal(a["index"], b["index"])
     assert (a["accepted"] != b["accepted"]).mean() < 2e-3
     same = a["accepted"][:-1] == b["accepted"][:-1]
-    dL = np.abs(a["log_likelihood"][:-1] - b["log_likelihood"][:-1])[same]
-    assert dL.max() < 2e-3 * max(1.0, S / 20), dL.max()                       # per event
+    dL = (np.abs(a["log_likelihood"][:-1] - b["log_likelihood"][:-1]) /
+          (2e-3 + 1e-5 * np.abs(a["log_likelihood"][:-1])))[same]               # per event: abs + float32 relative
+    assert dL.max() < 1.0, dL.max()
     tot = np.abs(a["log_likelihood"][-1] - b["log_likelihood"][-1])            # per chain, after the shared step
     agree = a["accepted"][-1] == b["accepted"][-1]
     assert agree.mean() > 0.8
@@ -589,8 +590,11 @@ def test_blocked_gibbs_float32_shared_parameter_ratio_at_20000_events():
                            mode=H.MODE_BLOCKED_GIBBS, precision=32, step_size_vs=2e-4, step_size_qs=0.5,
                            step_size_t_corr=2e-3, step_size_a_corr=1e-3)
     worst, kinds = 0.0, set()
-    with H.HypoTremorB200(cfg) as g:
+    # float64 evaluator of the same data (htm_loglik computes in the handle's precision)
+    cfg64 = H.default_config(n_sta=S, n_events=E, mode=H.MODE_FACTORISED, precision=64, **NOSOLVE)
+    with H.HypoTremorB200(cfg) as g, H.HypoTremorB200(cfg64) as g64:
         g.load(syn)
+        g64.load(syn)
         g.init_chains()
         g.run(1, 30)
         it = 31
@@ -616,8 +620,8 @@ def test_blocked_gibbs_float32_shared_parameter_ratio_at_20000_events():
                     qsp[c] = xn[c]
                 elif which[c] == 4:
                     acp[c, idx[c]] = xn[c]
-            L_cur = g.loglik(hypo, tc, ac, vs, qs)
-            L_prop = g.loglik(hypo, tcp, acp, vsp, qsp)
+            L_cur = g64.loglik(hypo, tc, ac, vs, qs)
+            L_prop = g64.loglik(hypo, tcp, acp, vsp, qsp)
             err = np.abs((prop32 - cur32) - (L_prop - L_cur))
             worst = max(worst, float(err.max()))
             # the carried sums themselves are float32 accurate only: that is why differences are formed per event
@@ -817,8 +821,8 @@ def test_argument_and_state_errors():
     wide = H.default_config(n_sta=400, n_events=2, mode=H.MODE_BLOCKED_GIBBS, precision=32, n_procs=1, n_chains=2)
     with H.HypoTremorB200(wide) as g:                    # blocked-Gibbs stages 32 rows per CTA: n_sta limit
         g.load(H.Synthetic(2, 400, 1))
-        g.init_chains()
-        with pytest.raises(H.HtmError) as ei:
+        with pytest.raises(H.HtmError) as ei:            # (float32: the set-up pass uses the same kernel)
+            g.init_chains()
             g.run(1, 2)
         assert ei.value.code == H.config.HTM_ERR_UNSUPPORTED
 
