@@ -24,6 +24,7 @@ EXPORTS = [
     "htm_discard_samples", "htm_get_counts", "htm_get_histograms", "htm_device_ptr",
     "htm_last_run_stats", "htm_measure_fp32_peak", "htm_comm_unique_id", "htm_comm_init", "htm_gather",
     "htm_comm_p2p_export", "htm_comm_p2p_import", "htm_gather_samples", "htm_gibbs_pending", "htm_gibbs_last_sums",
+    "htm_posterior_quantiles",
 ]
 
 
@@ -85,6 +86,7 @@ def load_library():
         "htm_comm_init": [vp, ctypes.c_char_p],
         "htm_gather": [vp, ctypes.POINTER(ctypes.c_uint32), lp, lp],
         "htm_gather_samples": [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), dp, dp, dp, dp, dp],
+        "htm_posterior_quantiles": [vp, ip, dp, dp, dp, dp, dp],
         "htm_gibbs_pending": [vp, ip, ip, dp],
         "htm_gibbs_last_sums": [vp, dp, dp],
         "htm_comm_p2p_export": [vp, ctypes.c_char_p],
@@ -300,6 +302,17 @@ class HypoTremorB200:
                                                it.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                                                _dptr(lik)))
         return it[:n.value], lik[:n.value]
+
+    def posterior_quantiles(self):
+        """dict of {median, 2.5 %, 97.5 %} per marginal from the device-side store (cfg.summary = 1):
+        hypo [3 E, 3], vs [3], qs [3], t_corr [S, 3], a_corr [S, 3], n."""
+        E, S = self.n_events, self.n_sta
+        n = ctypes.c_int32()
+        hq, vq, qq = np.empty((3 * E, 3)), np.empty(3), np.empty(3)
+        tq, aq = np.empty((S, 3)), np.empty((S, 3))
+        self._ck(self.lib.htm_posterior_quantiles(self._h, ctypes.byref(n), _dptr(hq), _dptr(vq), _dptr(qq), _dptr(tq),
+                                                  _dptr(aq)))
+        return dict(n=n.value, hypo=hq, vs=vq, qs=qq, t_corr=tq, a_corr=aq)
 
     def discard_samples(self):
         self._ck(self.lib.htm_discard_samples(self._h))

@@ -67,7 +67,7 @@ class HtmConfig(ctypes.Structure):
         ("max_samples", ctypes.c_int32),
         ("lane_slots", ctypes.c_int32),
         ("gibbs_shard_events", ctypes.c_int32),
-        ("reserved1", ctypes.c_int32),
+        ("summary", ctypes.c_int32),
     ]
 
 

@@ -80,6 +80,11 @@ struct htm_handle_s {
   bool xch_on = false;
   uint32_t xch_epoch = 1;                  // number of the next exchange; advances identically on every shard
   int* d_xch_status = nullptr;
+  // device-side posterior store (cfg.summary): hypocentre marginals [3E][store_cap] in the handle's precision,
+  // shared-parameter marginals [2 + 2S][store_cap] float64 (blocked-Gibbs mode), filled by every htm_run
+  void* d_store_hypo = nullptr;
+  double* d_store_shared = nullptr;
+  size_t store_cap = 0, store_n = 0;
   int last_partials = 0, last_parity = 0;  // float32 mode C: layout of the partial sums of the last launch
   // stats
   bool timed = false;
@@ -201,7 +206,7 @@ int32_t ensure_tables(htm_handle h) {
   if (rc != HTM_OK) return rc;
   if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS && h->cfg.precision == HTM_PRECISION_F32) {
     // expanded station-pair rows for the float32 joint-chain sweep (layout: htm_forward.cuh)
-    const int xrow = 2 + 4 * (h->S / 2);
+    const int xrow = 4 + 4 * (h->S / 2);  // htm_gibbs_f32.cu: f32_xrow
     HTM_CK(h, launch_expand_obs(tables_of(h), h->E, h->S, h->d_obsx, h->stream));
     h->gl.obsx = h->d_obsx;
     h->gl.xrow = xrow;
@@ -257,6 +262,8 @@ FactLaunch fact_launch_of(htm_handle h) {
   return a;
 }
 
+bool record_ids(int first, int last, int n_interval, int* m_lo, int* m_hi);
+
 int32_t alloc_state(htm_handle h) {
   const size_t nB = static_cast<size_t>(h->E) * h->R * h->K;
   {  // input staging + device tables (sizes are fixed by the configuration)
@@ -272,7 +279,7 @@ int32_t alloc_state(htm_handle h) {
     HTM_CK(h, cudaMalloc(&h->d_prior_xy, h->E * 2 * h->rs));
     if (h->cfg.mode == HTM_MODE_REPLAY) HTM_CK(h, cudaMalloc(&h->d_prior_xy64, h->E * 2 * sizeof(double)));
     if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS && h->cfg.precision == HTM_PRECISION_F32)
-      HTM_CK(h, cudaMalloc(&h->d_obsx, static_cast<size_t>(h->E) * (2 + 4 * (h->S / 2)) * 16));
+      HTM_CK(h, cudaMalloc(&h->d_obsx, static_cast<size_t>(h->E) * (4 + 4 * (h->S / 2)) * 16));
   }
   if (h->cfg.mode == HTM_MODE_FACTORISED) {
     for (void** p : {&h->d_x, &h->d_y, &h->d_z, &h->d_L, &h->d_T}) {
@@ -378,6 +385,19 @@ int32_t alloc_state(htm_handle h) {
     h->cur_samp.assign(h->R, 0);
     h->cur_lik.assign(h->R, 0);
   }
+  if (h->cfg.summary) {
+    // recorded iterations after the burn-in: it = m n_interval + 1 with n_burn < it <= n_iter
+    int m_lo = 0, m_hi = -1;
+    long n_rec = 0;
+    if (record_ids(h->cfg.n_burn + 1, h->cfg.n_iter, h->cfg.n_interval, &m_lo, &m_hi)) n_rec = m_hi - m_lo + 1;
+    h->store_cap = static_cast<size_t>(n_rec > 0 ? n_rec : 1) * h->R * h->cfg.n_cool;
+    const size_t bytes = static_cast<size_t>(3) * h->E * h->store_cap * h->rs;
+    if (bytes > (static_cast<size_t>(96) << 30))
+      return fail(h, HTM_ERR_UNSUPPORTED, "summary store would exceed 96 GB: thin more (n_interval) or summarise from the files");
+    HTM_CK(h, cudaMalloc(&h->d_store_hypo, bytes));
+    if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS)
+      HTM_CK(h, cudaMalloc(&h->d_store_shared, static_cast<size_t>(2 + 2 * h->S) * h->store_cap * sizeof(double)));
+  }
   return HTM_OK;
 }
 
@@ -475,6 +495,27 @@ int32_t queue_sample_copy(htm_handle h, int first, int end) {
   return HTM_OK;
 }
 
+// cfg.summary: the post-burn-in records among ring slots [first, end) (a suffix: slots are in iteration order) go
+// into the device-side store, behind the kernel that wrote them, on the same stream
+int32_t append_to_store(htm_handle h, int first, int end, int origin) {
+  if (!h->cfg.summary || end <= first) return HTM_OK;
+  int s0 = first;
+  while (s0 < end && (origin + s0) * h->cfg.n_interval + 1 <= h->cfg.n_burn) ++s0;
+  const int per_slot = h->cfg.mode == HTM_MODE_BLOCKED_GIBBS ? h->n_cold_total : h->R * h->cfg.n_cool;
+  const int n_new = (end - s0) * per_slot;
+  if (n_new <= 0) return HTM_OK;
+  if (h->store_n + n_new > h->store_cap)
+    return fail(h, HTM_ERR_STATE, "summary store full: more post-burn-in records than n_iter / n_burn / n_interval announce");
+  const void* ring = h->cfg.mode == HTM_MODE_BLOCKED_GIBBS ? h->gl.hypo_rec : h->d_samples;
+  HTM_CK(h, launch_store_append_hypo(h->cfg.precision, ring, s0 * per_slot, n_new, h->E, h->d_store_hypo, h->store_cap,
+                                     h->store_n, h->stream));
+  if (h->cfg.mode == HTM_MODE_BLOCKED_GIBBS)
+    HTM_CK(h, launch_store_append_shared(h->gl.rec_vs, h->gl.rec_qs, h->gl.rec_tc, h->gl.rec_ac, s0 * per_slot, n_new, h->S,
+                                         h->d_store_shared, h->store_cap, h->store_n, h->stream));
+  h->store_n += n_new;
+  return HTM_OK;
+}
+
 // the pending records are in the pinned mirror once the last queued copy has completed
 int32_t pull_samples(htm_handle h) {
   if (h->host_samples_valid) return HTM_OK;
@@ -561,6 +602,8 @@ int32_t htm_create(htm_handle* out, const htm_config* cfg) {
   if (cfg->mode != HTM_MODE_REPLAY && cfg->mode != HTM_MODE_FACTORISED && cfg->mode != HTM_MODE_BLOCKED_GIBBS)
     return fail(nullptr, HTM_ERR_ARG, "unknown mode");
   if (cfg->hist_bins < 0 || cfg->max_samples < 0) return fail(nullptr, HTM_ERR_ARG, "negative hist_bins/max_samples");
+  if (cfg->summary && (cfg->max_samples < 1 || cfg->mode == HTM_MODE_REPLAY))
+    return fail(nullptr, HTM_ERR_ARG, "summary = 1 needs max_samples > 0 (the store is fed from the sample ring) and mode B or C");
   if (cfg->mode == HTM_MODE_BLOCKED_GIBBS && !cfg->gibbs_shard_events && cfg->shard_count > cfg->n_procs)
     return fail(nullptr, HTM_ERR_ARG, "blocked-Gibbs mode shards the virtual ranks: shard_count must be <= n_procs");
   if (cfg->gibbs_shard_events && cfg->mode != HTM_MODE_BLOCKED_GIBBS)
@@ -635,6 +678,8 @@ int32_t htm_destroy(htm_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->cstream) cudaStreamSynchronize(h->cstream);
   free_dev(h->d_in);
+  free_dev(h->d_store_hypo);
+  free_dev(h->d_store_shared);
   host_free(h->pin_in, h->pin_in_pinned);
   host_free(h->pin_samples, h->pin_samples_pinned);
   for (cudaEvent_t ev : {h->ev_in, h->ev_run, h->ev_copy})
@@ -731,10 +776,12 @@ int32_t htm_init_chains(htm_handle h) {
     HTM_CK(h, cudaMemsetAsync(h->gl.a_prev, 0, h->C * sizeof(int), h->stream));
     HTM_CK(h, cudaMemsetAsync(h->d_counts, 0, 14 * sizeof(unsigned long long), h->stream));
     h->rec_pending = 0;
+    h->store_n = 0;
     h->host_samples_valid = false;
     h->chains_ready = true;
     return HTM_OK;
   }
+  h->store_n = 0;
   FactLaunch a = fact_launch_of(h);
   HTM_CK(h, launch_factorised_init(a, h->cfg.temp_high, h->cfg.ladder, h->stream));
   HTM_CK(h, cudaMemsetAsync(h->d_counts, 0, 14 * sizeof(unsigned long long), h->stream));
@@ -974,7 +1021,8 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
     HTM_CK(h, cudaEventRecord(h->ev1, h->stream));
     commit();
     if (have_ring && recs) {
-      const int32_t rcq = queue_sample_copy(h, copy_first, new_pending);
+      int32_t rcq = append_to_store(h, copy_first, new_pending, new_origin);
+      if (rcq == HTM_OK) rcq = queue_sample_copy(h, copy_first, new_pending);
       if (rcq != HTM_OK) return rcq;
     }
     if (h->gl.xch.n > 1) h->xch_epoch += static_cast<uint32_t>(iter_last - iter_first + 1);
@@ -999,7 +1047,8 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
   HTM_CK(h, cudaEventRecord(h->ev1, h->stream));
   commit();
   if (have_ring && recs) {
-    const int32_t rcq = queue_sample_copy(h, copy_first, new_pending);
+    int32_t rcq = append_to_store(h, copy_first, new_pending, new_origin);
+    if (rcq == HTM_OK) rcq = queue_sample_copy(h, copy_first, new_pending);
     if (rcq != HTM_OK) return rcq;
   }
   h->timed = true;
@@ -1525,6 +1574,45 @@ int32_t htm_gather_samples(htm_handle h, int32_t rank, int32_t max_records, int3
   if (!ok && !why.empty()) return fail(h, HTM_ERR_CUDA, why);
   HTM_CK(h, e);
   return HTM_OK;
+}
+
+int32_t htm_posterior_quantiles(htm_handle h, int32_t* n_samples, double* hypo_q, double* vs_q, double* qs_q,
+                                double* t_corr_q, double* a_corr_q) {
+  if (!h || !n_samples) return fail(h, HTM_ERR_ARG, "null argument");
+  if (!h->cfg.summary) return fail(h, HTM_ERR_STATE, "the posterior store is off (cfg.summary = 0)");
+  HTM_CK(h, cudaSetDevice(h->cfg.device));
+  const int n = static_cast<int>(h->store_n), S = h->S;
+  *n_samples = n;
+  if (n == 0) return fail(h, HTM_ERR_STATE, "no post-burn-in sample has been recorded yet");
+  // src/cls_statistics.f90:230-232: il = 0.025 * n_mod etc. -- default REAL products, truncated; 1-based
+  const int il = static_cast<int>(0.025f * static_cast<float>(n)), im = static_cast<int>(0.5f * static_cast<float>(n)),
+            iu = static_cast<int>(0.975f * static_cast<float>(n));
+  const int r_m = (im > 1 ? im : 1) - 1, r_l = (il > 1 ? il : 1) - 1, r_u = (iu > 1 ? iu : 1) - 1;
+  const bool gibbs = h->cfg.mode == HTM_MODE_BLOCKED_GIBBS;
+  const int n_h = 3 * h->E, n_s = gibbs ? 2 + 2 * S : 0;
+  double* d_out = nullptr;
+  HTM_CK(h, cudaMalloc(&d_out, static_cast<size_t>(n_h + n_s) * 3 * sizeof(double)));
+  cudaError_t e = launch_quantile_select(h->cfg.precision, h->d_store_hypo, h->store_cap, n_h, n, r_m, r_l, r_u, d_out, h->stream);
+  if (e == cudaSuccess && gibbs)
+    e = launch_quantile_select(64, h->d_store_shared, h->store_cap, n_s, n, r_m, r_l, r_u, d_out + static_cast<size_t>(n_h) * 3,
+                               h->stream);
+  std::vector<double> sh(static_cast<size_t>(n_s) * 3);
+  if (e == cudaSuccess && hypo_q)
+    e = cudaMemcpyAsync(hypo_q, d_out, static_cast<size_t>(n_h) * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && gibbs)
+    e = cudaMemcpyAsync(sh.data(), d_out + static_cast<size_t>(n_h) * 3, sh.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  free_dev(d_out);
+  HTM_CK(h, e);
+  for (int k = 0; k < 3; ++k) {
+    if (vs_q) vs_q[k] = gibbs ? sh[k] : h->g_vs;
+    if (qs_q) qs_q[k] = gibbs ? sh[3 + k] : h->g_qs;
+    for (int j = 0; j < S; ++j) {
+      if (t_corr_q) t_corr_q[3 * j + k] = gibbs ? sh[3 * (2 + j) + k] : h->g_tc[j];
+      if (a_corr_q) a_corr_q[3 * j + k] = gibbs ? sh[3 * (2 + S + j) + k] : h->g_ac[j];
+    }
+  }
+  return check_exchange(h);
 }
 
 // Validation entry points of the float32 blocked-Gibbs kernel (tests/): the shared-parameter proposal that the

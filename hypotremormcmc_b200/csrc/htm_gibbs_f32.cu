@@ -47,16 +47,30 @@ namespace cg = cooperative_groups;
 
 namespace htm {
 
+// tuning macros (tools/build_variants.sh): the register budget per thread (it decides how many CTAs fit an SM), and whether the
+// per-lane state of the next octet visit is prefetched into shared memory with cp.async
+#ifndef HTM_GIBBS_MAXREG
+#define HTM_GIBBS_MAXREG 128
+#endif
+#ifndef HTM_GIBBS_PREFETCH
+#define HTM_GIBBS_PREFETCH 1
+#endif
+constexpr bool kPrefetch = HTM_GIBBS_PREFETCH != 0;
 constexpr int kOct = 8;
 constexpr int kQuad = 4;
 constexpr float kHalfLn2 = 0.34657359027997264f;
 
 // ---- expanded rows: built once per table upload -------------------------------------------------------------
-// row[0] = A of station 0, row[1] = {t_obs0, a_obs0, sum_{j>=1} w_t, sum_{j>=1} w_a}, then 4 float4 per station
-// pair (1,2), (3,4), ... (store_station_pair); an even station count leaves a zero-weight half pair.
+// row[0] = A of station 0, row[1] = {t_obs0, a_obs0, sum_{j>=1} w_t, sum_{j>=1} w_a}, row[2] = the event's
+// constants {C_e, 1/W_t, 1/W_a, 0}, row[3] = {x_mu, y_mu, 0, 0} (so that everything an event needs arrives with
+// its ONE bulk copy), then 4 float4 per station pair (1,2), (3,4), ... (store_station_pair); an even station
+// count leaves a zero-weight half pair.
+constexpr int kRowHead = 4;
+__host__ __device__ inline int f32_xrow(int S) { return kRowHead + 4 * (S / 2); }
 __global__ void expand_obs_kernel(const float4* __restrict__ sta4, const float4* __restrict__ obs4,
-                                  const float2* __restrict__ prior_xy, int E, int S, float4* __restrict__ obsx) {
-  const int n_pairs = S / 2, per_ev = n_pairs + 1, xrow = 2 + 4 * n_pairs;
+                                  const float4* __restrict__ evc4, const float2* __restrict__ prior_xy, int E, int S,
+                                  float4* __restrict__ obsx) {
+  const int n_pairs = S / 2, per_ev = n_pairs + 1, xrow = f32_xrow(S);
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(E) * per_ev) return;
   const int e = static_cast<int>(i / per_ev), m = static_cast<int>(i % per_ev) - 1;
@@ -72,6 +86,8 @@ __global__ void expand_obs_kernel(const float4* __restrict__ sta4, const float4*
     }
     row[0] = r0.A;
     row[1] = make_float4(ob[0].x, ob[0].z, wt, wa);
+    row[2] = evc4[e];
+    row[3] = make_float4(c.x, c.y, 0.f, 0.f);
     return;
   }
   const int j0 = 1 + 2 * m, j1 = j0 + 1;
@@ -81,14 +97,14 @@ __global__ void expand_obs_kernel(const float4* __restrict__ sta4, const float4*
     b = expand_station(sta4[j1], ob[j1], c.x, c.y);
   else
     b.B = make_float4(0.f, 0.f, 0.f, 0.f);
-  store_station_pair(row + 2 + 4 * m, a, b);
+  store_station_pair(row + kRowHead + 4 * m, a, b);
 }
 
 cudaError_t launch_expand_obs(const Tables& tab, int E, int S, void* obsx, cudaStream_t stream) {
   const size_t n = static_cast<size_t>(E) * (S / 2 + 1);
   expand_obs_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(
       static_cast<const float4*>(tab.sta4), static_cast<const float4*>(tab.obs4_raw),
-      static_cast<const float2*>(tab.prior_xy), E, S, static_cast<float4*>(obsx));
+      static_cast<const float4*>(tab.evc4), static_cast<const float2*>(tab.prior_xy), E, S, static_cast<float4*>(obsx));
   return cudaGetLastError();
 }
 
@@ -128,7 +144,7 @@ __device__ __forceinline__ Moments eval_moments_f32(const float4* __restrict__ r
   float2 a1t = f2(0.f, 0.f), a1a = f2(0.f, 0.f), a2 = f2(0.f, 0.f);
   float2 m1t = f2(0.f, 0.f), m2t = f2(0.f, 0.f), m3t = f2(0.f, 0.f);
   float2 m1a = f2(0.f, 0.f), m2a = f2(0.f, 0.f), m3a = f2(0.f, 0.f);
-  const float4* r = row + 2;
+  const float4* r = row + kRowHead;
 #pragma unroll kMomentsUnroll
   for (int m = 0; m < n_pairs; ++m) {
     const float4 r0 = r[4 * m], r1 = r[4 * m + 1], r2 = r[4 * m + 2], r3 = r[4 * m + 3];
@@ -178,63 +194,58 @@ struct PropF32 {
 struct DeltaSums {
   float dS1t, dS2t, dA2t, dS1a, dS2a, dA2a;
 };
-__device__ __forceinline__ DeltaSums pending_delta(const PropF32& pr, const float4* __restrict__ row, const int n_pairs,
+// The four chains of a warp usually hold proposals of different kinds, so the station-term case is written
+// WITHOUT divergent branches: every lane evaluates station 0 and "its" station at the current hypocentre (one
+// gather from its own event row) and the results are selected by kind.  `any_station` is warp-uniform.
+__device__ __forceinline__ DeltaSums pending_delta(const PropF32& pr, const bool any_station, const float4* __restrict__ row,
                                                    const float hx, const float hy, const float hz, const Glob<float>& g,
                                                    const float4* __restrict__ cp, const float ntc0, const float nac0,
                                                    const float4 Mm, const float4 Q) {
-  DeltaSums o = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (pr.which == 1 || pr.which == 3) {
-    o.dS1t = pr.qa * Mm.x;
-    o.dS2t = pr.qa * fmaf(pr.qa, Mm.y, 2.f * Q.z);
-    o.dA2t = pr.qa * Mm.y;
-    o.dS1a = pr.qb * Mm.z;
-    o.dS2a = pr.qb * fmaf(pr.qb, Mm.w, 2.f * Q.w);
-    o.dA2a = pr.qb * Mm.w;
-    return o;
-  }
-  if (pr.which != 2 && pr.which != 4) return o;
-  const bool is_t = pr.which == 2;
+  DeltaSums o;
+  // vs / qs: polynomial in the coefficients (qa = qb = 0 for the other kinds)
+  o.dS1t = pr.qa * Mm.x;
+  o.dS2t = pr.qa * fmaf(pr.qa, Mm.y, 2.f * Q.z);
+  o.dA2t = pr.qa * Mm.y;
+  o.dS1a = pr.qb * Mm.z;
+  o.dS2a = pr.qb * fmaf(pr.qb, Mm.w, 2.f * Q.w);
+  o.dA2a = pr.qb * Mm.w;
+  if (!any_station) return o;
+  const bool is_t = pr.which == 2, is_a = pr.which == 4;
   const float dlt = pr.dlt;
-  if (pr.idx == 0) {  // station 0 carries the shift: every other residual moves by +dlt
-    const float4 h1 = row[1];
-    if (is_t) {
-      o.dS1t = dlt * h1.z;
-      o.dS2t = dlt * fmaf(dlt, h1.z, 2.f * Q.x);
-      o.dA2t = dlt * Mm.x;
-    } else {
-      o.dS1a = dlt * h1.w;
-      o.dS2a = dlt * fmaf(dlt, h1.w, 2.f * Q.y);
-      o.dA2a = dlt * Mm.z;
-    }
-    return o;
-  }
-  // one station of the event at the CURRENT hypocentre (plus station 0 for the shift)
   const float h2 = fmaf(hz, hz, fmaf(hy, hy, hx * hx));
   const RowHead hd = row_head(row, hx, hy, hz, h2, g, ntc0, nac0);
-  const int m = (pr.idx - 1) >> 1;
-  const bool hi = ((pr.idx - 1) & 1) != 0;
-  const float4* r = row + 2 + 4 * m;
+  const int j = max(pr.idx, 1) - 1, m = j >> 1;
+  const bool hi = (j & 1) != 0;
+  const float4* r = row + kRowHead + 4 * m;
   const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], c4 = cp[m];
   const float cx = hi ? r0.y : r0.x, cy = hi ? r0.w : r0.z, cz = hi ? r1.y : r1.x, cc = hi ? r1.w : r1.z;
   const float d2 = fmaf(hx, cx, fmaf(hy, cy, fmaf(hz, cz, cc + h2)));
   const float d = d2 * mufu_rsq(d2);
+  const float l2 = mufu_lg2(d2);
   const float D = d - hd.d0;
-  if (is_t) {
-    const float sw = hi ? r2.y : r2.x, so = hi ? r2.w : r2.z, ntc = hi ? c4.y : c4.x;
-    const float u = fmaf(sw, fmaf(d, g.ivs, hd.nct) + ntc, so);  // sqrt(w) e
-    const float w = sw * sw;
-    o.dS1t = -w * dlt;
-    o.dS2t = dlt * fmaf(w, dlt, -2.f * sw * u);
-    o.dA2t = -w * dlt * D;
-  } else {
-    const float l2 = mufu_lg2(d2);
-    const float sw = hi ? r3.y : r3.x, so = hi ? r3.w : r3.z, nac = hi ? c4.w : c4.z;
-    const float u = fmaf(sw, fmaf(-kHalfLn2, l2, fmaf(-g.B, d, hd.nca)) + nac, so);
-    const float w = sw * sw;
-    o.dS1a = -w * dlt;
-    o.dS2a = dlt * fmaf(w, dlt, -2.f * sw * u);
-    o.dA2a = -w * dlt * D;
-  }
+  // station j >= 1 of kind t / a: e_j -= dlt
+  const float swt = hi ? r2.y : r2.x, sot = hi ? r2.w : r2.z, ntc = hi ? c4.y : c4.x;
+  const float swa = hi ? r3.y : r3.x, soa = hi ? r3.w : r3.z, nac = hi ? c4.w : c4.z;
+  const float ut = fmaf(swt, fmaf(d, g.ivs, hd.nct) + ntc, sot);  // sqrt(w) e
+  const float ua = fmaf(swa, fmaf(-kHalfLn2, l2, fmaf(-g.B, d, hd.nca)) + nac, soa);
+  const float wt = swt * swt, wa = swa * swa;
+  float s1t = -wt * dlt, s2t = dlt * fmaf(wt, dlt, -2.f * swt * ut), a2t = -wt * dlt * D;
+  float s1a = -wa * dlt, s2a = dlt * fmaf(wa, dlt, -2.f * swa * ua), a2a = -wa * dlt * D;
+  // station 0 carries the shift: every other residual moves by +dlt
+  const float4 h1 = row[1];
+  const bool first = pr.idx == 0;
+  s1t = first ? dlt * h1.z : s1t;
+  s2t = first ? dlt * fmaf(dlt, h1.z, 2.f * Q.x) : s2t;
+  a2t = first ? dlt * Mm.x : a2t;
+  s1a = first ? dlt * h1.w : s1a;
+  s2a = first ? dlt * fmaf(dlt, h1.w, 2.f * Q.y) : s2a;
+  a2a = first ? dlt * Mm.z : a2a;
+  o.dS1t = is_t ? s1t : o.dS1t;
+  o.dS2t = is_t ? s2t : o.dS2t;
+  o.dA2t = is_t ? a2t : o.dA2t;
+  o.dS1a = is_a ? s1a : o.dS1a;
+  o.dS2a = is_a ? s2a : o.dS2a;
+  o.dA2a = is_a ? a2a : o.dA2a;
   return o;
 }
 
@@ -243,15 +254,16 @@ struct F32Sm {
   uint64_t* full;   // [2]
   uint64_t* empty;  // [2]
   float4* rows;     // [2][kOct][row]
-  float4* cp;       // [nc][cps]
+  float4* cp;       // [nc][cps]  {-tc_j0, -tc_j1, -ac_j0, -ac_j1}: station terms of the CTA's chains (persistent)
   float4* c0;       // [nc]  {-tc0, -ac0, 0, 0}
+  float4* pf;       // [2][n_warps * 32][4]  per-lane state of the next octet visit (cp.async): H, M, Q | P, Lp
   float* pq;        // [nc][3]  qa, qb, dlt of the pending proposal
   int row, cps;
 };
 __host__ __device__ inline int f32_cps(int S) { return (S / 2) | 1; }
 __host__ __device__ inline size_t f32_sweep_smem(int S, int nc) {
-  const int xrow = 2 + 4 * (S / 2);
-  return 32 + (static_cast<size_t>(2) * kOct * (xrow + 1) + static_cast<size_t>(nc) * (f32_cps(S) + 1)) * sizeof(float4) +
+  return 32 + (static_cast<size_t>(2) * kOct * (f32_xrow(S) + 1) + static_cast<size_t>(nc) * (f32_cps(S) + 1) +
+               (kPrefetch ? static_cast<size_t>(2) * (nc / kQuad) * 32 * 4 : 0)) * sizeof(float4) +
          static_cast<size_t>(nc) * 4 * sizeof(float);
 }
 __device__ __forceinline__ F32Sm carve_f32_sm(unsigned char* base, int S, int xrow, int nc) {
@@ -263,11 +275,29 @@ __device__ __forceinline__ F32Sm carve_f32_sm(unsigned char* base, int S, int xr
   m.rows = reinterpret_cast<float4*>(base + 32);
   m.cp = m.rows + 2 * kOct * m.row;
   m.c0 = m.cp + nc * m.cps;
-  m.pq = reinterpret_cast<float*>(m.c0 + nc);
+  m.pf = m.c0 + nc;
+  m.pq = reinterpret_cast<float*>(m.pf + (kPrefetch ? 2 * (nc / kQuad) * 32 * 4 : 0));
   return m;
 }
 
-// the station terms of the CTA's chains from global memory (L2) and the coefficients of their pending proposals
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// The station terms of the CTA's chains from global memory (L2), once per launch; afterwards only the entry an
+// accepted t_corr / a_corr proposal changed is rewritten (f32_update_chain_terms).
 __device__ __forceinline__ void f32_stage_chain_terms(const F32Sm& m, const ChainSm& cs, int nc, int c_base, int J, int S) {
   const int n_pairs = S / 2;
   for (int i = threadIdx.x; i < nc * n_pairs; i += blockDim.x) {
@@ -286,25 +316,39 @@ __device__ __forceinline__ void f32_stage_chain_terms(const F32Sm& m, const Chai
   for (int lc = threadIdx.x; lc < nc; lc += blockDim.x) {
     const int c = c_base + lc;
     if (c >= J) continue;
-    const double tc0 = __ldcg(cs.tc + static_cast<size_t>(c) * S), ac0 = __ldcg(cs.ac + static_cast<size_t>(c) * S);
-    m.c0[lc] = make_float4(-static_cast<float>(tc0), -static_cast<float>(ac0), 0.f, 0.f);
-    const int wh = cs.which[c];
-    const double vs = cs.vs[c], qs = cs.qs[c], xn = cs.xnew[c];
-    double qa = 0.0, qb = 0.0, dlt = 0.0;
-    if (wh == 1) {
-      qa = 1.0 / xn - 1.0 / vs;
-      qb = -(kPi * kFreq / (qs * xn) - kPi * kFreq / (qs * vs));
-    } else if (wh == 3) {
-      qb = -(kPi * kFreq / (xn * vs) - kPi * kFreq / (qs * vs));
-    } else if (wh == 2) {
-      dlt = xn - __ldcg(cs.tc + static_cast<size_t>(c) * S + cs.idx[c]);
-    } else if (wh == 4) {
-      dlt = xn - __ldcg(cs.ac + static_cast<size_t>(c) * S + cs.idx[c]);
-    }
-    m.pq[3 * lc] = static_cast<float>(qa);
-    m.pq[3 * lc + 1] = static_cast<float>(qb);
-    m.pq[3 * lc + 2] = static_cast<float>(dlt);
+    m.c0[lc] = make_float4(-static_cast<float>(__ldcg(cs.tc + static_cast<size_t>(c) * S)),
+                           -static_cast<float>(__ldcg(cs.ac + static_cast<size_t>(c) * S)), 0.f, 0.f);
   }
+}
+// one thread per chain of the CTA: the entry an accepted station-term proposal (which, idx, x_new) changed
+__device__ __forceinline__ void f32_update_chain_term(const F32Sm& m, int lc, int which, int idx, double x_new) {
+  const float v = -static_cast<float>(x_new);
+  if (idx == 0) {
+    if (which == 2) m.c0[lc].x = v;
+    if (which == 4) m.c0[lc].y = v;
+    return;
+  }
+  float* w = reinterpret_cast<float*>(m.cp + lc * m.cps + ((idx - 1) >> 1));
+  w[(which == 2 ? 0 : 2) + ((idx - 1) & 1)] = v;
+}
+// one thread per chain of the CTA: coefficients of the chain's pending proposal
+__device__ __forceinline__ void f32_stage_proposal(const F32Sm& m, const ChainSm& cs, int lc, int c, int S) {
+  const int wh = cs.which[c];
+  const double vs = cs.vs[c], qs = cs.qs[c], xn = cs.xnew[c];
+  double qa = 0.0, qb = 0.0, dlt = 0.0;
+  if (wh == 1) {
+    qa = 1.0 / xn - 1.0 / vs;
+    qb = -(kPi * kFreq / (qs * xn) - kPi * kFreq / (qs * vs));
+  } else if (wh == 3) {
+    qb = -(kPi * kFreq / (xn * vs) - kPi * kFreq / (qs * vs));
+  } else if (wh == 2) {
+    dlt = xn - __ldcg(cs.tc + static_cast<size_t>(c) * S + cs.idx[c]);
+  } else if (wh == 4) {
+    dlt = xn - __ldcg(cs.ac + static_cast<size_t>(c) * S + cs.idx[c]);
+  }
+  m.pq[3 * lc] = static_cast<float>(qa);
+  m.pq[3 * lc + 1] = static_cast<float>(qb);
+  m.pq[3 * lc + 2] = static_cast<float>(dlt);
 }
 
 struct F32State {
@@ -315,7 +359,7 @@ struct F32State {
 // INIT = true: generate_model for every (chain, event) (src/cls_model.f90:139-158, Philox draws as in the
 // float64 path) and its state at the initial shared parameters; no iteration is run.
 template <bool TRACE, bool INIT>
-__global__ void __launch_bounds__(kCW * 32, 2)
+__global__ void __maxnreg__(HTM_GIBBS_MAXREG)
     gibbs_f32_kernel(const GibbsParams<float> p, const GibbsDecide d, const F32State st, const int iter_first,
                      const int iter_last, const int rec_origin, const int rec_cap, htm_step_trace* trace_base,
                      htm_swap_trace* swap_base, double* part /* [2][2][J][gridDim.x] */, const int n_oct,
@@ -360,6 +404,7 @@ __global__ void __launch_bounds__(kCW * 32, 2)
   }
   chain_load(d, cs, /*terms=*/false);
   __syncthreads();
+  f32_stage_chain_terms(m, cs, nc, c_base, J, S);
 
   const int es = lane >> 2, chs = lane & (kQuad - 1);
   const bool warp_ok = c_base + warp * kQuad < J;
@@ -367,6 +412,15 @@ __global__ void __launch_bounds__(kCW * 32, 2)
   const int lc = c_ok ? warp * kQuad + chs : warp * kQuad;
   const int c = warp_ok ? c_base + lc : 0;
   const size_t per_it = static_cast<size_t>(E + 1) * J, psz = static_cast<size_t>(J) * gridDim.x;
+  // this lane's rows of the state arrays (a (chain, event) is always visited by the same thread)
+  const size_t cE = static_cast<size_t>(c) * E;
+  float4* const gH = st.H + cE;
+  float4* const gM = st.M + cE;
+  float4* const gQ = st.Q + cE;
+  float4* const gP = st.P + cE;
+  float* const gLp = st.Lp + cE;
+  float4* const pf0 = m.pf + static_cast<size_t>(threadIdx.x) * 4;                     // stage 0
+  float4* const pf1 = pf0 + static_cast<size_t>(blockDim.x) * 4;                       // stage 1
   uint32_t cnt_p[3] = {0, 0, 0}, cnt_a[3] = {0, 0, 0};
   long t_run = 0;
 
@@ -377,9 +431,23 @@ __global__ void __launch_bounds__(kCW * 32, 2)
     int rec_slot = rec ? (it - 1) / p.n_interval - rec_origin : -1;
     if (rec_slot >= rec_cap) rec_slot = -1;
     htm_step_trace* trace_it = trace_base ? trace_base + static_cast<size_t>(it - iter_first) * per_it : nullptr;
-    // the CTA's chain terms for this iteration (decide_core ended with a block barrier; the previous
-    // iteration's reads of cp / pq are over)
-    f32_stage_chain_terms(m, cs, nc, c_base, J, S);
+    const bool a_prev = !INIT && cs.aprev[c] != 0;
+    // this lane's state of octet visit i -> shared memory, asynchronously (one group per visit): the L2 latency
+    // of the state hides behind the previous visit's arithmetic
+    auto prefetch = [&](int i) {
+      if (INIT || !kPrefetch) return;
+      const int ee = min((o_begin + i) * kOct + es, E - 1);
+      float4* dst = (i & 1) ? pf1 : pf0;
+      cp_async16(dst, gH + ee);
+      cp_async16(dst + 1, gM + ee);
+      cp_async16(dst + 2, (a_prev ? gP : gQ) + ee);
+      if (a_prev) cp_async4(dst + 3, gLp + ee);
+      cp_async_commit();
+    };
+    if (warp_ok) prefetch(0);
+    // coefficients of the chains' pending proposals (decide_core ended with a block barrier; the previous
+    // iteration's reads of pq are over)
+    if (threadIdx.x < nc && c_base + threadIdx.x < J && !INIT) f32_stage_proposal(m, cs, threadIdx.x, c_base + threadIdx.x, S);
     __syncthreads();
     const float T = static_cast<float>(cs.T[c]);
     const float iT = 1.f / T;
@@ -388,18 +456,28 @@ __global__ void __launch_bounds__(kCW * 32, 2)
     PropF32 pr;
     pr.which = INIT ? 0 : cs.which[c];
     pr.idx = cs.idx[c];
-    pr.qa = m.pq[3 * lc];
-    pr.qb = m.pq[3 * lc + 1];
-    pr.dlt = m.pq[3 * lc + 2];
+    pr.qa = INIT ? 0.f : m.pq[3 * lc];
+    pr.qb = INIT ? 0.f : m.pq[3 * lc + 1];
+    pr.dlt = INIT ? 0.f : m.pq[3 * lc + 2];
+    const bool any_station = __any_sync(0xffffffffu, pr.which == 2 || pr.which == 4);
     const float4* cp = m.cp + lc * m.cps;
     const float4 c0 = warp_ok ? m.c0[lc] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool a_prev = !INIT && cs.aprev[c] != 0;
     const int rec_chain_slot = (rec_slot >= 0 && p.hypo_rec) ? cs.slot[c] : -1;
+    float4* const rec_row =
+        rec_chain_slot >= 0 ? p.hypo_rec + (static_cast<size_t>(rec_slot) * p.n_cool_total + rec_chain_slot) * E : nullptr;
     double s_cur = 0.0, s_prop = 0.0;
     for (int i = 0; i < n_my; ++i, ++t_run) {
       const int buf = static_cast<int>(t_run & 1);
       const uint32_t ph = static_cast<uint32_t>((t_run >> 1) & 1);
       const int o = o_begin + i;
+      if (warp_ok) {
+        if (i + 1 < n_my) {
+          prefetch(i + 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+      }
       mbar_wait(m.full + buf, ph);
       if (warp_ok) {
         const int n_ev = min(kOct, E - o * kOct);
@@ -407,9 +485,8 @@ __global__ void __launch_bounds__(kCW * 32, 2)
         const bool ev_ok = e < E;
         const int ee = ev_ok ? e : E - 1;  // idle lanes clone the last event and never write
         const float4* row = m.rows + (buf * kOct + (ev_ok ? es : n_ev - 1)) * m.row;
-        const size_t ci = static_cast<size_t>(c) * E + ee;
-        const float4 evc = p.evc4[ee];
-        const float2 mu = reinterpret_cast<const float2*>(p.prior_xy)[ee];
+        const float4 evc = row[2];
+        const float4 mu = row[3];
         const uint32_t gid = (static_cast<uint32_t>(ee) + p.event_offset) * p.J_total + p.chain_offset + static_cast<uint32_t>(c);
         float4 H, Mm, Q;
         bool acc = false, dirty = false;
@@ -426,15 +503,19 @@ __global__ void __launch_bounds__(kCW * 32, 2)
           Q = make_float4(o1.S1t, o1.S1a, o1.A2t, o1.A2a);
           dirty = acc = true;
         } else {
-          H = st.H[ci];
-          Mm = st.M[ci];
-          if (a_prev) {  // lazy commit of the last shared-parameter acceptance: exactly what was judged
-            Q = st.P[ci];
-            H.w = st.Lp[ci];
-            dirty = true;
+          if (kPrefetch) {
+            const float4* src = (i & 1) ? pf1 : pf0;
+            H = src[0];
+            Mm = src[1];
+            Q = src[2];
+            if (a_prev) H.w = reinterpret_cast<const float*>(src + 3)[0];
           } else {
-            Q = st.Q[ci];
+            H = __ldcg(gH + ee);
+            Mm = __ldcg(gM + ee);
+            Q = __ldcg((a_prev ? gP : gQ) + ee);
+            if (a_prev) H.w = __ldcg(gLp + ee);
           }
+          dirty = a_prev;  // lazy commit of the last shared-parameter acceptance: exactly what was judged
           // model_perturb for one coordinate (src/cls_model.f90:162-190); icmp 0 -> z, 1 -> y, 2 -> x
           const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(it), gid, PHX_STEP, 0u);
           icmp = static_cast<int>(below(w.v[0], 3u));
@@ -478,19 +559,18 @@ __global__ void __launch_bounds__(kCW * 32, 2)
           }
         }
         // the chain's pending shared-parameter proposal, for this event: O(1)
-        const DeltaSums ds = pending_delta(pr, row, n_pairs, H.x - mu.x, H.y - mu.y, H.z, g, cp, c0.x, c0.y, Mm, Q);
+        const DeltaSums ds = pending_delta(pr, any_station, row, H.x - mu.x, H.y - mu.y, H.z, g, cp, c0.x, c0.y, Mm, Q);
         const float dchi = (ds.dS2t - ds.dS1t * fmaf(2.f, Q.x, ds.dS1t) * evc.y) + (ds.dS2a - ds.dS1a * fmaf(2.f, Q.y, ds.dS1a) * evc.z);
         const float dL = -0.5f * dchi;
         if (ev_ok && c_ok) {
           if (dirty) {
-            st.H[ci] = H;
-            st.Q[ci] = Q;
+            gH[e] = H;
+            gQ[e] = Q;
           }
-          if (acc) st.M[ci] = Mm;
-          st.P[ci] = make_float4(Q.x + ds.dS1t, Q.y + ds.dS1a, Q.z + ds.dA2t, Q.w + ds.dA2a);
-          st.Lp[ci] = H.w + dL;
-          if (rec_chain_slot >= 0)
-            p.hypo_rec[(static_cast<size_t>(rec_slot) * p.n_cool_total + rec_chain_slot) * E + e] = H;
+          if (acc) gM[e] = Mm;
+          gP[e] = make_float4(Q.x + ds.dS1t, Q.y + ds.dS1a, Q.z + ds.dA2t, Q.w + ds.dA2a);
+          gLp[e] = H.w + dL;
+          if (rec_row) rec_row[e] = H;
           s_cur += static_cast<double>(H.w);
           s_prop += static_cast<double>(H.w) + static_cast<double>(dL);
           if (cold && !INIT) {
@@ -532,6 +612,10 @@ __global__ void __launch_bounds__(kCW * 32, 2)
     }
     htm_step_trace* trace_g = trace_it ? trace_it + static_cast<size_t>(E) * J : nullptr;
     htm_swap_trace* swap_it = swap_base ? swap_base + (it - iter_first) : nullptr;
+    // the proposal being judged, of the chain this thread looks after (decide_core replaces it by the next one)
+    const bool mine = threadIdx.x < nc && c_base + threadIdx.x < J;
+    const int j_which = mine ? cs.which[c_base + threadIdx.x] : 0, j_idx = mine ? cs.idx[c_base + threadIdx.x] : 0;
+    const double j_xnew = mine ? cs.xnew[c_base + threadIdx.x] : 0.0;
     if (d.xch.n > 1) {
       // event shards: CTA (0,0) adds this shard's partials, exchanges the sums with the other GPUs through peer
       // memory and hands the totals over all events to every CTA of its grid
@@ -550,6 +634,9 @@ __global__ void __launch_bounds__(kCW * 32, 2)
     } else {
       decide_core(d, cs, it, it + 1, part_cur, part_prop, rec_slot, trace_g, swap_it, writer, false, true);
     }
+    // an accepted station-term proposal changes one entry of the chain's terms in shared memory
+    if (mine && cs.aprev[c_base + threadIdx.x] && (j_which == 2 || j_which == 4))
+      f32_update_chain_term(m, threadIdx.x, j_which, j_idx, j_xnew);
   }
   if (INIT) return;
   if (warp_ok) {

@@ -34,6 +34,15 @@ cudaError_t launch_build_tables(int precision, const TableBuild& b, cudaStream_t
 cudaError_t launch_pack_hypo(int precision, const void* ring, const int* slot_of_rec, int n_rec, int E, size_t ring_stride,
                              size_t row_offset, double* out, size_t out_stride, cudaStream_t stream);
 
+// device-side posterior store and order statistics (htm_summary.cu)
+cudaError_t launch_store_append_hypo(int precision, const void* ring, int row0, int n_new, int E, void* store,
+                                     size_t cap, size_t pos0, cudaStream_t stream);
+cudaError_t launch_store_append_shared(const double* rec_vs, const double* rec_qs, const double* rec_tc, const double* rec_ac,
+                                       int row0, int n_new, int S, double* store, size_t cap, size_t pos0,
+                                       cudaStream_t stream);
+cudaError_t launch_quantile_select(int precision_bits, const void* store, size_t cap, int n_marginals, int n, int r0, int r1,
+                                   int r2, double* out, cudaStream_t stream);
+
 // everything a factorised-mode launch needs
 struct FactLaunch {
   int precision = 32;

@@ -52,7 +52,7 @@ module htm_b200_binding
      integer(c_int32_t) :: max_samples
      integer(c_int32_t) :: lane_slots
      integer(c_int32_t) :: gibbs_shard_events
-     integer(c_int32_t) :: reserved1
+     integer(c_int32_t) :: summary
   end type htm_config
 
   type, bind(c) :: htm_step_trace
@@ -284,6 +284,16 @@ module htm_b200_binding
        real(c_double), intent(out) :: vs(*), qs(*), hypo_all(*), t_corr(*), a_corr(*)
        integer(c_int32_t) :: rc
      end function htm_gather_samples
+
+     ! device-side quantile tables of hypo_tremor_statistics (cfg%summary = 1)
+     function htm_posterior_quantiles(h, n_samples, hypo_q, vs_q, qs_q, t_corr_q, a_corr_q) &
+          & bind(c, name="htm_posterior_quantiles") result(rc)
+       import
+       type(c_ptr), value :: h
+       integer(c_int32_t), intent(out) :: n_samples
+       real(c_double), intent(out) :: hypo_q(3,*), vs_q(3), qs_q(3), t_corr_q(3,*), a_corr_q(3,*)
+       integer(c_int32_t) :: rc
+     end function htm_posterior_quantiles
 
      ! validation entry points of the float32 blocked-Gibbs kernel (per joint chain of this shard)
      function htm_gibbs_pending(h, which, idx, x_new) bind(c, name="htm_gibbs_pending") result(rc)

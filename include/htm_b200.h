@@ -121,7 +121,9 @@ typedef struct htm_config {
   int32_t gibbs_shard_events; /* mode C only: 1 = shard the EVENTS of every joint chain over the shards (all
                                shards hold all chains; one NCCL all-reduce of the per-chain sums per
                                iteration; needs htm_comm_init).  0 = shard the virtual ranks.        */
-  int32_t reserved1;        /* keeps sizeof(htm_config) a multiple of 8                 */
+  int32_t summary;          /* 1 = keep every post-burn-in cold-chain sample in a device-side store for
+                               htm_posterior_quantiles (needs max_samples > 0); 0 = off.  (This member also
+                               keeps sizeof(htm_config) a multiple of 8.)                                   */
 } htm_config;
 
 /* One record per (iteration, rank, chain) step of the replay mode, in loop order
@@ -277,6 +279,17 @@ int32_t htm_get_counts(htm_handle h, int64_t n_propose[7], int64_t n_accept[7]);
 /* New: device-side posterior histograms of cold-chain hypocentres after burn-in.
  * hist: [n_events(shard)][3][hist_bins] counts (x, y, z). */
 int32_t htm_get_histograms(htm_handle h, uint32_t* hist);
+
+/* Device-side form of the tables `hypo_tremor_statistics` computes from the .out files: per marginal the sorted
+ * post-burn-in cold-chain sample at the 1-based positions im = 0.5 n, il = 0.025 n, iu = 0.975 n
+ * (src/cls_statistics.f90:230-232,360-362; default-real products truncated to integer), in the column order of
+ * hypo.stat / station_corrections.stat / uniform_structure.stat: {50 %, 2.5 %, 97.5 %}
+ * (src/cls_statistics.f90:216-264,345-431).  Needs cfg.summary = 1; covers everything recorded since
+ * htm_init_chains.  n_samples = n_mod of src/cls_statistics.f90:65 once the run is complete.
+ * hypo_q: [3*n_events(shard)][3] (x, y, z of event 1, then event 2, ...); vs_q, qs_q: [3];
+ * t_corr_q, a_corr_q: [n_sta][3].  Any output pointer may be NULL. */
+int32_t htm_posterior_quantiles(htm_handle h, int32_t* n_samples, double* hypo_q, double* vs_q, double* qs_q,
+                                double* t_corr_q, double* a_corr_q);
 
 /* ---- multi-GPU (one process per GPU, events sharded by cfg.shard_rank / cfg.shard_count) -----
  * The data path needs no exchange; these calls are the once-per-flush gathers.  NCCL is loaded

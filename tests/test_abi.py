@@ -50,7 +50,7 @@ def test_config_struct_matches_c_defaults():
     # a layout mismatch would scramble them
     for name, _ in H.HtmConfig._fields_:
         if name in ("n_sta", "n_events", "device", "shard_rank", "max_samples", "hist_bins", "lane_slots",
-                    "gibbs_shard_events", "reserved1"):
+                    "gibbs_shard_events", "summary"):
             continue
         assert getattr(c, name) == getattr(d, name), name
     assert ctypes.sizeof(H.HtmConfig) == 21 * 8 + 28 * 4

@@ -117,3 +117,40 @@ def test_full_size_float32_vs_float64_oracle_on_100_events(E, S, n_it, burn, int
                 if not r["ok"]:
                     bad.append((lo + e, c, r["D"], r["D_max"], r["n_eff"]))
     assert n_marg == 300 and len(bad) <= 3, bad           # >= 99 % of the marginals
+
+
+@pytest.mark.parametrize("mode", ["factorised", "blocked_gibbs"])
+def test_device_posterior_quantiles_equal_the_sorted_samples(mode):
+    """(f)-1: the device-side summary (radix selection on the marginal-major store, csrc/htm_summary.cu) must pick
+    exactly the elements `hypo_tremor_statistics` picks from the sorted samples (src/cls_statistics.f90:230-232):
+    compared bit for bit with hypotremormcmc_b200.io.quantile_summary on the records the same run handed out."""
+    from hypotremormcmc_b200 import io as hio
+    E, S, R, K = 37, 11, 3, 4
+    syn = H.Synthetic(E, S, 5)
+    n_it, burn, interval = 6000, 1500, 7
+    kw = dict(NOSOLVE, mode=H.MODE_FACTORISED) if mode == "factorised" else dict(mode=H.MODE_BLOCKED_GIBBS)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=2, n_iter=n_it, n_burn=burn,
+                           n_interval=interval, precision=32, max_samples=120, summary=1, **kw)
+    parts = []
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        it0 = 1
+        while it0 <= n_it:
+            it1 = min(n_it, it0 + 100 * interval - 1)
+            g.run(it0, it1)
+            for r in range(R):
+                parts.append(g.fetch_samples(r))
+                g.fetch_likelihood(r)
+            it0 = it1 + 1
+        q = g.posterior_quantiles()
+    all_ = {k: np.concatenate([p[k] for p in parts]) for k in ("vs", "qs", "hypo", "t_corr", "a_corr")}
+    n_mod = (n_it - burn) * R * cfg.n_cool // interval                      # src/cls_statistics.f90:65
+    assert q["n"] == len(all_["vs"]) and abs(q["n"] - n_mod) <= R * cfg.n_cool
+    for m in range(3 * E):
+        assert tuple(q["hypo"][m]) == tuple(hio.quantile_summary(all_["hypo"][:, m])), m
+    assert tuple(q["vs"]) == tuple(hio.quantile_summary(all_["vs"])) and tuple(q["qs"]) == tuple(hio.quantile_summary(all_["qs"]))
+    for j in range(S):
+        assert tuple(q["t_corr"][j]) == tuple(hio.quantile_summary(all_["t_corr"][:, j])), j
+        assert tuple(q["a_corr"][j]) == tuple(hio.quantile_summary(all_["a_corr"][:, j])), j
+    assert np.all(q["hypo"][:, 1] <= q["hypo"][:, 0]) and np.all(q["hypo"][:, 0] <= q["hypo"][:, 2])
