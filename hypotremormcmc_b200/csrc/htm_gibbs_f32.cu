@@ -380,11 +380,14 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
   const int n_it = INIT ? 1 : iter_last - iter_first + 1;
   const long n_run = static_cast<long>(n_my) * n_it;  // octet visits of this CTA
   const uint32_t row_bytes = static_cast<uint32_t>(p.xrow * sizeof(float4));
+  // warps whose four chain slots all lie past chain J-1 (the last chain group of a CTA row) stay out of the ring:
+  // they would only spin on its barriers
+  const int n_active = min(n_warps, (J - c_base + kQuad - 1) / kQuad);
   if (threadIdx.x == 0) {
     mbar_init(m.full, 1);
     mbar_init(m.full + 1, 1);
-    mbar_init(m.empty, n_warps);
-    mbar_init(m.empty + 1, n_warps);
+    mbar_init(m.empty, n_active);
+    mbar_init(m.empty + 1, n_active);
     fence_mbar_init();
     fence_proxy_async();
   }
@@ -466,7 +469,7 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
     float4* const rec_row =
         rec_chain_slot >= 0 ? p.hypo_rec + (static_cast<size_t>(rec_slot) * p.n_cool_total + rec_chain_slot) * E : nullptr;
     double s_cur = 0.0, s_prop = 0.0;
-    for (int i = 0; i < n_my; ++i, ++t_run) {
+    for (int i = 0; i < (warp_ok ? n_my : 0); ++i, ++t_run) {
       const int buf = static_cast<int>(t_run & 1);
       const uint32_t ph = static_cast<uint32_t>((t_run >> 1) & 1);
       const int o = o_begin + i;

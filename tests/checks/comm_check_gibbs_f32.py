@@ -1,8 +1,13 @@
-"""Event-sharded blocked Gibbs in float32 under torchrun (one rank per GPU): the sharded run (persistent octet sweep
-with the peer-memory exchange, or the per-iteration paths) must reproduce, flag for flag and bit for bit, the
-UNSHARDED float32 run of the same library on one GPU (which the single-GPU suite ties to the oracle)."""
+"""Event-sharded blocked Gibbs in float32 under torchrun (one rank per GPU): the sharded run (persistent kernel with the
+peer-memory exchange between two grid barriers) must reproduce, flag for flag and bit for bit, the UNSHARDED float32
+run of the same library on one GPU (which the single-GPU suite ties to the oracle).
+
+HTM_TEST_DELAY_S=<s>: the last rank starts its run <s> seconds late -- the exchange must simply wait (wall-clock
+budget HTM_XCH_TIMEOUT_S, default 120 s).  With HTM_TEST_EXPECT_TIMEOUT=1 the delay exceeds the budget: every rank
+must then get an ERROR from the calls that return results, never numbers decided on partial sums."""
 import os
 import sys
+import time
 
 sys.path.insert(0, ".")
 import numpy as np
@@ -31,6 +36,23 @@ with H.HypoTremorB200(cfg) as g:
         handles = [None] * world
         dist.all_gather_object(handles, mine)
         g.comm_p2p_import(handles)
+    delay = float(os.environ.get("HTM_TEST_DELAY_S", "0"))
+    if delay and rank == world - 1:
+        time.sleep(delay)
+    if os.environ.get("HTM_TEST_EXPECT_TIMEOUT"):
+        failed = []
+        for call in (lambda: g.run_traced(1, 50), g.get_counts, lambda: g.get_chain_state(0, 0), lambda: g.fetch_samples(0),
+                     g.synchronize):
+            try:
+                call()
+                failed.append(False)
+            except H.HtmError as ex:
+                failed.append("exchange timed out" in str(ex))
+        print("comm_check_gibbs_f32 rank %d/%d: every result call reports the exchange time-out: %s" % (rank, world, all(failed)))
+        flag = torch.tensor([1 if all(failed) else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.destroy_process_group()
+        sys.exit(0 if int(flag) == 1 else 1)
     tr, sw = g.run_traced(1, 50)
     g.run(51, n_it)
     _, nl, _ = g.last_run_stats()

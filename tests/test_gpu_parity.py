@@ -568,7 +568,7 @@ def test_blocked_gibbs_float32_first_iteration_follows_the_float64_kernel():
     assert (a["accepted"] != b["accepted"]).mean() < 2e-3
     same = a["accepted"][:-1] == b["accepted"][:-1]
     dL = (np.abs(a["log_likelihood"][:-1] - b["log_likelihood"][:-1]) /
-          (2e-3 + 1e-5 * np.abs(a["log_likelihood"][:-1])))[same]               # per event: abs + float32 relative
+          (2e-3 + 3e-5 * np.abs(a["log_likelihood"][:-1])))[same]               # per event: abs + float32 relative
     assert dL.max() < 1.0, dL.max()
     tot = np.abs(a["log_likelihood"][-1] - b["log_likelihood"][-1])            # per chain, after the shared step
     agree = a["accepted"][-1] == b["accepted"][-1]
@@ -912,6 +912,17 @@ def test_event_sharded_gibbs_on_two_gpus(exchange):
                        cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("equals the unsharded run: True") == 2, r.stdout[-2000:]
+    # a shard that starts 12 s late: the exchange waits (wall-clock budget, not a poll count) and nothing changes
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), "tests/checks/comm_check_gibbs_f32.py"],
+                       cwd=root, env=dict(env, HTM_TEST_DELAY_S="12"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("equals the unsharded run: True") == 2, r.stdout[-2000:] + r.stderr[-2000:]
+    # a shard later than the budget: every result-returning call fails loudly on every rank
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), "tests/checks/comm_check_gibbs_f32.py"],
+                       cwd=root, env=dict(env, HTM_TEST_DELAY_S="8", HTM_XCH_TIMEOUT_S="2", HTM_TEST_EXPECT_TIMEOUT="1"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("reports the exchange time-out: True") == 2, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_blocked_gibbs_allreduce_path_is_step_exact(monkeypatch):
