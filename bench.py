@@ -319,7 +319,7 @@ def hbm_block(traffic, ms_per_launch):
             "peak_source": "MEASURED_PEAKS.json hbm_gbs"}
 
 
-def extra_mode_b(H, timer, a, local, E, S, K, R, precision, iters, peak_tf):
+def extra_mode_b(H, timer, a, local, E, S, K, R, precision, iters, peak_tf, peak64_tf=None):
     """short device-resident run of another mode-B shape / instantiation"""
     syn = H.Synthetic(E, S, SEED - 1)
     cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=iters, n_burn=0,
@@ -338,10 +338,13 @@ def extra_mode_b(H, timer, a, local, E, S, K, R, precision, iters, peak_tf):
             "value": rate, "unit": UNIT, "ms_per_step": sum(ms) / 5, "iterations_per_step": iters, "steps": 5, "warmup": 3,
             "gpu_launches": nl,
             "roofline": {"bound": "fp%d" % precision, "achieved": rate * flop / 1e12,
-                         "peak": peak_tf if precision == 32 else None, "unit": "TFLOP/s",
-                         "frac": rate * flop / 1e12 / peak_tf if precision == 32 else None,
+                         "peak": peak_tf if precision == 32 else peak64_tf, "unit": "TFLOP/s",
+                         "frac": rate * flop / 1e12 / (peak_tf if precision == 32 else peak64_tf),
                          "flop_per_proposal": flop, "traffic": tr, "traffic_source": src,
-                         "note": None if precision == 32 else "no FP64 vector peak measured; fraction not quoted"}}
+                         "note": None if precision == 32 else
+                         "peak = own-measured DFMA microbenchmark (htm_measure_fp64_peak); the float64 kernel keeps the "
+                         "reference's operation order (IEEE sqrt, division, libdevice log), so most of its FP64 work is "
+                         "inside those, not in the 30 S algorithmic operations"}}
 
 
 def extra_mode_c(H, timer, a, local, E, S, R, K, iters, peak_tf, cpu_seconds):
@@ -417,7 +420,8 @@ def multi_gpu_mode_c(H, dist, torch, a, world, rank, local, peak_tf):
     for f in ("proposal_type", "prior_ok", "accepted"):
         ok &= bool(np.array_equal(tr[f][:, :-1], tr_u[f][:, lo:lo + sh.n_events]) and np.array_equal(tr[f][:, -1], tr_u[f][:, -1]))
     ok &= bool(np.array_equal(sw, sw_u))
-    ok &= bool(np.array_equal(tr["log_likelihood"][:, -1], tr_u["log_likelihood"][:, -1]))
+    # (the float64 sums of float32 terms depend on the grouping into partial sums in their last bits only)
+    ok &= bool(np.all(np.abs(tr["log_likelihood"][:, -1] - tr_u["log_likelihood"][:, -1]) <= 1e-13 * np.abs(tr_u["log_likelihood"][:, -1])))
     ok &= st["vs"] == su["vs"] and st["qs"] == su["qs"] and st["temp"] == su["temp"]
     ok &= bool(np.array_equal(st["hypo"], su["hypo"][3 * lo:3 * (lo + sh.n_events)]))
     ok &= bool(np.array_equal(p, pu) and np.array_equal(acc, au))
@@ -425,8 +429,8 @@ def multi_gpu_mode_c(H, dist, torch, a, world, rank, local, peak_tf):
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     selfcheck = {"event_sharded_gibbs_equals_unsharded": bool(int(flag.item()) == 1),
                  "what": "%d events x %d stations, %d joint chains, f32, %d iterations traced + %d more: every flag, "
-                         "swap, summed log-likelihood, counter and final state identical on every rank (peer-memory "
-                         "exchange inside the persistent sweep)" % (E, S, R * K, 40, n_it - 40)}
+                         "swap, counter and final state identical on every rank, summed log-likelihoods equal to 1e-13 "
+                         "(peer-memory exchange inside the persistent sweep)" % (E, S, R * K, 40, n_it - 40)}
     # ---- throughput: 100,000 x 50, 20 joint chains, events sharded ----
     E, S, R, K, n_it = 100000, 50, 4, 5, 300
     syn = H.Synthetic(E, S, SEED + 11).shard(rank, world)
@@ -574,8 +578,9 @@ def run_b200(a):
     if not a.no_extra:
         if world == 1:
             extra["configs1_f32"] = extra_mode_b(H, timer, a, local, 1000, 20, 16, 4, 32, 20000, peak_tf)
+            from hypotremormcmc_b200.api import measure_fp64_peak
             extra["configs2_f64"] = extra_mode_b(H, timer, a, local, a.events or 10000, a.stations, a.chains, a.ranks, 64,
-                                                 500, peak_tf)
+                                                 500, peak_tf, measure_fp64_peak(local))
             if not a.no_cpu:
                 from oracle import pyoracle
                 pyoracle.build()

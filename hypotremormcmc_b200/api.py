@@ -24,7 +24,7 @@ EXPORTS = [
     "htm_discard_samples", "htm_get_counts", "htm_get_histograms", "htm_device_ptr",
     "htm_last_run_stats", "htm_measure_fp32_peak", "htm_comm_unique_id", "htm_comm_init", "htm_gather",
     "htm_comm_p2p_export", "htm_comm_p2p_import", "htm_gather_samples", "htm_gibbs_pending", "htm_gibbs_last_sums",
-    "htm_posterior_quantiles",
+    "htm_posterior_quantiles", "htm_measure_fp64_peak",
 ]
 
 
@@ -82,6 +82,7 @@ def load_library():
         "htm_device_ptr": [vp, i32, ctypes.POINTER(vp), lp],
         "htm_last_run_stats": [vp, dp, lp, lp],
         "htm_measure_fp32_peak": [i32, dp, dp],
+        "htm_measure_fp64_peak": [i32, dp],
         "htm_comm_unique_id": [ctypes.c_char_p],
         "htm_comm_init": [vp, ctypes.c_char_p],
         "htm_gather": [vp, ctypes.POINTER(ctypes.c_uint32), lp, lp],
@@ -118,6 +119,15 @@ def measure_fp32_peak(device=0):
     if rc != HTM_OK:
         raise HtmError(rc, "htm_measure_fp32_peak failed (no CUDA device?)")
     return tf.value, mu.value
+
+
+def measure_fp64_peak(device=0):
+    lib = load_library()
+    tf = ctypes.c_double()
+    rc = lib.htm_measure_fp64_peak(device, ctypes.byref(tf))
+    if rc != HTM_OK:
+        raise HtmError(rc, "htm_measure_fp64_peak failed (no CUDA device?)")
+    return tf.value
 
 
 class HypoTremorB200:

@@ -1691,4 +1691,12 @@ int32_t htm_measure_fp32_peak(int32_t device, double* tflops, double* mufu_gops)
   return HTM_OK;
 }
 
+int32_t htm_measure_fp64_peak(int32_t device, double* tflops) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(nullptr, HTM_ERR_CUDA, "no CUDA device");
+  cudaError_t e = measure_fp64_peak(device, tflops);
+  if (e != cudaSuccess) return fail(nullptr, HTM_ERR_CUDA, cudaGetErrorString(e));
+  return HTM_OK;
+}
+
 }  // extern "C"

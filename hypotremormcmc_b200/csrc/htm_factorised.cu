@@ -472,6 +472,203 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
 }
 
 // ================================================================================================
+// Wide-group kernel: tempering groups of MORE than 32 chains (the reference puts no limit on n_chains,
+// src/hypo_tremor_mcmc.f90:114-118).  CTA = one group (event, rank): chain k sits in thread k of ceil(K/32) warps.
+// Same per-chain step as the lane kernel with one chain per lane; what a warp shuffle did there -- the swap
+// partner's (L, T), the pair and ln r of the iteration's swap attempt, the numbering of the cold chains for the
+// records -- goes through double-buffered shared memory with ONE block barrier per iteration.
+// ================================================================================================
+template <typename real, bool TRACE>
+__global__ void __launch_bounds__(1024) fact_wide_kernel(const FactParams<real> p) {
+  typedef typename M<real>::real4 real4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool kF32 = sizeof(real) == 4;
+  const int K = p.K, S = p.S, R = p.R, n_pairs = (S + 1) / 2;
+  const int k = threadIdx.x, lane = threadIdx.x & 31;
+  const int e = blockIdx.x / R, r = blockIdx.x % R;
+  const bool valid = k < K;
+  const int kk = valid ? k : K - 1;  // idle threads of the last warp clone a chain and never write
+  // shared memory: staged tables | (float32) expanded pair records | barrier | published (L, T)[2][K] | swap draw [2]
+  real4* s_sta = reinterpret_cast<real4*>(smem_raw);
+  real4* s_obs = s_sta + S;
+  float4* s_x = reinterpret_cast<float4*>(s_obs + S);
+  unsigned char* after = reinterpret_cast<unsigned char*>(kF32 ? reinterpret_cast<real4*>(s_x + 4 * n_pairs) : s_obs + S);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(after);
+  real* s_L = reinterpret_cast<real*>(bar + 2);  // [2][K]
+  real* s_T = s_L + 2 * K;                       // [2][K]
+  real* s_lr = s_T + 2 * K;                      // [2]
+  int* s_pair = reinterpret_cast<int*>(s_lr + 2);  // [2]
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+    const uint32_t bytes = static_cast<uint32_t>(S * sizeof(real4));
+    mbar_expect_tx(bar, 2 * bytes);
+    tma_load_1d(s_sta, p.sta4, bytes, bar);
+    tma_load_1d(s_obs, p.obs4 + static_cast<size_t>(e) * S, bytes, bar);
+  }
+  __syncthreads();
+  const real4 evc = p.evc4[e];
+  const typename R2<real>::type pxy = p.prior_xy[e];
+  const Glob<real> g = make_glob<real>(p.vs, p.qs);
+  const uint32_t eg = static_cast<uint32_t>(e) + p.event_offset;
+  const size_t ci = (static_cast<size_t>(e) * R + r) * K + kk;
+  const uint32_t gid = (eg * R + r) * K + kk, grp = eg * R + r;
+  real x = p.x[ci], y = p.y[ci], z = p.z[ci], L = p.L[ci], T = p.T[ci];
+  uint32_t cnt_p[3] = {0, 0, 0}, cnt_a[3] = {0, 0, 0};
+  mbar_wait(bar, 0);
+  if constexpr (kF32) {  // expand the staged tables into packed station-pair records (htm_forward.cuh), once
+    const float4* st = reinterpret_cast<const float4*>(s_sta);
+    const float4* ob = reinterpret_cast<const float4*>(s_obs);
+    for (int m = threadIdx.x; m < n_pairs; m += blockDim.x) {
+      const int j0 = 2 * m, j1 = j0 + 1;
+      const StaRecF a = expand_station(st[j0], ob[j0], pxy.x, pxy.y);
+      StaRecF b = a;
+      if (j1 < S)
+        b = expand_station(st[j1], ob[j1], pxy.x, pxy.y);
+      else
+        b.B = make_float4(0.f, 0.f, 0.f, 0.f);
+      store_station_pair(s_x + 4 * m, a, b);
+    }
+    __syncthreads();
+  }
+  // float32: the chain carries the (negated) weighted mean residuals of its accepted state as the shift
+  float nct[1] = {0.f}, nca[1] = {0.f};
+  if constexpr (kF32) {
+    const float hx[1] = {x - pxy.x}, hy[1] = {y - pxy.y}, hz[1] = {z}, z0[1] = {0.f};
+    float a1t[1], a1a[1], a2[1];
+    forward_pairs<1>(s_x, n_pairs, hx, hy, hz, g, z0, z0, a1t, a1a, a2);
+    nct[0] = -a1t[0] * evc.y;
+    nca[0] = -a1a[0] * evc.z;
+  }
+  for (int it = p.iter_first; it <= p.iter_last; ++it) {
+    const int buf = it & 1;
+    const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(it), gid, PHX_STEP, 0u);
+    int icmp;
+    real nx, ny, nz, lpr;
+    bool ok;
+    propose_hypo<real>(w, x, y, z, pxy.x, pxy.y, p, icmp, nx, ny, nz, lpr, ok);
+    real S1t, S1a, S2;
+    if constexpr (kF32) {
+      const float hx[1] = {nx - pxy.x}, hy[1] = {ny - pxy.y}, hz[1] = {nz};
+      float a1t[1], a1a[1], a2[1];
+      forward_pairs<1>(s_x, n_pairs, hx, hy, hz, g, nct, nca, a1t, a1a, a2);
+      S1t = a1t[0];
+      S1a = a1a[0];
+      S2 = a2[0];
+    } else {
+      real ct, ca;
+      station_resid(nx, ny, nz, g, s_sta[0], s_obs[0], static_cast<real>(0), static_cast<real>(0), ct, ca);
+      S1t = S1a = S2 = 0;
+      for (int j = 1; j < S; ++j) station_accum(nx, ny, nz, g, -ct, -ca, s_sta[j], s_obs[j], S1t, S1a, S2);
+    }
+    const real Lnew = finish_loglik<real>(S1t, S2, S1a, static_cast<real>(0), evc);
+    const bool acc = judge<real>(Lnew, L, T, lpr, ok, w.v[3]);
+    const bool cold = is_cold<real>(T);
+    if (cold && valid) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        cnt_p[c] += (icmp == c) ? 1u : 0u;
+        cnt_a[c] += (acc && icmp == c) ? 1u : 0u;
+      }
+    }
+    if (acc) {
+      x = nx;
+      y = ny;
+      z = nz;
+      L = Lnew;
+      if constexpr (kF32) {
+        nct[0] = fmaf(-static_cast<float>(S1t), static_cast<float>(evc.y), nct[0]);
+        nca[0] = fmaf(-static_cast<float>(S1a), static_cast<float>(evc.z), nca[0]);
+      }
+    }
+    if (TRACE) {
+      if (valid && p.trace) {
+        htm_step_trace t;
+        t.proposal_type = 5 + icmp;
+        t.index = 3 * (e + 1) - icmp;
+        t.prior_ok = ok ? 1 : 0;
+        t.accepted = acc ? 1 : 0;
+        t.log_likelihood = static_cast<double>(L);
+        p.trace[static_cast<size_t>(it - p.iter_first) * p.E * R * K + ci] = t;
+      }
+    }
+    // publish (L, T) and the iteration's swap attempt; one barrier; then everyone reads
+    if (valid) {
+      s_L[buf * K + k] = L;
+      s_T[buf * K + k] = T;
+    }
+    if (k == 0) {
+      const u32x4 ws = philox4x32_10(p.rk, static_cast<uint32_t>(it), grp, PHX_SWAP, 0u);
+      const int i1 = static_cast<int>(below(ws.v[0], static_cast<uint32_t>(K)));
+      int i2 = i1 + 1 + static_cast<int>(below(ws.v[1], static_cast<uint32_t>(K - 1)));
+      if (i2 >= K) i2 -= K;
+      const real ru = M<real>::u_co(ws.v[2]);
+      s_pair[buf] = i1 | (i2 << 16);
+      s_lr[buf] = ru > static_cast<real>(0) ? M<real>::log(ru) : static_cast<real>(3.0e38);  // r = 0 never accepts
+    }
+    __syncthreads();
+    const real* bL = s_L + buf * K;
+    const real* bT = s_T + buf * K;
+    // record (src/hypo_tremor_mcmc.f90:270-280): slot m = this chain's rank among the group's cold chains
+    if (p.n_interval > 1 && (it % p.n_interval) == 1 && cold && valid) {
+      int m = 0;
+      for (int q = 0; q < k; ++q) m += is_cold<real>(bT[q]) ? 1 : 0;
+      const int slot = (it - 1) / p.n_interval - p.rec_origin;
+      if (p.samples && slot >= 0 && slot < p.rec_cap && m < p.n_cool) {
+        real4 rec;
+        rec.x = x;
+        rec.y = y;
+        rec.z = z;
+        rec.w = L;
+        p.samples[((static_cast<size_t>(slot) * R + r) * p.n_cool + m) * p.E + e] = rec;
+      }
+      if (p.hist && it > p.n_burn) hist_add<real>(p, e, x, y, z, pxy.x, pxy.y);
+    }
+    // swap inside the group (src/cls_parallel.f90:100-216, 285-302): temperatures are exchanged
+    {
+      const int i1 = s_pair[buf] & 0xffff, i2 = s_pair[buf] >> 16;
+      const real L1 = bL[i1], L2 = bL[i2], T1 = bT[i1], T2 = bT[i2];
+      const real del_s = (L2 - L1) * (static_cast<real>(1) / T1 - static_cast<real>(1) / T2);
+      const bool sacc = s_lr[buf] <= del_s;
+      if (sacc && valid) {
+        if (k == i1)
+          T = T2;
+        else if (k == i2)
+          T = T1;
+      }
+      if (TRACE) {
+        if (k == 0 && p.swaps) {
+          htm_swap_trace t;
+          t.rank1 = r;
+          t.chain1 = i1 + 1;
+          t.rank2 = r;
+          t.chain2 = i2 + 1;
+          t.accepted = sacc ? 1 : 0;
+          t.reserved = 0;
+          p.swaps[(static_cast<size_t>(it - p.iter_first) * p.E + e) * R + r] = t;
+        }
+      }
+    }
+  }
+  if (valid) {
+    p.x[ci] = x;
+    p.y[ci] = y;
+    p.z[ci] = z;
+    p.L[ci] = L;
+    p.T[ci] = T;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const uint32_t sp = warp_sum<uint32_t>(cnt_p[c]), sa = warp_sum<uint32_t>(cnt_a[c]);
+    if (lane == 0 && p.counts) {
+      if (sp) atomicAdd(p.counts + 4 + c, static_cast<unsigned long long>(sp));
+      if (sa) atomicAdd(p.counts + 7 + 4 + c, static_cast<unsigned long long>(sa));
+    }
+  }
+}
+
+// ================================================================================================
 // Warp-per-chain kernel.  CTA = gpc tempering groups x K warps, all of ONE event.
 // ================================================================================================
 template <typename real, int SPL, bool TRACE>
@@ -807,10 +1004,43 @@ static cudaError_t launch_warp(const FactLaunch& a, cudaStream_t stream) {
 }
 
 template <typename real>
-static cudaError_t launch_factorised_t(const FactLaunch& a, cudaStream_t stream, const char** why) {
-  if (a.K > 32) {
-    *why = "factorised mode supports at most 32 chains per tempering group (n_chains <= 32)";
+static cudaError_t launch_wide(const FactLaunch& a, cudaStream_t stream, const char** why) {
+  typedef typename M<real>::real4 real4;
+  if (a.K > 1024) {
+    *why = "factorised mode supports at most 1024 chains per tempering group (one CTA per group)";
     return cudaErrorInvalidValue;
+  }
+  const FactParams<real> p = make_params<real>(a);
+  const int n_pairs = (a.S + 1) / 2;
+  const size_t smem = 2 * a.S * sizeof(real4) + (sizeof(real) == 4 ? 4 * n_pairs * sizeof(float4) : 0) + 2 * sizeof(uint64_t) +
+                      (4 * a.K + 2) * sizeof(real) + 2 * sizeof(int) + 16;
+  if (smem > 200 * 1024) {
+    *why = "n_sta too large for the shared-memory staging of the wide-group kernel";
+    return cudaErrorInvalidValue;
+  }
+  const unsigned grid = static_cast<unsigned>(a.E) * a.R, block = static_cast<unsigned>((a.K + 31) / 32 * 32);
+  const bool trace = a.trace || a.swaps;
+  cudaError_t err;
+  if (trace) {
+    err = cudaFuncSetAttribute(fact_wide_kernel<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    fact_wide_kernel<real, true><<<grid, block, smem, stream>>>(p);
+  } else {
+    err = cudaFuncSetAttribute(fact_wide_kernel<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    fact_wide_kernel<real, false><<<grid, block, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+template <typename real>
+static cudaError_t launch_factorised_t(const FactLaunch& a, cudaStream_t stream, const char** why) {
+  if (a.K > 32) {  // a tempering group wider than a warp: one CTA per group
+    if (a.kernel == HTM_KERNEL_WARP_PER_CHAIN) {
+      *why = "warp-per-chain kernel supports n_chains <= 16 (one CTA of <= 512 threads per tempering group)";
+      return cudaErrorInvalidValue;
+    }
+    return launch_wide<real>(a, stream, why);
   }
   if (a.kernel == HTM_KERNEL_WARP_PER_CHAIN) {
     if (a.K > 16) {

@@ -179,5 +179,6 @@ bool nccl_allreduce_u64(void* comm, const void* send, void* recv, size_t count, 
 
 // FFMA / MUFU microbenchmark (roofline denominators)
 cudaError_t measure_fp32_peak(int device, double* tflops, double* mufu_gops);
+cudaError_t measure_fp64_peak(int device, double* tflops);
 
 }  // namespace htm

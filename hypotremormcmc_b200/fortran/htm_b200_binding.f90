@@ -326,6 +326,13 @@ module htm_b200_binding
        integer(c_int32_t) :: rc
      end function htm_comm_p2p_import
 
+     function htm_measure_fp64_peak(device, tflops) bind(c, name="htm_measure_fp64_peak") result(rc)
+       import
+       integer(c_int32_t), value :: device
+       real(c_double), intent(out) :: tflops
+       integer(c_int32_t) :: rc
+     end function htm_measure_fp64_peak
+
      function htm_measure_fp32_peak(device, tflops, mufu_gops) &
           & bind(c, name="htm_measure_fp32_peak") result(rc)
        import

@@ -333,6 +333,8 @@ int32_t htm_last_run_stats(htm_handle h, double* ms, int64_t* n_launches,
 /* FFMA/MUFU microbenchmark used as the FP32 roofline denominator (no driver-measured
  * FP32 vector peak exists).  Returns TFLOP/s (FFMA = 2 flops). */
 int32_t htm_measure_fp32_peak(int32_t device, double* tflops, double* mufu_gops);
+/* The same for the float64 instantiations (the validation path): DFMA microbenchmark, TFLOP/s. */
+int32_t htm_measure_fp64_peak(int32_t device, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -226,6 +226,46 @@ def test_factorised_float64_step_exact(kernel, slots, E, S, R, K):
     assert hist.sum() == 3 * n_rec_post * E
 
 
+@pytest.mark.parametrize("E,S,R,K,n_cool", [(3, 9, 2, 33, 1), (2, 20, 1, 70, 3), (4, 7, 3, 128, 2)])
+def test_factorised_wide_groups_float64_step_exact(E, S, R, K, n_cool):
+    """Tempering groups of more than 32 chains (the reference has no limit on n_chains): one CTA per group, swap and
+    record numbering through shared memory (fact_wide_kernel) -- step-exact against the oracle like the others."""
+    syn = H.Synthetic(E, S, 90 + K)
+    cfg = fact_cfg(E, S, R, K, precision=64, n_iter=60, n_interval=6, n_burn=12, n_cool=n_cool, max_samples=16, hist_bins=8)
+    o = Oracle(cfg, syn)
+    o.init_chains()
+    tr_o, sw_o = o.run(1, 60)
+    with H.HypoTremorB200(cfg) as g:
+        g.load(syn)
+        g.init_chains()
+        tr_g, sw_g = g.run_traced(1, 35)
+        tr_g2, sw_g2 = g.run_traced(36, 60)
+        cg = g.get_counts()
+        smp = [g.fetch_samples(r) for r in range(R)]
+        lik = [g.fetch_likelihood(r) for r in range(R)]
+    tr_g, sw_g = np.concatenate([tr_g, tr_g2]), np.concatenate([sw_g, sw_g2])
+    for f in FLAGS:
+        assert np.array_equal(tr_o[f], tr_g[f]), f
+    assert np.array_equal(sw_o, sw_g) and rel(tr_g["log_likelihood"], tr_o["log_likelihood"]) <= 1e-9
+    co = o.get_counts()
+    assert np.array_equal(co[0], cg[0]) and np.array_equal(co[1], cg[1])
+    for r in range(R):
+        so = o.fetch_samples(r)
+        assert np.array_equal(so["iter"], smp[r]["iter"]) and np.allclose(so["hypo"], smp[r]["hypo"], rtol=1e-10, atol=1e-10)
+        lo = o.fetch_likelihood(r)
+        assert np.array_equal(lo[0], lik[r][0]) and np.allclose(lo[1], lik[r][1], rtol=1e-10)
+    # float32: runs, counts every cold proposal, keeps the temperature multiset
+    c32 = H.copy_config(cfg, precision=32, max_samples=64)
+    with H.HypoTremorB200(c32) as g:
+        g.load(syn)
+        g.init_chains()
+        t0 = sorted(g.get_chain_state(0, k)["temp"] for k in range(K))
+        g.run(1, 300)
+        p, a = g.get_counts()
+        t1 = sorted(g.get_chain_state(0, k)["temp"] for k in range(K))
+    assert p[4:].sum() == 300 * E * R * n_cool and 0 < a.sum() < p.sum() and t0 == t1
+
+
 def test_factorised_two_cold_chains_and_geometric_ladder():
     syn = H.Synthetic(4, 15, 3)
     cfg = H.default_config(n_sta=15, n_events=4, n_procs=2, n_chains=6, n_cool=2, n_iter=60, n_burn=0, n_interval=6,
@@ -811,7 +851,7 @@ def test_argument_and_state_errors():
         g.run(41, 80)
         with pytest.raises(H.HtmError):                 # wrong mode
             g.replay(1, 2, [np.zeros(4, dtype=np.int32)] * 2)
-    big = fact_cfg(2, 6, 1, 33)                          # n_chains > 32 in factorised mode
+    big = fact_cfg(2, 6, 1, 1025)                        # one CTA per tempering group: n_chains <= 1024
     with H.HypoTremorB200(big) as g:
         g.load(H.Synthetic(2, 6, 1))
         g.init_chains()
