@@ -3,7 +3,11 @@
 // same order, so the boundary is exercised end to end in an image that has no Fortran compiler.
 //
 //   hypo_tremor_mcmc_b200 <parameter file> [--precision 32|64] [--seed N] [--little-endian]
-//                         [--chunk RECORDS] [--dry-run] [--loader-threads N]
+//                         [--chunk RECORDS] [--dry-run] [--loader-threads N] [--summary]
+//
+// --summary additionally writes hypo.stat, station_corrections.stat and uniform_structure.stat -- the tables
+// hypo_tremor_statistics computes from the .out files (src/cls_statistics.f90:216-264,345-431) -- from the
+// device-side posterior store (htm_posterior_quantiles), without re-reading the samples.
 //
 // Inputs in the working directory as for the reference (src/hypo_tremor_mcmc.f90:53-98): the
 // parameter file's station_file, selected_win.dat, opt_data.NNNNNN.dat.  Outputs: hypo.RR.out,
@@ -31,7 +35,7 @@ int main(int argc, char** argv) {
   std::string param_file;
   int precision = 32, chunk = 0;  // 0 = choose from the record size
   unsigned long long seed = 20231001ull;
-  bool big_endian = true, dry = false;
+  bool big_endian = true, dry = false, summary = false;
   unsigned loader_threads = 0;  // 0 = all host cores
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -40,6 +44,7 @@ int main(int argc, char** argv) {
     else if (a == "--chunk" && i + 1 < argc) chunk = std::atoi(argv[++i]);
     else if (a == "--little-endian") big_endian = false;
     else if (a == "--dry-run") dry = true;
+    else if (a == "--summary") summary = true;
     else if (a == "--loader-threads" && i + 1 < argc) loader_threads = static_cast<unsigned>(std::atoi(argv[++i]));
     else if (param_file.empty()) param_file = a;
     else param_file = "?";
@@ -108,6 +113,7 @@ int main(int argc, char** argv) {
       chunk = static_cast<int>(std::max(1.0, std::min(64.0, 2.56e8 / per_rec - 1.0)));
     }
     cfg.max_samples = chunk + 1;
+    cfg.summary = summary ? 1 : 0;
 
     if (dry) {  // parse-only: what the driver understood, as JSON (used by the CPU tests)
       std::printf("{\"n_sta\": %d, \"n_events\": %d, \"n_procs\": %d, \"n_chains\": %d, \"n_cool\": %d, "
@@ -176,6 +182,36 @@ int main(int argc, char** argv) {
     FILE* pc = std::fopen("proposal_count.txt", "w");
     for (int k = 0; k < 7; ++k) std::fprintf(pc, "\"%s\"%20lld%20lld\n", label[k], static_cast<long long>(np[k]), static_cast<long long>(na[k]));
     std::fclose(pc);
+    if (summary) {
+      int32_t n_mod = 0;
+      std::vector<double> hq(static_cast<size_t>(9) * n_events), vq(3), qq(3), tq(static_cast<size_t>(3) * n_sta),
+          aq(static_cast<size_t>(3) * n_sta);
+      check(h, htm_posterior_quantiles(h, &n_mod, hq.data(), vq.data(), qq.data(), tq.data(), aq.data()), "htm_posterior_quantiles");
+      FILE* f = std::fopen("hypo.stat", "w");   // '(I9,9F13.6)', src/cls_statistics.f90:244-255
+      std::fprintf(f, "# window ID, x (50%%), x (2.5%%) x (97.5%%), y (50%%), y (2.5%%), y (97.5%%)z (50 %%), z (2.5%%), z (97.5%%)\n");
+      for (int i = 0; i < n_events; ++i) {
+        std::fprintf(f, "%9d", win_id[i]);
+        for (int k = 0; k < 9; ++k) std::fprintf(f, "%13.6f", hq[static_cast<size_t>(9) * i + k]);
+        std::fprintf(f, "\n");
+      }
+      std::fclose(f);
+      f = std::fopen("station_corrections.stat", "w");   // '(A12,6F13.6)', :373-381
+      std::fprintf(f, "# station name, t_corr (50%%), t_corr (2.5%%) t_corr (97.5%%), a_corr (50%%), a_corr (2.5%%), a_corr (97.5%%)\n");
+      for (int j = 0; j < n_sta; ++j) {
+        std::fprintf(f, "%12.12s", sta.name[j].c_str());
+        for (int k = 0; k < 3; ++k) std::fprintf(f, "%13.6f", tq[static_cast<size_t>(3) * j + k]);
+        for (int k = 0; k < 3; ++k) std::fprintf(f, "%13.6f", aq[static_cast<size_t>(3) * j + k]);
+        std::fprintf(f, "\n");
+      }
+      std::fclose(f);
+      f = std::fopen("uniform_structure.stat", "w");   // '(6F13.6)', :419-423
+      std::fprintf(f, "# Vs (50%%), Vs (2.5%%) Vs (97.5%%), Qs (50%%), Qs (2.5%%), Qs (97.5%%)\n");
+      for (int k = 0; k < 3; ++k) std::fprintf(f, "%13.6f", vq[k]);
+      for (int k = 0; k < 3; ++k) std::fprintf(f, "%13.6f", qq[k]);
+      std::fprintf(f, "\n");
+      std::fclose(f);
+      std::fprintf(stderr, "posterior summary of %d samples written\n", n_mod);
+    }
     for (int r = 0; r < R; ++r) {
       f_hypo[r].close();
       f_tc[r].close();

@@ -104,8 +104,10 @@ def test_driver_end_to_end(tmp_path, solve):
     cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=2000, n_burn=500, n_interval=10,
                            **kw)
     hio.write_dataset(str(tmp_path), syn, cfg)
-    r = run_driver(tmp_path, "--chunk", "37")
+    r = run_driver(tmp_path, "--chunk", "37", "--summary")
     assert r.returncode == 0, r.stderr
+    # the statistics stage's three tables straight from the device-side store
+    dev_stat = {f: open(tmp_path / f).read() for f in ("hypo.stat", "station_corrections.stat", "uniform_structure.stat")}
     out = hio.read_outputs(str(tmp_path), R, E, S)
     n_mod = (cfg.n_iter - cfg.n_burn) * R * cfg.n_cool // cfg.n_interval     # src/cls_statistics.f90:65
     for k in ("hypo", "t_corr", "vs", "a_corr", "qs"):
@@ -131,6 +133,9 @@ def test_driver_end_to_end(tmp_path, solve):
     assert np.array_equal(np.concatenate([x["vs"] for x in s]), out["vs"][:, 0])
     # the statistics stage's tables from these files: medians bracketed by the 2.5 / 97.5 % bounds
     hio.write_stat_files(str(tmp_path), out, list(range(1, E + 1)), ["ST%02d" % j for j in range(S)])
+    # ... equal, character for character, the tables computed from the .out files the way hypo_tremor_statistics does
+    for f, text in dev_stat.items():
+        assert open(tmp_path / f).read() == text, f
     rows = [ln for ln in open(tmp_path / "hypo.stat").read().splitlines()[1:]]
     assert len(rows) == E
     for ln in rows:

@@ -7,8 +7,8 @@
     sample's step sizes, n_chains 5, n_cool 1, temp_high 200) and n_procs = 4 -- the float32 blocked-Gibbs kernel
     against the oracle's mode A (the reference's own schedule and mod_random), all 25 marginals
     (x, y, z, vs, qs, 10 t_corr, 10 a_corr).
-(b) configs[1] and configs[2] at FULL size on the GPU (float32 lane kernel) against the float64 oracle on a subset of
-    100 of the same events (events are independent when solve_* = F and Philox ids are global, so the oracle runs
+(b) configs[1], configs[2] and a configs[3]-sized catalogue (100 000 events x 50 stations on one GPU) at FULL size on
+    the GPU (float32 lane kernel) against the float64 oracle on a subset of 100 of the same events (events are independent when solve_* = F and Philox ids are global, so the oracle runs
     exactly those events' chains).
 """
 from concurrent.futures import ThreadPoolExecutor
@@ -81,39 +81,49 @@ def subset(syn, lo, n):
     return sub
 
 
-@pytest.mark.parametrize("E,S,n_it,burn,interval", [(1000, 20, 12000, 2000, 5), (10000, 50, 6000, 1000, 5)],
-                         ids=["configs1", "configs2"])
+@pytest.mark.parametrize("E,S,n_it,burn,interval", [(1000, 20, 12000, 2000, 5), (10000, 50, 6000, 1000, 5),
+                                                    (100000, 50, 6000, 1000, 5)],
+                         ids=["configs1", "configs2", "configs3_size_on_one_gpu"])
 def test_full_size_float32_vs_float64_oracle_on_100_events(E, S, n_it, burn, interval):
-    R, K, n_sub, n_blocks = 4, 16, 100, 10
+    R, K, n_sub, n_blocks, chunk = 4, 16, 100, 10, 50
     syn = H.Synthetic(E, S, 20231001 + (2 if E == 1000 else 3))
     cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=n_it, n_burn=burn,
                            n_interval=interval, mode=H.MODE_FACTORISED, precision=32, seed=77,
-                           max_samples=n_it // interval + 2, **NOSOLVE)
+                           max_samples=chunk + 1, **NOSOLVE)
     picks = [(E // n_blocks) * b + 7 for b in range(n_blocks)]      # ten blocks of ten events spread over the catalogue
+    nb = n_sub // n_blocks
+    cols = np.concatenate([np.arange(3 * lo, 3 * (lo + nb)) for lo in picks])
 
     def run_block(lo):
-        nb = n_sub // n_blocks
-        o = Oracle(H.copy_config(cfg, precision=64, n_events=nb), subset(syn, lo, nb), event_offset=lo)
+        o = Oracle(H.copy_config(cfg, precision=64, n_events=nb, max_samples=0), subset(syn, lo, nb), event_offset=lo)
         o.init_chains()
         o.run(1, n_it, trace=False)
         return [o.fetch_samples(r)["hypo"] for r in range(R)]
 
     with ThreadPoolExecutor(max_workers=n_blocks) as pool:        # the oracle call releases the GIL
         fut = [pool.submit(run_block, lo) for lo in picks]
+        parts = [[] for _ in range(R)]
         with H.HypoTremorB200(cfg) as g:
             g.load(syn)
             g.init_chains()
-            g.run(1, n_it)
-            sg = [g.fetch_samples(r)["hypo"] for r in range(R)]
+            it0 = 1
+            while it0 <= n_it:                                     # drained in chunks like the driver does; only the
+                it1 = min(n_it, it0 + chunk * interval - 1)        # subset's columns are kept
+                g.run(it0, it1)
+                for r in range(R):
+                    parts[r].append(g.fetch_samples(r)["hypo"][:, cols].copy())
+                    g.fetch_likelihood(r)
+                it0 = it1 + 1
+        sg = [np.concatenate(p) for p in parts]
         so = [f.result() for f in fut]
-    assert sg[0].shape == ((n_it - burn) // interval, 3 * E)
+    assert sg[0].shape == ((n_it - burn) // interval, 3 * n_sub)
     bad, n_marg = [], 0
     for b, lo in enumerate(picks):
-        for e in range(n_sub // n_blocks):
+        for e in range(nb):
             for c in range(3):
                 n_marg += 1
                 r = compare_marginal([so[b][rk][:, 3 * e + c] for rk in range(R)],
-                                     [sg[rk][:, 3 * (lo + e) + c] for rk in range(R)])
+                                     [sg[rk][:, 3 * (b * nb + e) + c] for rk in range(R)])
                 if not r["ok"]:
                     bad.append((lo + e, c, r["D"], r["D_max"], r["n_eff"]))
     assert n_marg == 300 and len(bad) <= 3, bad           # >= 99 % of the marginals
