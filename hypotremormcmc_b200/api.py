@@ -24,7 +24,7 @@ EXPORTS = [
     "htm_discard_samples", "htm_get_counts", "htm_get_histograms", "htm_device_ptr",
     "htm_last_run_stats", "htm_measure_fp32_peak", "htm_comm_unique_id", "htm_comm_init", "htm_gather",
     "htm_comm_p2p_export", "htm_comm_p2p_import", "htm_gather_samples", "htm_gibbs_pending", "htm_gibbs_last_sums",
-    "htm_posterior_quantiles", "htm_measure_fp64_peak",
+    "htm_posterior_quantiles", "htm_measure_fp64_peak", "htm_select_events",
 ]
 
 
@@ -83,6 +83,8 @@ def load_library():
         "htm_last_run_stats": [vp, dp, lp, lp],
         "htm_measure_fp32_peak": [i32, dp, dp],
         "htm_measure_fp64_peak": [i32, dp],
+        "htm_select_events": [i32, i32, i32, dp, dp, dp, ctypes.c_double, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double,
+                              ctypes.c_double, ctypes.c_double, dp, dp, dp, dp, dp, dp, ip, dp],
         "htm_comm_unique_id": [ctypes.c_char_p],
         "htm_comm_init": [vp, ctypes.c_char_p],
         "htm_gather": [vp, ctypes.POINTER(ctypes.c_uint32), lp, lp],
@@ -119,6 +121,27 @@ def measure_fp32_peak(device=0):
     if rc != HTM_OK:
         raise HtmError(rc, "htm_measure_fp32_peak failed (no CUDA device?)")
     return tf.value, mu.value
+
+
+def select_events(sta_x, sta_y, sta_z, z_guess, t, t_err, a, a_err, vs_min=2.0, vs_max=4.0, b_min=0.015, b_max=0.03,
+                  device=0):
+    """hypo_tremor_select for all windows at once (defaults: sample/hypo_tremor.in:109-117).  t, t_err, a, a_err:
+    [n_events, n_sta].  Returns dict(vs, t0, b, a0, cc_t, cc_a, selected, kernel_ms)."""
+    lib = load_library()
+    t = _f64(t)
+    E, S = t.shape
+    arr = [_f64(v, (S,)) for v in (sta_x, sta_y, sta_z)] + [t] + [_f64(v, (E, S)) for v in (t_err, a, a_err)]
+    out = [np.empty(E) for _ in range(6)]
+    sel = np.zeros(E, dtype=np.int32)
+    ms = ctypes.c_double()
+    rc = lib.htm_select_events(device, S, E, _dptr(arr[0]), _dptr(arr[1]), _dptr(arr[2]), z_guess, _dptr(arr[3]),
+                               _dptr(arr[4]), _dptr(arr[5]), _dptr(arr[6]), vs_min, vs_max, b_min, b_max,
+                               *[_dptr(o) for o in out], sel.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ctypes.byref(ms))
+    if rc != HTM_OK:
+        buf = ctypes.create_string_buffer(512)
+        lib.htm_last_error(None, buf, 512)
+        raise HtmError(rc, buf.value.decode())
+    return dict(vs=out[0], t0=out[1], b=out[2], a0=out[3], cc_t=out[4], cc_a=out[5], selected=sel, kernel_ms=ms.value)
 
 
 def measure_fp64_peak(device=0):

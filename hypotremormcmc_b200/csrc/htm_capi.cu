@@ -1691,6 +1691,82 @@ int32_t htm_measure_fp32_peak(int32_t device, double* tflops, double* mufu_gops)
   return HTM_OK;
 }
 
+int32_t htm_select_events(int32_t device, int32_t n_sta, int32_t n_events, const double* sta_x, const double* sta_y,
+                          const double* sta_z, double z_guess, const double* t, const double* t_err, const double* a,
+                          const double* a_err, double vs_min, double vs_max, double b_min, double b_max, double* vs,
+                          double* t0, double* b, double* a0, double* cc_t, double* cc_a, int32_t* selected,
+                          double* kernel_ms) {
+  if (!sta_x || !sta_y || !sta_z || !t || !t_err || !a || !a_err || !vs || !t0 || !b || !a0 || !cc_t || !cc_a || !selected)
+    return fail(nullptr, HTM_ERR_ARG, "null argument");
+  if (n_sta < 3 || n_events < 1) return fail(nullptr, HTM_ERR_ARG, "need n_sta >= 3 and n_events >= 1");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(nullptr, HTM_ERR_CUDA, "no CUDA device (libhtm_b200 has no CPU fallback)");
+  if (device < 0 || device >= n_dev) return fail(nullptr, HTM_ERR_ARG, "device ordinal out of range");
+  cudaError_t e = cudaSetDevice(device);
+  const size_t S = n_sta, ES = static_cast<size_t>(n_events) * n_sta, E = n_events;
+  double *d_in = nullptr, *d_out = nullptr;
+  int32_t* d_sel = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaMalloc(&d_in, (3 * S + 4 * ES) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, 6 * E * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_sel, E * sizeof(int32_t));
+  const double* src[7] = {sta_x, sta_y, sta_z, t, t_err, a, a_err};
+  size_t off = 0;
+  for (int k = 0; k < 7 && e == cudaSuccess; ++k) {
+    const size_t n = k < 3 ? S : ES;
+    e = cudaMemcpyAsync(d_in + off, src[k], n * sizeof(double), cudaMemcpyHostToDevice, st);
+    off += n;
+  }
+  SelectArgs sa;
+  sa.E = n_events;
+  sa.S = n_sta;
+  sa.sta_x = d_in;
+  sa.sta_y = d_in + S;
+  sa.sta_z = d_in + 2 * S;
+  sa.t = d_in + 3 * S;
+  sa.t_err = sa.t + ES;
+  sa.a = sa.t_err + ES;
+  sa.a_err = sa.a + ES;
+  sa.z_guess = z_guess;
+  sa.vs_min = vs_min;
+  sa.vs_max = vs_max;
+  sa.b_min = b_min;
+  sa.b_max = b_max;
+  sa.vs = d_out;
+  sa.t0 = d_out + E;
+  sa.b = d_out + 2 * E;
+  sa.a0 = d_out + 3 * E;
+  sa.cc_t = d_out + 4 * E;
+  sa.cc_a = d_out + 5 * E;
+  sa.selected = d_sel;
+  if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+  if (e == cudaSuccess) e = launch_select(sa, st);
+  if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+  double* dst[6] = {vs, t0, b, a0, cc_t, cc_a};
+  for (int k = 0; k < 6 && e == cudaSuccess; ++k)
+    e = cudaMemcpyAsync(dst[k], d_out + k * E, E * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(selected, d_sel, E * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && kernel_ms) {
+    float ms = 0;
+    e = cudaEventElapsedTime(&ms, e0, e1);
+    *kernel_ms = ms;
+  }
+  free_dev(d_in);
+  free_dev(d_out);
+  free_dev(d_sel);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (st) cudaStreamDestroy(st);
+  if (e != cudaSuccess) return fail(nullptr, HTM_ERR_CUDA, std::string("htm_select_events: ") + cudaGetErrorString(e));
+  return HTM_OK;
+}
+
 int32_t htm_measure_fp64_peak(int32_t device, double* tflops) {
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(nullptr, HTM_ERR_CUDA, "no CUDA device");

@@ -177,6 +177,17 @@ bool nccl_allgather_u32(void* comm, const void* send, void* recv, size_t count, 
 bool nccl_allreduce_f64(void* comm, const void* send, void* recv, size_t count, cudaStream_t s, std::string* why);
 bool nccl_allreduce_u64(void* comm, const void* send, void* recv, size_t count, cudaStream_t s, std::string* why);
 
+// upstream QC stage hypo_tremor_select, batched (htm_select.cu); all pointers are device memory
+struct SelectArgs {
+  int E = 0, S = 0;
+  const double *sta_x = nullptr, *sta_y = nullptr, *sta_z = nullptr;                   // [S]
+  const double *t = nullptr, *t_err = nullptr, *a = nullptr, *a_err = nullptr;        // [E][S]
+  double z_guess = 0, vs_min = 0, vs_max = 0, b_min = 0, b_max = 0;
+  double *vs = nullptr, *t0 = nullptr, *b = nullptr, *a0 = nullptr, *cc_t = nullptr, *cc_a = nullptr;  // [E]
+  int32_t* selected = nullptr;                                                         // [E]
+};
+cudaError_t launch_select(const SelectArgs& a, cudaStream_t stream);
+
 // FFMA / MUFU microbenchmark (roofline denominators)
 cudaError_t measure_fp32_peak(int device, double* tflops, double* mufu_gops);
 cudaError_t measure_fp64_peak(int device, double* tflops);

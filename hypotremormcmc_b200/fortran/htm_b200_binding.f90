@@ -326,6 +326,20 @@ module htm_b200_binding
        integer(c_int32_t) :: rc
      end function htm_comm_p2p_import
 
+     ! hypo_tremor_select for all windows at once (arrays (n_sta, n_events) column-major)
+     function htm_select_events(device, n_sta, n_events, sta_x, sta_y, sta_z, z_guess, t, t_err, a, a_err, &
+          & vs_min, vs_max, b_min, b_max, vs, t0, b, a0, cc_t, cc_a, selected, kernel_ms) &
+          & bind(c, name="htm_select_events") result(rc)
+       import
+       integer(c_int32_t), value :: device, n_sta, n_events
+       real(c_double), intent(in) :: sta_x(*), sta_y(*), sta_z(*), t(*), t_err(*), a(*), a_err(*)
+       real(c_double), value :: z_guess, vs_min, vs_max, b_min, b_max
+       real(c_double), intent(out) :: vs(*), t0(*), b(*), a0(*), cc_t(*), cc_a(*)
+       integer(c_int32_t), intent(out) :: selected(*)
+       real(c_double), intent(out) :: kernel_ms
+       integer(c_int32_t) :: rc
+     end function htm_select_events
+
      function htm_measure_fp64_peak(device, tflops) bind(c, name="htm_measure_fp64_peak") result(rc)
        import
        integer(c_int32_t), value :: device

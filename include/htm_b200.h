@@ -330,6 +330,23 @@ int32_t htm_device_ptr(htm_handle h, int32_t what, void** ptr, int64_t* n_bytes)
 int32_t htm_last_run_stats(htm_handle h, double* ms, int64_t* n_launches,
                            int64_t* n_proposals);
 
+/* ---- upstream stage ---------------------------------------------------------------
+ * Replaces the loop `do i = i1, i2; call slct%eval_wave_propagation(win_id(i), vs(i), t0(i), b(i), a0(i), cc_t(i),
+ * cc_a(i))` of src/hypo_tremor_select.f90:93-96 and the acceptance test of :122-127, for all detected windows at
+ * once: per window the station of maximum log-amplitude is taken as the epicentre guess, distances use z_guess
+ * (src/cls_selector.f90:61-67), amplitudes are corrected for geometrical spreading, arrival times and amplitudes are
+ * fitted against distance with weights 1/err^2 (src/mod_regress.f90:5-38: vs = 1/slope, B = -slope) and the
+ * correlation coefficients of weighted_corr (:40-58) are formed.  t, t_err, a, a_err: [n_events][n_sta] as read from
+ * opt_data.NNNNNN.dat columns 4-7 (src/cls_selector.f90:92-95).  Outputs [n_events]; selected = 1 where
+ * vs_min <= vs <= vs_max and b_min <= B <= b_max (what the driver then writes to selected_win.dat, and all six
+ * numbers to regress.dat).  Stand-alone: no handle; float64 throughout; kernel_ms (may be NULL) receives the
+ * CUDA-event time of the kernel. */
+int32_t htm_select_events(int32_t device, int32_t n_sta, int32_t n_events, const double* sta_x, const double* sta_y,
+                          const double* sta_z, double z_guess, const double* t, const double* t_err, const double* a,
+                          const double* a_err, double vs_min, double vs_max, double b_min, double b_max, double* vs,
+                          double* t0, double* b, double* a0, double* cc_t, double* cc_a, int32_t* selected,
+                          double* kernel_ms);
+
 /* FFMA/MUFU microbenchmark used as the FP32 roofline denominator (no driver-measured
  * FP32 vector peak exists).  Returns TFLOP/s (FFMA = 2 flops). */
 int32_t htm_measure_fp32_peak(int32_t device, double* tflops, double* mufu_gops);

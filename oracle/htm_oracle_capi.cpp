@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "htm_oracle_run.hpp"
+#include "htm_oracle_select.hpp"
 
 using hto::Oracle;
 
@@ -255,6 +256,18 @@ void hto_fetch_likelihood(void* h, int32_t rank, int32_t max_records, int32_t* n
   if (lik) std::memcpy(lik, ro.lik.data() + ro.lik_fetched, n * sizeof(double));
   ro.lik_fetched += n;
   *n_records = static_cast<int32_t>(n);
+}
+
+// hypo_tremor_select for n_events windows: out [n_events][6] = vs, t0, b, a0, cc_t, cc_a; selected [n_events]
+void hto_select(int32_t S, int32_t E, const double* sta_x, const double* sta_y, const double* sta_z, double z_guess,
+                const double* t, const double* t_err, const double* a, const double* a_err, double vs_min, double vs_max,
+                double b_min, double b_max, double* out, int32_t* selected) {
+  for (int32_t e = 0; e < E; ++e) {
+    const size_t o = static_cast<size_t>(e) * S;
+    double* r = out + static_cast<size_t>(e) * 6;
+    hto::select_window(S, sta_x, sta_y, sta_z, z_guess, t + o, t_err + o, a + o, a_err + o, r);
+    selected[e] = (r[0] >= vs_min && r[0] <= vs_max && r[2] >= b_min && r[2] <= b_max) ? 1 : 0;
+  }
 }
 
 }  // extern "C"

@@ -72,6 +72,23 @@ def judge_swap(t1, t2, l1, l2, r):
     return bool(f(t1, t2, l1, l2, r))
 
 
+def select_events(sta_x, sta_y, sta_z, z_guess, t, t_err, a, a_err, vs_min=2.0, vs_max=4.0, b_min=0.015, b_max=0.03):
+    """hypo_tremor_select restated (oracle/htm_oracle_select.hpp): dict(vs, t0, b, a0, cc_t, cc_a, selected)"""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    E, S = t.shape
+    arr = [np.ascontiguousarray(v, dtype=np.float64) for v in (sta_x, sta_y, sta_z, t, t_err, a, a_err)]
+    out = np.empty((E, 6))
+    sel = np.zeros(E, dtype=np.int32)
+    f = lib().hto_select
+    dp = ctypes.POINTER(ctypes.c_double)
+    f.argtypes = [ctypes.c_int32, ctypes.c_int32, dp, dp, dp, ctypes.c_double, dp, dp, dp, dp] + [ctypes.c_double] * 4 + \
+                 [dp, ctypes.POINTER(ctypes.c_int32)]
+    f.restype = None
+    f(S, E, _d(arr[0]), _d(arr[1]), _d(arr[2]), z_guess, _d(arr[3]), _d(arr[4]), _d(arr[5]), _d(arr[6]), vs_min, vs_max,
+      b_min, b_max, _d(out), sel.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    return dict(vs=out[:, 0], t0=out[:, 1], b=out[:, 2], a0=out[:, 3], cc_t=out[:, 4], cc_a=out[:, 5], selected=sel)
+
+
 class Oracle:
     def __init__(self, cfg, syn, event_offset=0):
         self.L = lib()
