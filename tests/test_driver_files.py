@@ -48,6 +48,32 @@ def test_dry_run_parses_the_reference_formats(tmp_path):
     assert d["sta_z_last"] == pytest.approx(syn.sta_z[-1], abs=1e-8)
 
 
+def test_observation_files_are_read_one_record_per_station_line(tmp_path):
+    """`read(io,*)` of 7 items per station (src/cls_obs_data.f90:92-99): extra columns and trailing text on a line are
+    ignored, a record may continue on the next line, `r*c` repeats count -- and a short file is an error, not a shift."""
+    syn = H.Synthetic(2, 4, 9)
+    cfg = H.default_config(n_sta=4, n_events=2, n_procs=1, n_chains=2, n_iter=10, n_burn=1, n_interval=5)
+    hio.write_dataset(str(tmp_path), syn, cfg)
+    ref = json.loads(run_driver(tmp_path, "--dry-run").stdout)
+    rows = open(tmp_path / "opt_data.000001.dat").read().splitlines()
+    v = rows[0].split()
+    rows[0] = " ".join(v) + "   99.0 extra columns are ignored"          # an 8th column must not shift the next station
+    v = rows[1].split()
+    rows[1] = " ".join(v[:4]) + "\n   " + ", ".join(v[4:])               # a record continued on the next line, commas
+    open(tmp_path / "opt_data.000001.dat", "w").write("\n".join(rows) + "\n")
+    got = json.loads(run_driver(tmp_path, "--dry-run").stdout)
+    assert got == ref
+    rows2 = open(tmp_path / "opt_data.000002.dat").read().splitlines()
+    v = rows2[-1].split()
+    rows2[-1] = " ".join(v[:5]) + " 2*" + v[5]                            # a_obs and a_stdv := 2 copies of one value
+    open(tmp_path / "opt_data.000002.dat", "w").write("\n".join(rows2) + "\n")
+    got = json.loads(run_driver(tmp_path, "--dry-run").stdout)
+    assert got["a_stdv_last"] == float(v[5])
+    open(tmp_path / "opt_data.000002.dat", "w").write("\n".join(rows2[:-1]) + "\n")   # one station short
+    r = run_driver(tmp_path, "--dry-run")
+    assert r.returncode != 0 and "short obs file" in r.stderr
+
+
 def test_missing_and_unknown_keys_are_fatal(tmp_path):
     syn = H.Synthetic(2, 4, 1)
     cfg = H.default_config(n_sta=4, n_events=2)

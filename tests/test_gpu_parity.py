@@ -8,7 +8,12 @@ Tolerances (stated here because the reference states none):
   replay (mode A)  proposal type / index / prior_ok / accept flags and swap records IDENTICAL at
                    every step; |L_gpu - L_oracle| <= 1e-9 * max(1, |L|)
   factorised f64   same, against the oracle's statement of the factorised schedule
-  factorised f32   statistical: two-sample KS against float64 oracle samples
+  factorised f32   statistical: two-sample KS against float64 oracle samples (SURVEY tolerances at BASELINE sizes:
+                   tests/test_gpu_posterior.py)
+  blocked Gibbs    f64: step-exact like the others.  f32 (moment form, htm_gibbs_f32.cu): first iteration follows the
+                   f64 kernel (per-event |dL| <= 2e-3 + 3e-5 |L|, > 99.8 % equal flags); the Metropolis difference of a
+                   shared parameter at 20 000 events within 1e-2 log-likelihood units of a float64 recomputation;
+                   carried sums within 2e-5 relative; posterior: tests/test_gpu_posterior.py
 """
 import numpy as np
 import pytest
