@@ -356,6 +356,21 @@ struct F32State {
   float* Lp;
 };
 
+// -DHTM_GIBBS_PHASE_TRACE (tools/build_variants.sh + tools/gibbs_phase_trace.py): CTA (0,0) stamps globaltimer at the
+// phase boundaries of the first 4096 iterations of a launch -- where an iteration's time goes (sweep, grid barrier,
+// exchange, second barrier, decide).  Not compiled into the product library.
+#ifdef HTM_GIBBS_PHASE_TRACE
+__device__ unsigned long long g_phase_ns[8 * 4096];
+#define HTM_PHASE(k)                                                                                  \
+  do {                                                                                                \
+    if (writer && threadIdx.x == 0 && !INIT && it - iter_first < 4096) g_phase_ns[(it - iter_first) * 8 + (k)] = global_timer_ns(); \
+  } while (0)
+#else
+#define HTM_PHASE(k) \
+  do {               \
+  } while (0)
+#endif
+
 // INIT = true: generate_model for every (chain, event) (src/cls_model.f90:139-158, Philox draws as in the
 // float64 path) and its state at the initial shared parameters; no iteration is run.
 template <bool TRACE, bool INIT>
@@ -447,6 +462,7 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
       if (a_prev) cp_async4(dst + 3, gLp + ee);
       cp_async_commit();
     };
+    HTM_PHASE(0);
     if (warp_ok) prefetch(0);
     // coefficients of the chains' pending proposals (decide_core ended with a block barrier; the previous
     // iteration's reads of pq are over)
@@ -469,6 +485,7 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
     float4* const rec_row =
         rec_chain_slot >= 0 ? p.hypo_rec + (static_cast<size_t>(rec_slot) * p.n_cool_total + rec_chain_slot) * E : nullptr;
     double s_cur = 0.0, s_prop = 0.0;
+    HTM_PHASE(1);
     for (int i = 0; i < (warp_ok ? n_my : 0); ++i, ++t_run) {
       const int buf = static_cast<int>(t_run & 1);
       const uint32_t ph = static_cast<uint32_t>((t_run >> 1) & 1);
@@ -604,7 +621,15 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
         part_prop[static_cast<size_t>(c) * gridDim.x + blockIdx.x] = s_prop;
       }
     }
-    grid.sync();
+    HTM_PHASE(2);
+    // one CTA (tiny problems, e.g. BASELINE configs[0]): a block barrier orders the partial sums as well
+    if (gridDim.x * gridDim.y > 1) {
+      grid.sync();
+    } else {
+      __threadfence();
+      __syncthreads();
+    }
+    HTM_PHASE(3);
     if (INIT) {  // g_L[c] = sum_e L_e (fixed order: partials in CTA order)
       if (writer) {
         sum_partials(d.n_tiles, part_cur, part_prop, J, cs.tot);
@@ -629,7 +654,9 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
           for (int t = threadIdx.x; t < 2 * J; t += blockDim.x) totals[t] = cs.tot[t];
         __threadfence();
       }
+      HTM_PHASE(4);
       grid.sync();
+      HTM_PHASE(5);
       // a peer that never answered ends the run here, on every CTA alike (only this shard's writer sets the
       // flag, before the barrier): no decision is taken from partial sums; the host reports HTM_ERR_CUDA
       if (*reinterpret_cast<volatile int*>(d.xch.status) != 0) break;
@@ -640,6 +667,7 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
     // an accepted station-term proposal changes one entry of the chain's terms in shared memory
     if (mine && cs.aprev[c_base + threadIdx.x] && (j_which == 2 || j_which == 4))
       f32_update_chain_term(m, threadIdx.x, j_which, j_idx, j_xnew);
+    HTM_PHASE(6);
   }
   if (INIT) return;
   if (warp_ok) {
@@ -738,6 +766,15 @@ cudaError_t launch_gibbs_f32(const GibbsLaunch& a, cudaStream_t stream, int* n_l
   if (n_launches) *n_launches = 2;
   return cudaGetLastError();
 }
+
+#ifdef HTM_GIBBS_PHASE_TRACE
+}  // namespace htm
+extern "C" int32_t htm_debug_phase_trace(unsigned long long* out, int32_t n_iter) {
+  if (n_iter > 4096) n_iter = 4096;
+  return cudaMemcpyFromSymbol(out, htm::g_phase_ns, static_cast<size_t>(n_iter) * 8 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 3;
+}
+namespace htm {
+#endif
 
 // hypocentres + state of every (chain, event) at the initial shared parameters, and g_L
 cudaError_t launch_gibbs_f32_init(const GibbsLaunch& a, cudaStream_t stream) {
