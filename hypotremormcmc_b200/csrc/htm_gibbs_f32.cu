@@ -298,7 +298,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // The station terms of the CTA's chains from global memory (L2), once per launch; afterwards only the entry an
 // accepted t_corr / a_corr proposal changed is rewritten (f32_update_chain_terms).
-__device__ __forceinline__ void f32_stage_chain_terms(const F32Sm& m, const ChainSm& cs, int nc, int c_base, int J, int S) {
+__device__ __forceinline__ void f32_stage_chain_terms(const F32Sm& m, const ChainSm& cs, int nc, int c_base, int J /* first chain past the CTA's */, int S) {
   const int n_pairs = S / 2;
   for (int i = threadIdx.x; i < nc * n_pairs; i += blockDim.x) {
     const int lc = i / n_pairs, mm = i - lc * n_pairs, c = c_base + lc;
@@ -384,7 +384,12 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   const int S = p.S, J = p.J, E = p.E, n_pairs = S / 2;
   const int nc = n_warps * kQuad;
-  const int c_base = blockIdx.y * nc;
+  // the chain quads are spread EVENLY over the CTA rows (e.g. 25 quads over 4 rows: 7, 6, 6, 6 -- not 7, 7, 7, 4), so
+  // that the SMs, which hold CTAs of different rows, carry the same number of active warps
+  const int n_quads = (J + kQuad - 1) / kQuad;
+  const int q_begin = static_cast<int>(static_cast<long>(n_quads) * blockIdx.y / gridDim.y);
+  const int q_end = static_cast<int>(static_cast<long>(n_quads) * (blockIdx.y + 1) / gridDim.y);
+  const int c_base = q_begin * kQuad, c_end = min(J, q_end * kQuad);
   const bool writer = blockIdx.x == 0 && blockIdx.y == 0;
   const F32Sm m = carve_f32_sm(smem_raw, S, p.xrow, nc);
   const ChainSm cs = carve_chain_sm_small(smem_raw + ((f32_sweep_smem(S, nc) + 15) & ~static_cast<size_t>(15)), J,
@@ -397,7 +402,7 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
   const uint32_t row_bytes = static_cast<uint32_t>(p.xrow * sizeof(float4));
   // warps whose four chain slots all lie past chain J-1 (the last chain group of a CTA row) stay out of the ring:
   // they would only spin on its barriers
-  const int n_active = min(n_warps, (J - c_base + kQuad - 1) / kQuad);
+  const int n_active = q_end - q_begin;  // <= n_warps
   if (threadIdx.x == 0) {
     mbar_init(m.full, 1);
     mbar_init(m.full + 1, 1);
@@ -422,11 +427,11 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
   }
   chain_load(d, cs, /*terms=*/false);
   __syncthreads();
-  f32_stage_chain_terms(m, cs, nc, c_base, J, S);
+  f32_stage_chain_terms(m, cs, nc, c_base, c_end, S);
 
   const int es = lane >> 2, chs = lane & (kQuad - 1);
-  const bool warp_ok = c_base + warp * kQuad < J;
-  const bool c_ok = c_base + warp * kQuad + chs < J;
+  const bool warp_ok = warp < n_active;
+  const bool c_ok = warp_ok && c_base + warp * kQuad + chs < c_end;
   const int lc = c_ok ? warp * kQuad + chs : warp * kQuad;
   const int c = warp_ok ? c_base + lc : 0;
   const size_t per_it = static_cast<size_t>(E + 1) * J, psz = static_cast<size_t>(J) * gridDim.x;
@@ -466,7 +471,7 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
     if (warp_ok) prefetch(0);
     // coefficients of the chains' pending proposals (decide_core ended with a block barrier; the previous
     // iteration's reads of pq are over)
-    if (threadIdx.x < nc && c_base + threadIdx.x < J && !INIT) f32_stage_proposal(m, cs, threadIdx.x, c_base + threadIdx.x, S);
+    if (c_base + threadIdx.x < c_end && !INIT) f32_stage_proposal(m, cs, threadIdx.x, c_base + threadIdx.x, S);
     __syncthreads();
     const float T = static_cast<float>(cs.T[c]);
     const float iT = 1.f / T;
@@ -641,7 +646,7 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
     htm_step_trace* trace_g = trace_it ? trace_it + static_cast<size_t>(E) * J : nullptr;
     htm_swap_trace* swap_it = swap_base ? swap_base + (it - iter_first) : nullptr;
     // the proposal being judged, of the chain this thread looks after (decide_core replaces it by the next one)
-    const bool mine = threadIdx.x < nc && c_base + threadIdx.x < J;
+    const bool mine = c_base + threadIdx.x < c_end;
     const int j_which = mine ? cs.which[c_base + threadIdx.x] : 0, j_idx = mine ? cs.idx[c_base + threadIdx.x] : 0;
     const double j_xnew = mine ? cs.xnew[c_base + threadIdx.x] : 0.0;
     if (d.xch.n > 1) {
