@@ -361,6 +361,7 @@ struct F32State {
 // exchange, second barrier, decide).  Not compiled into the product library.
 #ifdef HTM_GIBBS_PHASE_TRACE
 __device__ unsigned long long g_phase_ns[8 * 4096];
+__device__ unsigned long long g_cta_done_ns[2 * 4096];  // per CTA: sweep start / end of launch-relative iteration 10
 #define HTM_PHASE(k)                                                                                  \
   do {                                                                                                \
     if (writer && threadIdx.x == 0 && !INIT && it - iter_first < 4096) g_phase_ns[(it - iter_first) * 8 + (k)] = global_timer_ns(); \
@@ -491,6 +492,10 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
         rec_chain_slot >= 0 ? p.hypo_rec + (static_cast<size_t>(rec_slot) * p.n_cool_total + rec_chain_slot) * E : nullptr;
     double s_cur = 0.0, s_prop = 0.0;
     HTM_PHASE(1);
+#ifdef HTM_GIBBS_PHASE_TRACE
+    if (!INIT && it - iter_first == 10 && threadIdx.x == 0 && blockIdx.y * gridDim.x + blockIdx.x < 4096)
+      g_cta_done_ns[2 * (blockIdx.y * gridDim.x + blockIdx.x)] = global_timer_ns();
+#endif
     for (int i = 0; i < (warp_ok ? n_my : 0); ++i, ++t_run) {
       const int buf = static_cast<int>(t_run & 1);
       const uint32_t ph = static_cast<uint32_t>((t_run >> 1) & 1);
@@ -627,6 +632,13 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
       }
     }
     HTM_PHASE(2);
+#ifdef HTM_GIBBS_PHASE_TRACE
+    if (!INIT && it - iter_first == 10) {
+      __syncthreads();
+      const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
+      if (threadIdx.x == 0 && cta < 4096) g_cta_done_ns[2 * cta + 1] = global_timer_ns();
+    }
+#endif
     // one CTA (tiny problems, e.g. BASELINE configs[0]): a block barrier orders the partial sums as well
     if (gridDim.x * gridDim.y > 1) {
       grid.sync();
@@ -774,6 +786,10 @@ cudaError_t launch_gibbs_f32(const GibbsLaunch& a, cudaStream_t stream, int* n_l
 
 #ifdef HTM_GIBBS_PHASE_TRACE
 }  // namespace htm
+extern "C" int32_t htm_debug_cta_trace(unsigned long long* out, int32_t n_cta) {
+  if (n_cta > 4096) n_cta = 4096;
+  return cudaMemcpyFromSymbol(out, htm::g_cta_done_ns, static_cast<size_t>(n_cta) * 2 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 3;
+}
 extern "C" int32_t htm_debug_phase_trace(unsigned long long* out, int32_t n_iter) {
   if (n_iter > 4096) n_iter = 4096;
   return cudaMemcpyFromSymbol(out, htm::g_phase_ns, static_cast<size_t>(n_iter) * 8 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 3;

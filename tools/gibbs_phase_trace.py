@@ -47,6 +47,8 @@ with H.HypoTremorB200(cfg) as g:
     buf = np.zeros((n, 8), dtype=np.uint64)
     rc = g.lib.htm_debug_phase_trace(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), n)
     assert rc == 0
+    cta = np.zeros((4096, 2), dtype=np.uint64)
+    assert g.lib.htm_debug_cta_trace(cta.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), 4096) == 0
 if rank == 0:
     t = buf.astype(np.float64)[5:]                      # skip the first iterations
     sharded = world > 1
@@ -57,5 +59,12 @@ if rank == 0:
           % (E, S, R * K, world, total, ms * 1e3 / n_it))
     for nm, (a, b) in zip(names, cols):
         print("  %-22s %7.2f us" % (nm, np.median(t[:, b] - t[:, a]) / 1e3))
+    c = cta[cta[:, 1] > 0].astype(np.float64)
+    if len(c) > 1:
+        t0 = c[:, 0].min()
+        dur, end = (c[:, 1] - c[:, 0]) / 1e3, (c[:, 1] - t0) / 1e3
+        print("  sweep of one iteration over %d CTAs: duration min / median / max %.1f / %.1f / %.1f us; start spread %.1f us; "
+              "last CTA ends %.1f us after the first starts" % (len(c), dur.min(), np.median(dur), dur.max(),
+                                                               (c[:, 0].max() - t0) / 1e3, end.max()))
 if world > 1:
     dist.destroy_process_group()
