@@ -266,8 +266,9 @@ static __device__ void sum_partials(const int n_tiles, const double* part_cur, c
       }
     }
   } else {
-    // four chains per pass, so that eight independent loads are in flight per lane instead of two
-    constexpr int kCh = 4;
+    // eight chains per pass, so that sixteen independent loads are in flight per lane instead of two (the step is a
+    // chain of L2 round trips: with 100 chains x 74 partials it was most of the 9 us decide step)
+    constexpr int kCh = 8;
     for (int c0 = warp * kCh; c0 < J; c0 += nw * kCh) {
       double a[kCh], b[kCh];
 #pragma unroll

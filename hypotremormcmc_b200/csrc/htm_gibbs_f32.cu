@@ -33,13 +33,16 @@
 // Mapping: persistent cooperative kernel, one wave of CTAs.  warp = 8 events x 4 chains (chain minor: lanes that
 // share an event row are neighbours, 2 shared-memory wavefronts per 16-byte row read instead of 4); a CTA owns up
 // to 32 chains and walks a contiguous range of event octets whose expanded rows (htm_forward.cuh) arrive through
-// a 2-stage ring of 1-D bulk-TMA copies (full / empty mbarriers) that runs across iteration boundaries.  Per
+// a 4-stage ring of 1-D bulk-TMA copies (full / empty mbarriers) that runs across iteration boundaries.  Per
 // iteration: sweep -> per-(chain, CTA) float64 partial sums -> ONE grid barrier -> every CTA adds the partials in
 // the same fixed order and takes the same decisions on its own shared-memory copy of the small per-chain state
 // (CTA (0,0) alone writes counters, records, traces).  The station terms t_corr/a_corr [J][S] stay in global
 // memory (L2): every CTA writes the same accepted values, reads bypass L1.  Event shards (several GPUs, one
 // ensemble) exchange the per-chain sums through NVLink peer memory between two grid barriers.
 #include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstdlib>
 
 #include "htm_gibbs_decide.cuh"
 
@@ -56,6 +59,10 @@ namespace htm {
 #define HTM_GIBBS_PREFETCH 1
 #endif
 constexpr bool kPrefetch = HTM_GIBBS_PREFETCH != 0;
+#ifndef HTM_GIBBS_STAGES
+#define HTM_GIBBS_STAGES 4
+#endif
+constexpr int kMaxStages = HTM_GIBBS_STAGES;  // depth of the TMA ring of event-octet rows (2 when shared memory is short)
 constexpr int kOct = 8;
 constexpr int kQuad = 4;
 constexpr float kHalfLn2 = 0.34657359027997264f;
@@ -251,9 +258,9 @@ __device__ __forceinline__ DeltaSums pending_delta(const PropF32& pr, const bool
 
 // ---- shared memory of one CTA ----------------------------------------------------------------------------------
 struct F32Sm {
-  uint64_t* full;   // [2]
-  uint64_t* empty;  // [2]
-  float4* rows;     // [2][kOct][row]
+  uint64_t* full;   // [n_stages]
+  uint64_t* empty;  // [n_stages]
+  float4* rows;     // [n_stages][kOct][row]
   float4* cp;       // [nc][cps]  {-tc_j0, -tc_j1, -ac_j0, -ac_j1}: station terms of the CTA's chains (persistent)
   float4* c0;       // [nc]  {-tc0, -ac0, 0, 0}
   float4* pf;       // [2][n_warps * 32][4]  per-lane state of the next octet visit (cp.async): H, M, Q | P, Lp
@@ -261,19 +268,19 @@ struct F32Sm {
   int row, cps;
 };
 __host__ __device__ inline int f32_cps(int S) { return (S / 2) | 1; }
-__host__ __device__ inline size_t f32_sweep_smem(int S, int nc) {
-  return 32 + (static_cast<size_t>(2) * kOct * (f32_xrow(S) + 1) + static_cast<size_t>(nc) * (f32_cps(S) + 1) +
+__host__ __device__ inline size_t f32_sweep_smem(int S, int nc, int n_stages) {
+  return 16 * n_stages + (static_cast<size_t>(n_stages) * kOct * (f32_xrow(S) + 1) + static_cast<size_t>(nc) * (f32_cps(S) + 1) +
                (kPrefetch ? static_cast<size_t>(2) * (nc / kQuad) * 32 * 4 : 0)) * sizeof(float4) +
          static_cast<size_t>(nc) * 4 * sizeof(float);
 }
-__device__ __forceinline__ F32Sm carve_f32_sm(unsigned char* base, int S, int xrow, int nc) {
+__device__ __forceinline__ F32Sm carve_f32_sm(unsigned char* base, int S, int xrow, int nc, int n_stages) {
   F32Sm m;
   m.row = xrow + 1;
   m.cps = f32_cps(S);
   m.full = reinterpret_cast<uint64_t*>(base);
-  m.empty = m.full + 2;
-  m.rows = reinterpret_cast<float4*>(base + 32);
-  m.cp = m.rows + 2 * kOct * m.row;
+  m.empty = m.full + n_stages;
+  m.rows = reinterpret_cast<float4*>(base + 16 * n_stages);
+  m.cp = m.rows + n_stages * kOct * m.row;
   m.c0 = m.cp + nc * m.cps;
   m.pf = m.c0 + nc;
   m.pq = reinterpret_cast<float*>(m.pf + (kPrefetch ? 2 * (nc / kQuad) * 32 * 4 : 0));
@@ -379,7 +386,7 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
     gibbs_f32_kernel(const GibbsParams<float> p, const GibbsDecide d, const F32State st, const int iter_first,
                      const int iter_last, const int rec_origin, const int rec_cap, htm_step_trace* trace_base,
                      htm_swap_trace* swap_base, double* part /* [2][2][J][gridDim.x] */, const int n_oct,
-                     double* totals /* [2*J] */, const uint64_t seed) {
+                     double* totals /* [2*J] */, const uint64_t seed, const int n_stages) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::grid_group grid = cg::this_grid();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
@@ -392,8 +399,8 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
   const int q_end = static_cast<int>(static_cast<long>(n_quads) * (blockIdx.y + 1) / gridDim.y);
   const int c_base = q_begin * kQuad, c_end = min(J, q_end * kQuad);
   const bool writer = blockIdx.x == 0 && blockIdx.y == 0;
-  const F32Sm m = carve_f32_sm(smem_raw, S, p.xrow, nc);
-  const ChainSm cs = carve_chain_sm_small(smem_raw + ((f32_sweep_smem(S, nc) + 15) & ~static_cast<size_t>(15)), J,
+  const F32Sm m = carve_f32_sm(smem_raw, S, p.xrow, nc, n_stages);
+  const ChainSm cs = carve_chain_sm_small(smem_raw + ((f32_sweep_smem(S, nc, n_stages) + 15) & ~static_cast<size_t>(15)), J,
                                           d.g_tc, d.g_ac);
   const int o_begin = static_cast<int>(static_cast<long>(n_oct) * blockIdx.x / gridDim.x);
   const int o_end = static_cast<int>(static_cast<long>(n_oct) * (blockIdx.x + 1) / gridDim.x);
@@ -405,16 +412,16 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
   // they would only spin on its barriers
   const int n_active = q_end - q_begin;  // <= n_warps
   if (threadIdx.x == 0) {
-    mbar_init(m.full, 1);
-    mbar_init(m.full + 1, 1);
-    mbar_init(m.empty, n_active);
-    mbar_init(m.empty + 1, n_active);
+    for (int b = 0; b < n_stages; ++b) {
+      mbar_init(m.full + b, 1);
+      mbar_init(m.empty + b, n_active);
+    }
     fence_mbar_init();
     fence_proxy_async();
   }
   __syncthreads();
-  auto issue = [&](long t) {  // visit t of this CTA -> ring stage t & 1
-    const int buf = static_cast<int>(t & 1), o = o_begin + static_cast<int>(t % n_my);
+  auto issue = [&](long t) {  // visit t of this CTA -> ring stage t mod n_stages
+    const int buf = static_cast<int>(t % n_stages), o = o_begin + static_cast<int>(t % n_my);
     const int n_ev = min(kOct, E - o * kOct);
     if (lane == 0) mbar_expect_tx(m.full + buf, row_bytes * n_ev);
     __syncwarp();
@@ -423,8 +430,8 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
                   m.full + buf);
   };
   if (warp == 0) {
-    if (n_run > 0) issue(0);
-    if (n_run > 1) issue(1);
+    for (int b = 0; b < n_stages; ++b)
+      if (n_run > b) issue(b);
   }
   chain_load(d, cs, /*terms=*/false);
   __syncthreads();
@@ -497,8 +504,8 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
       g_cta_done_ns[2 * (blockIdx.y * gridDim.x + blockIdx.x)] = global_timer_ns();
 #endif
     for (int i = 0; i < (warp_ok ? n_my : 0); ++i, ++t_run) {
-      const int buf = static_cast<int>(t_run & 1);
-      const uint32_t ph = static_cast<uint32_t>((t_run >> 1) & 1);
+      const int buf = static_cast<int>(t_run % n_stages);
+      const uint32_t ph = static_cast<uint32_t>((t_run / n_stages) & 1);
       const int o = o_begin + i;
       if (warp_ok) {
         if (i + 1 < n_my) {
@@ -614,10 +621,10 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(m.empty + buf);
-      if (warp == 0 && t_run + 2 < n_run) {
+      if (warp == 0 && t_run + n_stages < n_run) {
         if (lane == 0) mbar_wait(m.empty + buf, ph);
         __syncwarp();
-        issue(t_run + 2);
+        issue(t_run + n_stages);
       }
     }
     if (warp_ok) {
@@ -719,7 +726,7 @@ static cudaError_t launch_gibbs_prepare(const GibbsLaunch& a, cudaStream_t strea
 
 // ---- host launcher -----------------------------------------------------------------------------------------
 struct F32Shape {
-  int n_warps = kCW, gy = 1, n_oct = 1;
+  int n_warps = kCW, gy = 1, n_oct = 1, n_stages = 2;
   long gx = 1;
   size_t smem = 0;
 };
@@ -728,15 +735,39 @@ static cudaError_t f32_shape(const GibbsLaunch& a, F32Shape* s) {
   const int quads = (a.J + kQuad - 1) / kQuad;
   s->gy = (quads + kCW - 1) / kCW;
   s->n_warps = (quads + s->gy - 1) / s->gy;
-  s->smem = ((f32_sweep_smem(a.S, s->n_warps * kQuad) + 15) & ~static_cast<size_t>(15)) + chain_sm_small_bytes(a.J);
-  if (s->smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-  cudaError_t err = cudaFuncSetAttribute(gibbs_f32_kernel<TRACE, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(s->smem));
-  if (err != cudaSuccess) return err;
+  // ring depth: as deep as possible (fast warps may then run ahead of the slowest one, and the row copies have
+  // several visits to land) WITHOUT lowering the number of resident CTAs per SM that two stages allow
   int per_sm = 0, dev = 0, n_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_f32_kernel<TRACE, INIT>, s->n_warps * 32, s->smem);
+  int per_sm2 = 0, max_stages = kMaxStages;
+  if (const char* v = std::getenv("HTM_GIBBS_RING")) max_stages = std::max(2, std::min(kMaxStages, std::atoi(v)));  // tuning
+  cudaError_t err = cudaSuccess;
+  for (int ns : {2, max_stages, 3}) {
+    if (ns < 2 || ns > max_stages || (ns == 2 && per_sm2 > 0)) continue;
+    const size_t smem = ((f32_sweep_smem(a.S, s->n_warps * kQuad, ns) + 15) & ~static_cast<size_t>(15)) + chain_sm_small_bytes(a.J);
+    if (smem > 200 * 1024) {
+      if (ns == 2) return cudaErrorInvalidConfiguration;
+      continue;
+    }
+    err = cudaFuncSetAttribute(gibbs_f32_kernel<TRACE, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    int occ = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_f32_kernel<TRACE, INIT>, s->n_warps * 32, smem);
+    if (err != cudaSuccess) return err;
+    if (ns == 2) {
+      per_sm2 = occ;
+      s->n_stages = 2;
+      s->smem = smem;
+      per_sm = occ;
+    } else if (occ >= per_sm2) {
+      s->n_stages = ns;
+      s->smem = smem;
+      per_sm = occ;
+      break;
+    }
+  }
+  err = cudaFuncSetAttribute(gibbs_f32_kernel<TRACE, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s->smem));
   if (err != cudaSuccess) return err;
   s->n_oct = (a.E + kOct - 1) / kOct;
   s->gx = static_cast<long>(per_sm) * n_sm / s->gy;
@@ -768,7 +799,8 @@ static cudaError_t launch_f32(const GibbsLaunch& a, cudaStream_t stream) {
   double* part = a.part_cur;
   double* totals = a.totals;
   uint64_t seed = a.seed;
-  void* args[] = {&pp, &dp, &st, &iter_first, &iter_last, &rec_origin, &rec_cap, &tr, &sw, &part, &n_oct, &totals, &seed};
+  int n_stages = s.n_stages;
+  void* args[] = {&pp, &dp, &st, &iter_first, &iter_last, &rec_origin, &rec_cap, &tr, &sw, &part, &n_oct, &totals, &seed, &n_stages};
   return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gibbs_f32_kernel<TRACE, INIT>),
                                      dim3(static_cast<unsigned>(s.gx), s.gy), dim3(s.n_warps * 32), args, s.smem, stream);
 }

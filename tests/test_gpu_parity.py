@@ -744,6 +744,43 @@ def test_blocked_gibbs_full_size_properties():
         assert np.isfinite(x["hypo"]).all() and (x["hypo"][:, 2::3] > cfg.prior_z).all()
 
 
+def test_blocked_gibbs_float32_long_run_is_reproducible_and_consistent():
+    """20 000 iterations of 100 joint chains (four CTA rows, many CTAs per row) run twice: every state, counter and
+    record must be bit-identical (the kernel's cross-CTA traffic -- redundant writes of the accepted station terms,
+    partial sums, the grid barrier -- leaves no room for a timing-dependent result), and the carried sums must still
+    be the likelihood of the state after ~7000 incremental shared-parameter commits per chain."""
+    E, S, R, K, n_it = 3000, 20, 20, 5, 20000
+    syn = H.Synthetic(E, S, 12)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=n_it, n_burn=0, n_interval=2000,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=16, step_size_vs=2e-3, step_size_qs=2.0,
+                           step_size_t_corr=5e-3, step_size_a_corr=2e-3)
+    runs = []
+    for _ in range(2):
+        with H.HypoTremorB200(cfg) as g:
+            g.load(syn)
+            g.init_chains()
+            g.run(1, 7000)
+            g.run(7001, n_it)
+            states = [g.get_chain_state(r, k) for r in range(0, R, 3) for k in range(K)]
+            L64 = None
+            if not runs:
+                L64 = g.loglik(np.stack([s["hypo"] for s in states]), np.stack([s["t_corr"] for s in states]),
+                               np.stack([s["a_corr"] for s in states]), [s["vs"] for s in states], [s["qs"] for s in states])
+            runs.append((states, g.get_counts(), [g.fetch_samples(r) for r in range(R)], L64))
+    a, b = runs
+    for x, y in zip(a[0], b[0]):
+        assert np.array_equal(x["hypo"], y["hypo"]) and x["vs"] == y["vs"] and x["qs"] == y["qs"] and x["temp"] == y["temp"]
+        assert np.array_equal(x["t_corr"], y["t_corr"]) and np.array_equal(x["a_corr"], y["a_corr"])
+        assert x["log_likelihood"] == y["log_likelihood"]
+    assert np.array_equal(a[1][0], b[1][0]) and np.array_equal(a[1][1], b[1][1])
+    for x, y in zip(a[2], b[2]):
+        assert np.array_equal(x["iter"], y["iter"]) and np.array_equal(x["hypo"], y["hypo"]) and np.array_equal(x["vs"], y["vs"])
+    p, acc = a[1]
+    assert p[:4].sum() == n_it * R and acc[:4].sum() > 0.05 * p[:4].sum()     # shared parameters do get accepted
+    for s, L in zip(a[0], a[3]):
+        assert abs(s["log_likelihood"] - L) <= 2e-5 * abs(L), (s["log_likelihood"], L)
+
+
 def test_blocked_gibbs_chunked_runs_equal_one_run():
     syn = H.Synthetic(100, 20, 3)
     cfg = H.default_config(n_sta=20, n_events=100, n_procs=2, n_chains=4, n_iter=80, n_burn=0, n_interval=10,
