@@ -33,7 +33,7 @@
 // Mapping: persistent cooperative kernel, one wave of CTAs.  warp = 8 events x 4 chains (chain minor: lanes that
 // share an event row are neighbours, 2 shared-memory wavefronts per 16-byte row read instead of 4); a CTA owns up
 // to 32 chains and walks a contiguous range of event octets whose expanded rows (htm_forward.cuh) arrive through
-// a 4-stage ring of 1-D bulk-TMA copies (full / empty mbarriers) that runs across iteration boundaries.  Per
+// a 2-stage ring of 1-D bulk-TMA copies (full / empty mbarriers) that runs across iteration boundaries.  Per
 // iteration: sweep -> per-(chain, CTA) float64 partial sums -> ONE grid barrier -> every CTA adds the partials in
 // the same fixed order and takes the same decisions on its own shared-memory copy of the small per-chain state
 // (CTA (0,0) alone writes counters, records, traces).  The station terms t_corr/a_corr [J][S] stay in global
@@ -60,7 +60,7 @@ namespace htm {
 #endif
 constexpr bool kPrefetch = HTM_GIBBS_PREFETCH != 0;
 #ifndef HTM_GIBBS_STAGES
-#define HTM_GIBBS_STAGES 4
+#define HTM_GIBBS_STAGES 2
 #endif
 constexpr int kMaxStages = HTM_GIBBS_STAGES;  // depth of the TMA ring of event-octet rows (2 when shared memory is short)
 constexpr int kOct = 8;
