@@ -24,7 +24,7 @@ EXPORTS = [
     "htm_discard_samples", "htm_get_counts", "htm_get_histograms", "htm_device_ptr",
     "htm_last_run_stats", "htm_measure_fp32_peak", "htm_comm_unique_id", "htm_comm_init", "htm_gather",
     "htm_comm_p2p_export", "htm_comm_p2p_import", "htm_gather_samples", "htm_gibbs_pending", "htm_gibbs_last_sums",
-    "htm_posterior_quantiles", "htm_measure_fp64_peak", "htm_select_events",
+    "htm_posterior_quantiles", "htm_measure_fp64_peak", "htm_select_events", "htm_measure_windows",
 ]
 
 
@@ -85,6 +85,7 @@ def load_library():
         "htm_measure_fp64_peak": [i32, dp],
         "htm_select_events": [i32, i32, i32, dp, dp, dp, ctypes.c_double, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double,
                               ctypes.c_double, ctypes.c_double, dp, dp, dp, dp, dp, dp, ip, dp],
+        "htm_measure_windows": [i32, i32, ctypes.c_int64, dp, ctypes.c_double, i32, i32, i32, ip, dp, dp, dp, dp, ip, dp],
         "htm_comm_unique_id": [ctypes.c_char_p],
         "htm_comm_init": [vp, ctypes.c_char_p],
         "htm_gather": [vp, ctypes.POINTER(ctypes.c_uint32), lp, lp],
@@ -142,6 +143,32 @@ def select_events(sta_x, sta_y, sta_z, z_guess, t, t_err, a, a_err, vs_min=2.0, 
         lib.htm_last_error(None, buf, 512)
         raise HtmError(rc, buf.value.decode())
     return dict(vs=out[0], t0=out[1], b=out[2], a0=out[3], cc_t=out[4], cc_a=out[5], selected=sel, kernel_ms=ms.value)
+
+
+def measure_windows(env, dt, n_smp, n_step, win_id, want_lag=False, device=0):
+    """hypo_tremor_measure's lag / amplitude optimisation for all detected windows at once.  env: [n_sta, n_total] merged
+    envelopes sampled every dt; window w = samples (win_id[w] - 1) * n_step ... + n_smp - 1.  Returns dict(t, t_stdv, amp,
+    amp_stdv [n_win, n_sta], kernel_ms and, if asked for, lag [n_win, n_sta (n_sta - 1) / 2])."""
+    lib = load_library()
+    env = _f64(env)
+    S, n_total = env.shape
+    win_id = np.ascontiguousarray(win_id, dtype=np.int32)
+    W = win_id.size
+    out = [np.empty((W, S)) for _ in range(4)]
+    lag = np.zeros((W, S * (S - 1) // 2), dtype=np.int32) if want_lag else None
+    ms = ctypes.c_double()
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    rc = lib.htm_measure_windows(device, S, n_total, _dptr(env), dt, n_smp, n_step, W, win_id.ctypes.data_as(i32p),
+                                 *[_dptr(o) for o in out], lag.ctypes.data_as(i32p) if want_lag else None,
+                                 ctypes.byref(ms))
+    if rc != HTM_OK:
+        buf = ctypes.create_string_buffer(512)
+        lib.htm_last_error(None, buf, 512)
+        raise HtmError(rc, buf.value.decode())
+    r = dict(t=out[0], t_stdv=out[1], amp=out[2], amp_stdv=out[3], kernel_ms=ms.value)
+    if want_lag:
+        r["lag"] = lag
+    return r
 
 
 def measure_fp64_peak(device=0):

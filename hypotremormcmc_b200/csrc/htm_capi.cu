@@ -1767,6 +1767,84 @@ int32_t htm_select_events(int32_t device, int32_t n_sta, int32_t n_events, const
   return HTM_OK;
 }
 
+int32_t htm_measure_windows(int32_t device, int32_t n_sta, int64_t n_total, const double* env, double dt, int32_t n_smp,
+                            int32_t n_step, int32_t n_win, const int32_t* win_id, double* t, double* t_stdv, double* amp,
+                            double* amp_stdv, int32_t* lag, double* kernel_ms) {
+  if (!env || !win_id || !t || !t_stdv || !amp || !amp_stdv) return fail(nullptr, HTM_ERR_ARG, "null argument");
+  if (n_sta < 3 || n_smp < 2 || n_step < 1 || n_win < 1 || n_total < n_smp || !(dt > 0.0))
+    return fail(nullptr, HTM_ERR_ARG, "need n_sta >= 3, n_smp >= 2, n_step >= 1, n_win >= 1, n_total >= n_smp, dt > 0");
+  for (int32_t w = 0; w < n_win; ++w) {  // src/cls_measurer.f90:331-333: samples (id - 1) n_step + 1 ... + n_smp
+    const int64_t j1 = static_cast<int64_t>(win_id[w] - 1) * n_step;
+    if (win_id[w] < 1 || j1 + n_smp > n_total) return fail(nullptr, HTM_ERR_ARG, "window outside the envelopes");
+  }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(nullptr, HTM_ERR_CUDA, "no CUDA device (libhtm_b200 has no CPU fallback)");
+  if (device < 0 || device >= n_dev) return fail(nullptr, HTM_ERR_ARG, "device ordinal out of range");
+  cudaError_t e = cudaSetDevice(device);
+  const size_t S = n_sta, W = n_win, P = S * (S - 1) / 2, WS = W * S;
+  double *d_env = nullptr, *d_out = nullptr;
+  int32_t *d_id = nullptr, *d_lag = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaMalloc(&d_env, S * static_cast<size_t>(n_total) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, 4 * WS * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_id, W * sizeof(int32_t));
+  if (e == cudaSuccess && lag) e = cudaMalloc(&d_lag, W * P * sizeof(int32_t));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_env, env, S * static_cast<size_t>(n_total) * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_id, win_id, W * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  MeasureArgs ma;
+  ma.S = n_sta;
+  ma.n = n_smp;
+  ma.n_step = n_step;
+  ma.n_win = n_win;
+  ma.n_total = static_cast<long>(n_total);
+  ma.dt = dt;
+  ma.env = d_env;
+  ma.win_id = d_id;
+  ma.t = d_out;
+  ma.t_stdv = d_out + WS;
+  ma.amp = d_out + 2 * WS;
+  ma.amp_stdv = d_out + 3 * WS;
+  ma.lag = d_lag;
+  if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+  bool unsupported = false;
+  if (e == cudaSuccess) {
+    e = launch_measure(ma, st);
+    unsupported = e == cudaErrorNotSupported;
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+  double* dst[4] = {t, t_stdv, amp, amp_stdv};
+  for (int k = 0; k < 4 && e == cudaSuccess; ++k)
+    e = cudaMemcpyAsync(dst[k], d_out + k * WS, WS * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && lag) e = cudaMemcpyAsync(lag, d_lag, W * P * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && kernel_ms) {
+    float ms = 0;
+    e = cudaEventElapsedTime(&ms, e0, e1);
+    *kernel_ms = ms;
+  }
+  free_dev(d_env);
+  free_dev(d_out);
+  free_dev(d_id);
+  free_dev(d_lag);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (st) cudaStreamDestroy(st);
+  if (unsupported) {
+    cudaGetLastError();
+    return fail(nullptr, HTM_ERR_UNSUPPORTED,
+                "htm_measure_windows: n_sta x n_smp does not fit one CTA's shared memory (about n_sta (n_smp + 48) 8 B + "
+                "n_sta^2 8 B <= 227 KB)");
+  }
+  if (e != cudaSuccess) return fail(nullptr, HTM_ERR_CUDA, std::string("htm_measure_windows: ") + cudaGetErrorString(e));
+  return HTM_OK;
+}
+
 int32_t htm_measure_fp64_peak(int32_t device, double* tflops) {
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(nullptr, HTM_ERR_CUDA, "no CUDA device");

@@ -188,6 +188,19 @@ struct SelectArgs {
 };
 cudaError_t launch_select(const SelectArgs& a, cudaStream_t stream);
 
+// upstream stage hypo_tremor_measure, lag / amplitude optimisation of all detected windows (htm_measure.cu); all
+// pointers are device memory
+struct MeasureArgs {
+  int S = 0, n = 0, n_step = 0, n_win = 0;  // stations, samples per window, samples between window starts, windows
+  long n_total = 0;                         // samples per station in env
+  double dt = 0;
+  const double* env = nullptr;              // [S][n_total] merged envelopes
+  const int32_t* win_id = nullptr;          // [n_win] 1-based window numbers
+  double *t = nullptr, *t_stdv = nullptr, *amp = nullptr, *amp_stdv = nullptr;  // [n_win][S]
+  int32_t* lag = nullptr;                   // optional [n_win][S (S - 1) / 2]: sample index of each pair's maximum
+};
+cudaError_t launch_measure(const MeasureArgs& a, cudaStream_t stream);
+
 // FFMA / MUFU microbenchmark (roofline denominators)
 cudaError_t measure_fp32_peak(int device, double* tflops, double* mufu_gops);
 cudaError_t measure_fp64_peak(int device, double* tflops);

@@ -340,6 +340,22 @@ module htm_b200_binding
        integer(c_int32_t) :: rc
      end function htm_select_events
 
+     ! hypo_tremor_measure: optimize_cc + optimize_amp for all detected windows (env (n_total, n_sta) column-major,
+     ! outputs (n_sta, n_win)); pass c_null_ptr for lag to skip the per-pair arg-max samples
+     function htm_measure_windows(device, n_sta, n_total, env, dt, n_smp, n_step, n_win, win_id, t, t_stdv, amp, &
+          & amp_stdv, lag, kernel_ms) bind(c, name="htm_measure_windows") result(rc)
+       import
+       integer(c_int32_t), value :: device, n_sta, n_smp, n_step, n_win
+       integer(c_int64_t), value :: n_total
+       real(c_double), intent(in) :: env(*)
+       real(c_double), value :: dt
+       integer(c_int32_t), intent(in) :: win_id(*)
+       real(c_double), intent(out) :: t(*), t_stdv(*), amp(*), amp_stdv(*)
+       type(c_ptr), value :: lag
+       real(c_double), intent(out) :: kernel_ms
+       integer(c_int32_t) :: rc
+     end function htm_measure_windows
+
      function htm_measure_fp64_peak(device, tflops) bind(c, name="htm_measure_fp64_peak") result(rc)
        import
        integer(c_int32_t), value :: device

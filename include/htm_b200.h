@@ -347,6 +347,23 @@ int32_t htm_select_events(int32_t device, int32_t n_sta, int32_t n_events, const
                           double* t0, double* b, double* a0, double* cc_t, double* cc_a, int32_t* selected,
                           double* kernel_ms);
 
+/* Replaces, for all detected windows at once, the numerical core of `call msr%measure_lag_time()`
+ * (src/hypo_tremor_measure.f90:57; src/cls_measurer.f90:317-400): per window `optimize_cc` (:466-523 -- 5 % cosine taper,
+ * division by the window's sum of squares, circular cross-correlation of every station pair, first maximum -> signed
+ * lag, t_i = -(1/S) sum_j lag(i, j) and its scatter) and `optimize_amp` (:405-462 -- envelopes shifted by nint(t_i / dt)
+ * samples, log(sxy / sxx_i) per pair, the same averaging and scatter; a negative cross product zeroes the window).  The
+ * reference evaluates the correlation with FFTW; the kernel sums it directly in float64 (htm_measure.cu).
+ * env: [n_sta][n_total] merged envelopes (the second column of STA.merged.env), sampling interval dt; window w covers
+ * samples (win_id[w] - 1) * n_step ... + n_smp - 1 (0-based; win_id as in detected_win.dat, n_smp = nint(t_win / dt),
+ * n_step = nint(t_step / dt)).  Outputs [n_win][n_sta] = columns 4-7 of opt_data.NNNNNN.dat (:388-397); lag (may be
+ * NULL) [n_win][n_sta (n_sta - 1) / 2] receives each pair's 0-based arg-max sample, pairs in the order i < j of :488-489.
+ * Stand-alone: no handle; kernel_ms (may be NULL) receives the CUDA-event time of the kernel.  HTM_ERR_UNSUPPORTED when
+ * a window does not fit one CTA's shared memory (about n_sta (n_smp + 48) 8 B + n_sta^2 8 B <= 227 KB: 50 stations x 300
+ * samples use 176 KB; 20 stations reach 1 300 samples). */
+int32_t htm_measure_windows(int32_t device, int32_t n_sta, int64_t n_total, const double* env, double dt, int32_t n_smp,
+                            int32_t n_step, int32_t n_win, const int32_t* win_id, double* t, double* t_stdv, double* amp,
+                            double* amp_stdv, int32_t* lag, double* kernel_ms);
+
 /* FFMA/MUFU microbenchmark used as the FP32 roofline denominator (no driver-measured
  * FP32 vector peak exists).  Returns TFLOP/s (FFMA = 2 flops). */
 int32_t htm_measure_fp32_peak(int32_t device, double* tflops, double* mufu_gops);

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "htm_oracle_run.hpp"
+#include "htm_oracle_measure.hpp"
 #include "htm_oracle_select.hpp"
 
 using hto::Oracle;
@@ -267,6 +268,22 @@ void hto_select(int32_t S, int32_t E, const double* sta_x, const double* sta_y, 
     double* r = out + static_cast<size_t>(e) * 6;
     hto::select_window(S, sta_x, sta_y, sta_z, z_guess, t + o, t_err + o, a + o, a_err + o, r);
     selected[e] = (r[0] >= vs_min && r[0] <= vs_max && r[2] >= b_min && r[2] <= b_max) ? 1 : 0;
+  }
+}
+
+// hypo_tremor_measure's lag / amplitude optimisation for n_win windows cut from the merged envelopes env [S][n_total]
+// (src/cls_measurer.f90:331-343: window id -> samples (id - 1) * n_step + 1 ... + n); t, t_stdv, amp, amp_stdv
+// [n_win][S]; lag (may be null) [n_win][S (S - 1) / 2]
+void hto_measure(int32_t S, int64_t n_total, const double* env, double dt, int32_t n, int32_t n_step, int32_t n_win,
+                 const int32_t* win_id, double* t, double* t_stdv, double* amp, double* amp_stdv, int32_t* lag) {
+  std::vector<double> x(static_cast<size_t>(S) * n);
+  const size_t P = static_cast<size_t>(S) * (S - 1) / 2;
+  for (int32_t w = 0; w < n_win; ++w) {
+    const int64_t j1 = static_cast<int64_t>(win_id[w] - 1) * n_step;
+    for (int32_t i = 0; i < S; ++i)
+      for (int32_t m = 0; m < n; ++m) x[static_cast<size_t>(i) * n + m] = env[static_cast<size_t>(i) * n_total + j1 + m];
+    const size_t o = static_cast<size_t>(w) * S;
+    hto::measure_window(S, n, dt, x.data(), t + o, t_stdv + o, amp + o, amp_stdv + o, lag ? lag + w * P : nullptr);
   }
 }
 

@@ -89,6 +89,28 @@ def select_events(sta_x, sta_y, sta_z, z_guess, t, t_err, a, a_err, vs_min=2.0, 
     return dict(vs=out[:, 0], t0=out[:, 1], b=out[:, 2], a0=out[:, 3], cc_t=out[:, 4], cc_a=out[:, 5], selected=sel)
 
 
+def measure_windows(env, dt, n_smp, n_step, win_id, want_lag=False):
+    """hypo_tremor_measure's lag / amplitude optimisation restated (oracle/htm_oracle_measure.hpp):
+    dict(t, t_stdv, amp, amp_stdv [n_win][S] and, if asked for, lag [n_win][S (S - 1) / 2])"""
+    env = np.ascontiguousarray(env, dtype=np.float64)
+    S, n_total = env.shape
+    win_id = np.ascontiguousarray(win_id, dtype=np.int32)
+    W = win_id.size
+    out = [np.empty((W, S)) for _ in range(4)]
+    lag = np.zeros((W, S * (S - 1) // 2), dtype=np.int32) if want_lag else None
+    f = lib().hto_measure
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+    f.argtypes = [ctypes.c_int32, ctypes.c_int64, dp, ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ip,
+                  dp, dp, dp, dp, ip]
+    f.restype = None
+    f(S, n_total, _d(env), dt, n_smp, n_step, W, win_id.ctypes.data_as(ip), *[_d(o) for o in out],
+      lag.ctypes.data_as(ip) if want_lag else None)
+    r = dict(t=out[0], t_stdv=out[1], amp=out[2], amp_stdv=out[3])
+    if want_lag:
+        r["lag"] = lag
+    return r
+
+
 class Oracle:
     def __init__(self, cfg, syn, event_offset=0):
         self.L = lib()

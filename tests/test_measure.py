@@ -1,0 +1,214 @@
+"""The upstream stage hypo_tremor_measure, lag / amplitude optimisation (second half): oracle
+pins on the CPU, CUDA parity on the GPU.
+
+The reference holds no test or fixture for it (parity unpinned) and correlates with FFTW, which this image lacks.  The C++
+restatement (oracle/htm_oracle_measure.hpp, following src/cls_measurer.f90:405-523 and src/mod_signal_process.f90:10-28)
+sums the circular cross-correlation directly; it is pinned here by the TRANSFORM route written in numpy (rfft, conjugate
+product, inverse transform, arg-max -- the reference's own sequence of steps) and by an analytic known answer.  The CUDA
+kernel is then compared with the oracle.
+"""
+import numpy as np
+import pytest
+
+import hypotremormcmc_b200 as H
+from oracle import pyoracle
+
+
+def numpy_measure(env, dt, n, n_step, win_id):
+    """src/cls_measurer.f90:331-343,405-523 with numpy's FFT in the place of FFTW"""
+    S = env.shape[0]
+    out = dict(t=[], t_stdv=[], amp=[], amp_stdv=[], lag=[], gap=[])
+    nleng = int(n * 0.05)
+    for wid in win_id:
+        j1 = (wid - 1) * n_step
+        x = env[:, j1:j1 + n]
+        tap = np.ones(n)
+        fac = 0.5 * (1.0 - np.cos(np.arange(nleng) * np.pi / nleng)) if nleng else np.zeros(0)
+        tap[:nleng] = fac
+        tap[n - nleng:] = fac[::-1]
+        a = x * tap / (x ** 2).sum(1)[:, None]
+        cx = np.fft.rfft(a, axis=1)
+        lag_t = np.zeros((S, S))
+        lag_k, gap = [], []
+        for i in range(S - 1):
+            for j in range(i + 1, S):
+                r = np.fft.irfft(np.conj(cx[i]) * cx[j], n) * n
+                k = int(np.argmax(r))
+                top = np.sort(r)[-2:]
+                gap.append((top[1] - top[0]) / abs(top[1]))
+                ilag = k + 1
+                lag_t[i, j] = (ilag - 1) * dt if ilag <= n // 2 else (ilag - n - 1) * dt
+                lag_t[j, i] = -lag_t[i, j]
+                lag_k.append(k)
+        t = -lag_t.sum(1) / S
+        dev = t[None, :] - t[:, None] - lag_t
+        np.fill_diagonal(dev, 0.0)
+        t_stdv = np.sqrt((dev ** 2).sum(1) / (S - 2))
+        it = np.where(t >= 0, np.floor(t / dt + 0.5), np.ceil(t / dt - 0.5)).astype(int)     # nint
+        x2 = np.zeros_like(x)
+        for i in range(S):
+            for j in range(n):
+                if 0 <= j + it[i] < n:
+                    x2[i, j] = x[i, j + it[i]]
+        sxx = (x2 ** 2).sum(1)
+        sxy = x2 @ x2.T
+        if (sxy[np.triu_indices(S, 1)] < 0).any():
+            amp, amp_stdv = np.zeros(S), np.zeros(S)
+        else:
+            rel = np.zeros((S, S))
+            iu = np.triu_indices(S, 1)
+            rel[iu] = np.log(sxy[iu] / sxx[iu[0]])
+            rel = rel - rel.T
+            amp = -rel.sum(1) / S
+            dev = amp[None, :] - amp[:, None] - rel
+            np.fill_diagonal(dev, 0.0)
+            amp_stdv = np.sqrt((dev ** 2).sum(1) / (S - 2))
+        for k, v in (("t", t), ("t_stdv", t_stdv), ("amp", amp), ("amp_stdv", amp_stdv), ("lag", lag_k), ("gap", gap)):
+            out[k].append(v)
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def tremor_envelopes(S, n_total, seed, max_shift=12, noise=0.3):
+    """a common smooth positive source signal, delayed and scaled per station, plus station noise"""
+    rng = np.random.default_rng(seed)
+    kern = np.hanning(21)
+    kern /= kern.sum()
+    src = np.convolve(np.abs(rng.normal(0, 1, n_total + 200)) ** 2, kern, mode="same")
+    shift = rng.integers(-max_shift, max_shift + 1, S)
+    gain = np.exp(rng.normal(0, 0.5, S))
+    env = np.empty((S, n_total))
+    for i in range(S):
+        own = np.convolve(np.abs(rng.normal(0, 1, n_total)) ** 2, kern, mode="same")
+        env[i] = gain[i] * (src[100 - shift[i]:100 - shift[i] + n_total] + noise * own)
+    return env, shift, gain
+
+
+def compare(g, o, tol_amp):
+    assert np.array_equal(g["lag"], o["lag"])
+    assert np.allclose(g["t"], o["t"], rtol=0, atol=1e-12) and np.allclose(g["t_stdv"], o["t_stdv"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(g["amp"], o["amp"], rtol=0, atol=tol_amp)
+    assert np.allclose(g["amp_stdv"], o["amp_stdv"], rtol=1e-9, atol=tol_amp)
+
+
+@pytest.mark.parametrize("S,n,n_step,dt", [(7, 120, 60, 1.0), (5, 75, 30, 0.5), (12, 64, 64, 1.0), (3, 41, 7, 2.0)])
+def test_oracle_measure_equals_the_transform_route(S, n, n_step, dt):
+    env, _, _ = tremor_envelopes(S, 900, 40 + S)
+    win_id = np.arange(1, (900 - n) // n_step + 1, 3)
+    o = pyoracle.measure_windows(env, dt, n, n_step, win_id, want_lag=True)
+    r = numpy_measure(env, dt, n, n_step, win_id)
+    assert r["gap"].min() > 1e-9            # no near-ties between the two largest correlation values in these data
+    compare(o, r, 1e-12)
+    assert np.abs(o["t"]).max() > 0 and np.abs(o["amp"]).max() > 0
+
+
+def test_oracle_measure_known_answer():
+    """station envelopes that are shifted, scaled copies of one pulse: every pair's lag is the difference of the shifts, so
+    t_i = (s_i - mean s) dt with zero scatter, and amp_i = log g_i - mean log g with zero scatter"""
+    rng = np.random.default_rng(3)
+    S, n, n_step, dt = 9, 100, 50, 0.5
+    pulse = np.exp(-0.5 * ((np.arange(600) - 300) / 4.0) ** 2)          # centred in window 6 (samples 250 .. 349)
+    shift = np.array([0, 3, -2, 5, 1, -1, -6, 4, 5])                       # mean 1: nint(t_i / dt) = s_i - 1
+    gain = np.exp(rng.normal(0, 0.4, S))
+    env = np.stack([g * np.roll(pulse, s) for g, s in zip(gain, shift)])
+    o = pyoracle.measure_windows(env, dt, n, n_step, [6], want_lag=True)
+    assert np.array_equal(o["t"][0], (shift - shift.mean()) * dt) and np.all(o["t_stdv"][0] == 0.0)
+    assert np.allclose(o["amp"][0], np.log(gain) - np.log(gain).mean(), rtol=0, atol=1e-12)
+    assert np.all(o["amp_stdv"][0] < 1e-12)
+    k = 0
+    for i in range(S - 1):
+        for j in range(i + 1, S):
+            assert o["lag"][0, k] == (shift[j] - shift[i]) % n
+            k += 1
+
+
+def test_oracle_measure_properties():
+    S, n, n_step = 8, 90, 45
+    env, _, _ = tremor_envelopes(S, 700, 9)
+    win = np.arange(1, 12)
+    o = pyoracle.measure_windows(env, 1.0, n, n_step, win, want_lag=True)
+    # a station's gain moves only its own log-amplitude against the others: amp_i += (1 - 1/S) log c, amp_j -= log c / S
+    env2 = env.copy()
+    env2[2] *= 3.0
+    o2 = pyoracle.measure_windows(env2, 1.0, n, n_step, win, want_lag=True)
+    assert np.array_equal(o2["lag"], o["lag"]) and np.array_equal(o2["t"], o["t"])
+    d = o2["amp"] - o["amp"]
+    assert np.allclose(d[:, 2], (1 - 1 / S) * np.log(3.0), atol=1e-12) and np.allclose(np.delete(d, 2, 1), -np.log(3.0) / S, atol=1e-12)
+    # the sampling interval scales the times and nothing else
+    o3 = pyoracle.measure_windows(env, 0.25, n, n_step, win, want_lag=True)
+    assert np.array_equal(o3["lag"], o["lag"]) and np.array_equal(o3["t"], 0.25 * o["t"]) and np.allclose(o3["amp"], o["amp"], atol=1e-13)
+    # a negative cross product gives the whole window up (src/cls_measurer.f90:430-434); the times stay
+    env4 = env.copy()
+    env4[5] = -env4[5]
+    o4 = pyoracle.measure_windows(env4, 1.0, n, n_step, win)
+    assert np.all(o4["amp"] == 0.0) and np.all(o4["amp_stdv"] == 0.0) and np.abs(o4["t"]).max() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,n,n_step,dt", [(3, 41, 7, 2.0), (7, 120, 60, 1.0), (5, 75, 30, 0.5), (12, 64, 64, 1.0),
+                                           (33, 17, 5, 1.0), (50, 300, 150, 1.0), (20, 601, 300, 0.5)])
+def test_cuda_measure_equals_the_oracle(S, n, n_step, dt):
+    n_total = 4 * n + 200
+    env, _, _ = tremor_envelopes(S, n_total, 70 + S, max_shift=min(12, n // 5))
+    win_id = np.arange(1, (n_total - n) // n_step + 2)
+    win_id = win_id[:: max(1, len(win_id) // 6)]
+    o = pyoracle.measure_windows(env, dt, n, n_step, win_id, want_lag=True)
+    g = H.api.measure_windows(env, dt, n, n_step, win_id, want_lag=True)
+    # the same sums in the same order (the kernel fuses the multiply-adds of the correlation; its arg-max is what is
+    # compared); cos, log, sqrt and divisions may differ in the last place
+    compare(g, o, 1e-11)
+    assert g["kernel_ms"] > 0
+
+
+@pytest.mark.gpu
+def test_cuda_measure_known_answer_and_negative_product():
+    rng = np.random.default_rng(8)
+    S, n, n_step, dt = 50, 300, 150, 1.0
+    pulse = np.exp(-0.5 * ((np.arange(1500) - 750) / 5.0) ** 2)          # centred in window 5 (samples 600 .. 899)
+    shift = rng.integers(-20, 21, S)
+    shift[-1] -= shift.sum() % S                                          # integer mean
+    gain = np.exp(rng.normal(0, 0.4, S))
+    env = np.stack([g * np.roll(pulse, s) for g, s in zip(gain, shift)])
+    g = H.api.measure_windows(env, dt, n, n_step, [5], want_lag=True)
+    assert np.array_equal(g["t"][0], (shift - shift.mean()) * dt) and np.all(g["t_stdv"][0] == 0.0)
+    assert np.allclose(g["amp"][0], np.log(gain) - np.log(gain).mean(), rtol=0, atol=1e-11) and np.all(g["amp_stdv"][0] < 1e-11)
+    env[7] = -env[7]
+    g = H.api.measure_windows(env, dt, n, n_step, [5])
+    assert np.all(g["amp"] == 0.0) and np.all(g["amp_stdv"] == 0.0)
+
+
+@pytest.mark.gpu
+def test_cuda_measure_full_size_properties():
+    """2 000 overlapping windows x 50 stations x 300 samples (sample/hypo_tremor.in:74-76 at one sample per second): the
+    windows are independent (a permuted window list permutes the results), a window's result does not depend on what
+    else is in the batch, and the DFMA rate of the correlation is reported against the measured FP64 peak."""
+    S, n, n_step, W = 50, 300, 150, 2000
+    env, _, _ = tremor_envelopes(S, n_step * (W + 1), 20231005)
+    win = np.arange(1, W + 1)
+    g = H.api.measure_windows(env, 1.0, n, n_step, win, want_lag=True)
+    perm = np.random.default_rng(2).permutation(W)
+    g2 = H.api.measure_windows(env, 1.0, n, n_step, win[perm], want_lag=True)
+    for k in ("t", "t_stdv", "amp", "amp_stdv", "lag"):
+        assert np.array_equal(g[k][perm], g2[k]), k
+    o = pyoracle.measure_windows(env, 1.0, n, n_step, win[perm[:3]], want_lag=True)
+    compare({k: g2[k][:3] for k in o}, o, 1e-11)
+    assert np.isfinite(g["amp"]).all() and np.abs(g["t"]).max() > 0
+    flop = 2.0 * W * (S * (S - 1) // 2) * n * n
+    peak = H.api.measure_fp64_peak()
+    print("measure_kernel %d x %d x %d: %.2f ms, %.2f TFLOP/s float64 = %.2f of the measured DFMA peak %.1f"
+          % (W, S, n, g["kernel_ms"], flop / g["kernel_ms"] / 1e9, flop / g["kernel_ms"] / 1e9 / peak, peak))
+
+
+@pytest.mark.gpu
+def test_cuda_measure_argument_errors():
+    env, _, _ = tremor_envelopes(4, 500, 1)
+    with pytest.raises(H.HtmError) as ei:
+        H.api.measure_windows(env, 1.0, 100, 50, [9])                      # samples 400 .. 499 fit, window 10 does not
+        H.api.measure_windows(env, 1.0, 100, 50, [10])
+    assert ei.value.code == H.config.HTM_ERR_ARG
+    with pytest.raises(H.HtmError) as ei:
+        H.api.measure_windows(env[:2], 1.0, 100, 50, [1])                  # S - 2 = 0 in the scatter
+    assert ei.value.code == H.config.HTM_ERR_ARG
+    big, _, _ = tremor_envelopes(60, 1300, 2)
+    with pytest.raises(H.HtmError) as ei:
+        H.api.measure_windows(big, 1.0, 1200, 50, [1])                     # 60 x 1200 doubles: beyond one CTA
+    assert ei.value.code == H.config.HTM_ERR_UNSUPPORTED
