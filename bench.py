@@ -382,6 +382,51 @@ def extra_mode_c(H, timer, a, local, E, S, R, K, iters, peak_tf, cpu_seconds):
     return out
 
 
+def extra_upstream(H, a, local, peak64_tf):
+    """the two upstream stages built beside the hot path, each timed by its own CUDA events
+    inside the call, with the oracle timed on a bounded sample as the CPU baseline"""
+    import time
+    from hypotremormcmc_b200 import api
+    out = {}
+    E, S = 100000, 50
+    syn = H.Synthetic(E, S, SEED + 20)
+    args = (syn.sta_x, syn.sta_y, syn.sta_z, 7.0, syn.t_obs, syn.t_stdv, syn.a_obs, syn.a_stdv)
+    ms = min(api.select_events(*args, device=local)["kernel_ms"] for _ in range(4))
+    nbytes = E * (32 * S + 52)
+    hb = hbm_block(nbytes, ms)
+    out["select"] = {"workload": "hypo_tremor_select regression + acceptance, %d windows x %d stations, f64" % (E, S),
+                     "value": E / (ms * 1e-3), "unit": "windows/s", "kernel_ms": ms, "gpu_launches": 1,
+                     "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hb["peak"] if hb else None,
+                                  "unit": "GB/s", "frac": hb["frac"] if hb else None, "traffic": None,
+                                  "bytes_per_window": 32 * S + 52, "kernel": "select_kernel",
+                                  "note": "FP64 sqrt / log / divisions per station keep it far from the HBM bound"}}
+    W, n = 2000, 300
+    rng = np.random.default_rng(SEED)
+    kern = np.hanning(21)
+    env = np.stack([np.convolve(rng.normal(0, 1, (n // 2) * (W + 1)) ** 2, kern, mode="same") for _ in range(S)])
+    win = np.arange(1, W + 1)
+    ms = min(api.measure_windows(env, 1.0, n, n // 2, win, device=local)["kernel_ms"] for _ in range(3))
+    flop = 2.0 * W * (S * (S - 1) // 2) * n * n
+    out["measure"] = {"workload": "hypo_tremor_measure optimize_cc + optimize_amp, %d windows x %d stations x %d samples, f64"
+                                  % (W, S, n),
+                      "value": W / (ms * 1e-3), "unit": "windows/s", "kernel_ms": ms, "gpu_launches": 1,
+                      "roofline": {"bound": "fp64", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peak64_tf,
+                                   "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / peak64_tf, "traffic": None,
+                                   "flop_per_window": flop / W, "kernel": "measure_kernel",
+                                   "peak_source": "own-measured DFMA microbenchmark (htm_measure_fp64_peak)"}}
+    if not a.no_cpu:
+        from oracle import pyoracle
+        t0 = time.time()
+        pyoracle.select_events(*[v[:20000] if getattr(v, "ndim", 0) == 2 else v for v in args])
+        out["select"]["cpu_baseline"] = {"value": 20000 / (time.time() - t0), "unit": "windows/s", "cores": 1, "kind": "port",
+                                         "sample": "oracle/htm_oracle_select.hpp on the first 20 000 windows"}
+        t0 = time.time()
+        pyoracle.measure_windows(env, 1.0, n, n // 2, win[:16])
+        out["measure"]["cpu_baseline"] = {"value": 16 / (time.time() - t0), "unit": "windows/s", "cores": 1, "kind": "port",
+                                          "sample": "oracle/htm_oracle_measure.hpp (direct float64 sums) on the first 16 windows"}
+    return out
+
+
 def p2p_setup(g, dist, world, rank):
     ids = [g.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
@@ -587,6 +632,7 @@ def run_b200(a):
             extra["mode_c_10k"] = extra_mode_c(H, timer, a, local, 10000, 50, 20, 5, 100, peak_tf,
                                                0 if a.no_cpu else min(6.0, a.cpu_seconds))
             extra["mode_c_100k"] = extra_mode_c(H, timer, a, local, 100000, 50, 20, 5, 20, peak_tf, 0)
+            extra["upstream"] = extra_upstream(H, a, local, measure_fp64_peak(local))
         else:
             selfcheck, extra["mode_c_event_sharded"] = multi_gpu_mode_c(H, dist, torch, a, world, rank, local, peak_tf)
 

@@ -85,7 +85,7 @@ struct htm_handle_s {
   void* d_store_hypo = nullptr;
   double* d_store_shared = nullptr;
   size_t store_cap = 0, store_n = 0;
-  int last_partials = 0, last_parity = 0;  // float32 mode C: layout of the partial sums of the last launch
+  int last_partials = 0, last_parity = 0;  // float32 mode C: which accumulator set holds the sums of the last iteration
   // stats
   bool timed = false;
   int64_t last_launches = 0, last_proposals = 0;
@@ -358,7 +358,7 @@ int32_t alloc_state(htm_handle h) {
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.part_cur), 4 * J * nt * 8));  // [2 buffers][cur, prop][J][tiles]
     g.part_prop = g.part_cur + J * nt;
     HTM_CK(h, grab(reinterpret_cast<void**>(&g.done_counter), 8));
-    HTM_CK(h, grab(reinterpret_cast<void**>(&g.totals), 2 * J * 8));
+    HTM_CK(h, grab(reinterpret_cast<void**>(&g.totals), 4 * J * 8));  // float32: [cur, prop][J][2 limbs]
     if (h->cfg.max_samples > 0) {
       h->rec_cap = h->cfg.max_samples;
       const size_t n = static_cast<size_t>(h->rec_cap) * h->n_cold_total;
@@ -999,7 +999,7 @@ static int32_t run_impl(htm_handle h, int32_t iter_first, int32_t iter_last, htm
     h->gl.trace = d_trace;
     h->gl.swaps = d_swaps;
     h->gl.out_partials = &h->last_partials;
-    h->last_parity = iter_last & 1;
+    h->last_parity = iter_last % 3;
     int nlg = 0;
     HTM_CK(h, cudaEventRecord(h->ev0, h->stream));
     {
@@ -1638,18 +1638,14 @@ int32_t htm_gibbs_last_sums(htm_handle h, double* cur, double* prop) {
   if (h->last_partials <= 0) return fail(h, HTM_ERR_STATE, "nothing was run yet");
   HTM_CK(h, cudaSetDevice(h->cfg.device));
   HTM_CK(h, cudaStreamSynchronize(h->stream));
-  const size_t J = h->C, gx = h->last_partials, psz = J * gx;
-  std::vector<double> buf(2 * psz);
-  HTM_CK(h, cudaMemcpy(buf.data(), h->gl.part_cur + static_cast<size_t>(h->last_parity) * 2 * psz, 2 * psz * sizeof(double),
-                       cudaMemcpyDeviceToHost));
+  // the accumulator set of the last iteration: [cur, prop][J][2 limbs] fixed-point words (htm_gibbs_f32.cu)
+  const size_t J = h->C;
+  std::vector<unsigned long long> buf(4 * J);
+  HTM_CK(h, cudaMemcpy(buf.data(), reinterpret_cast<const unsigned long long*>(h->gl.part_cur) + static_cast<size_t>(h->last_parity) * 4 * J,
+                       4 * J * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   for (size_t c = 0; c < J; ++c) {
-    double a = 0.0, b = 0.0;
-    for (size_t t = 0; t < gx; ++t) {
-      a += buf[c * gx + t];
-      b += buf[psz + c * gx + t];
-    }
-    cur[c] = a;
-    prop[c] = b;
+    cur[c] = gibbs_f32_sum_to_double(buf[2 * c], buf[2 * c + 1]);
+    prop[c] = gibbs_f32_sum_to_double(buf[2 * (J + c)], buf[2 * (J + c) + 1]);
   }
   return check_exchange(h);
 }

@@ -305,8 +305,10 @@ static __device__ void decide_core(const GibbsDecide& d, const ChainSm& cs, cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int J = d.J, S = d.S;
   if (it > 0) {
-    sum_partials(summed ? 1 : d.n_tiles, part_cur, part_prop, J, cs.tot);
-    __syncthreads();
+    if (part_cur) {  // null: the caller has filled cs.tot (htm_gibbs_f32.cu: exact integer sums)
+      sum_partials(summed ? 1 : d.n_tiles, part_cur, part_prop, J, cs.tot);
+      __syncthreads();
+    }
     // a failed exchange ends the run: no decision is taken from partial sums (uniform for the CTA)
     if (!summed && d.xch.n > 1 && !peer_allreduce(d.xch, d.xch.epoch, cs.tot, 2 * J)) return;
     // ---- judge the shared-parameter proposal (src/cls_mcmc.f90:186-219) ----

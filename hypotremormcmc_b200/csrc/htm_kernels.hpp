@@ -118,7 +118,8 @@ struct PeerExchange {
                                                            // sets it from HTM_XCH_TIMEOUT_S
 };
 inline size_t peer_exchange_bytes(int n, int J) {
-  return static_cast<size_t>(2) * n * 2 * J * sizeof(double) + static_cast<size_t>(2) * n * sizeof(uint32_t);
+  // two exchange numbers in flight x n shards x (float64: 2 J doubles; float32: 4 J integer limbs), then the flags
+  return static_cast<size_t>(2) * n * 4 * J * sizeof(double) + static_cast<size_t>(2) * n * sizeof(uint32_t);
 }
 
 // mode C (blocked Gibbs): joint chains with solved shared parameters
@@ -162,6 +163,7 @@ struct GibbsLaunch {
   int* out_partials = nullptr;      // float32: receives the number of partial sums per chain of this launch
 };
 cudaError_t launch_gibbs(const GibbsLaunch& a, cudaStream_t stream, int* n_launches);
+double gibbs_f32_sum_to_double(unsigned long long l0, unsigned long long l1);  // htm_gibbs_f32.cu: limbs_to_double
 // float32: build the expanded rows from the raw tables (once per table upload)
 cudaError_t launch_expand_obs(const Tables& tab, int E, int S, void* obsx, cudaStream_t stream);
 cudaError_t launch_gibbs_init(const GibbsLaunch& a, double temp_high, int ladder, int n_cool, cudaStream_t stream);

@@ -49,6 +49,8 @@ with H.HypoTremorB200(cfg) as g:
     assert rc == 0
     cta = np.zeros((4096, 2), dtype=np.uint64)
     assert g.lib.htm_debug_cta_trace(cta.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), 4096) == 0
+    info = np.zeros((4096, 4), dtype=np.uint32)
+    assert g.lib.htm_debug_cta_info(info.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), 4096) == 0
 if rank == 0:
     t = buf.astype(np.float64)[5:]                      # skip the first iterations
     sharded = world > 1
@@ -66,5 +68,25 @@ if rank == 0:
         print("  sweep of one iteration over %d CTAs: duration min / median / max %.1f / %.1f / %.1f us; start spread %.1f us; "
               "last CTA ends %.1f us after the first starts" % (len(c), dur.min(), np.median(dur), dur.max(),
                                                                (c[:, 0].max() - t0) / 1e3, end.max()))
+        inf = info[cta[:, 1] > 0].astype(np.int64)
+        for nm, col in (("CTA row (blockIdx.y)", 1), ("event octets", 2)):
+            for v in np.unique(inf[:, col]):
+                k = inf[:, col] == v
+                print("    %-22s %3d: %4d CTAs, %d warps, duration median %.1f, max %.1f us" % (nm, v, k.sum(), inf[k, 3][0], np.median(dur[k]), dur[k].max()))
+        # what shares an SM: warps and octet visits per SM against the time its last CTA ends
+        sm = inf[:, 0]
+        ids = np.unique(sm)
+        work = np.array([(inf[sm == i, 2] * inf[sm == i, 3]).sum() for i in ids])
+        warps = np.array([inf[sm == i, 3].sum() for i in ids])
+        last = np.array([end[sm == i].max() for i in ids])
+        print("    per SM (%d SMs): CTAs %d..%d, warps %d..%d, warp-octets %d..%d; end of the SM's last CTA min / median / max %.1f / %.1f / %.1f us"
+              % (len(ids), min((sm == i).sum() for i in ids), max((sm == i).sum() for i in ids), warps.min(), warps.max(), work.min(), work.max(),
+                 last.min(), np.median(last), last.max()))
+        for wv in np.unique(work):
+            k = work == wv
+            print("      SMs with %4d warp-octets (%d warps): %3d, end median %.1f max %.1f us" % (wv, warps[k][0], k.sum(), np.median(last[k]), last[k].max()))
+        half = ids < np.median(ids)
+        print("      SM id below / above the median id: end median %.1f / %.1f us" % (np.median(last[half]), np.median(last[~half])))
+        print("      correlation(end, warp-octets) = %.2f" % np.corrcoef(last, work)[0, 1])
 if world > 1:
     dist.destroy_process_group()
