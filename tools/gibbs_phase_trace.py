@@ -85,6 +85,10 @@ if rank == 0:
         for wv in np.unique(work):
             k = work == wv
             print("      SMs with %4d warp-octets (%d warps): %3d, end median %.1f max %.1f us" % (wv, warps[k][0], k.sum(), np.median(last[k]), last[k].max()))
+        order = np.nonzero(cta[:, 1] > 0)[0]
+        print("      SM of CTAs 0..23: %s" % " ".join(str(v) for v in sm[:24]))
+        for i in ids[:4]:
+            print("      SM %d holds CTAs %s (ends %s us)" % (i, list(order[sm == i]), ["%.0f" % v for v in end[sm == i]]))
         half = ids < np.median(ids)
         print("      SM id below / above the median id: end median %.1f / %.1f us" % (np.median(last[half]), np.median(last[~half])))
         print("      correlation(end, warp-octets) = %.2f" % np.corrcoef(last, work)[0, 1])
