@@ -27,7 +27,10 @@ namespace {
 constexpr int kMeasureThreads = 512;
 constexpr int kLagTile = 16;  // consecutive lags per lane = length of the a_j window = m steps per unrolled block
 constexpr int kRowExt = 32;   // wrap extension of a row
-constexpr int kMaxSplit = 4;
+#ifndef HTM_MEASURE_UNITS
+#define HTM_MEASURE_UNITS 10
+#endif
+constexpr int kUnitsPerWarp = HTM_MEASURE_UNITS;  // units (32 pairs x a share of the lag tiles) per warp, at least
 
 __host__ __device__ inline int measure_stride(int n) {
   int s = n + kRowExt;
@@ -54,7 +57,7 @@ __host__ __device__ inline size_t measure_smem(int S, int n, int n_split) {
   b += n_split * P * 8;                                        // bestv
   b += n_split * P * 4 + P * 4;                                // bestk, lagk
   b = (b + 7) & ~static_cast<size_t>(7);
-  b += 2 * static_cast<size_t>(S) * 8 + static_cast<size_t>(S) * 4 + 4;  // tS, sxx, it, flag
+  b += 2 * static_cast<size_t>(S) * 8 + static_cast<size_t>(S) * 4 + 8;  // tS, sxx, it, flag[2]
   b += 2 * P * 2;                                                        // pi, pj
   return b + 16;
 }
@@ -79,7 +82,7 @@ __device__ inline MeasureSm carve_measure(unsigned char* base, int S, int n, int
   m.it = reinterpret_cast<int*>(q);
   q += static_cast<size_t>(S) * 4;
   m.flag = reinterpret_cast<int*>(q);
-  q += 4;
+  q += 8;
   m.pi = reinterpret_cast<uint16_t*>(q);
   q += P * 2;
   m.pj = reinterpret_cast<uint16_t*>(q);
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(kMeasureThreads, 1) measure_kernel(const Measu
       sm.pj[p] = static_cast<uint16_t>(j);
     }
   }
-  if (threadIdx.x == 0) *sm.flag = 0;
+  if (threadIdx.x == 0) sm.flag[0] = sm.flag[1] = 0;  // negative-product flag, next unit of the correlation phase
 
   // ---- optimize_cc :478-486: a_i = taper(x_i) / sum(x_i^2) -------------------------------------------------------
   const int nleng = static_cast<int>(n * 0.05);
@@ -169,7 +172,13 @@ __global__ void __launch_bounds__(kMeasureThreads, 1) measure_kernel(const Measu
 
   // ---- optimize_cc :488-505: first maximum of the circular cross-correlation of every pair -----------------------
   const int n_groups = (P + 31) / 32, n_tiles = (n + kLagTile - 1) / kLagTile, n_blk = n / kLagTile;
-  for (int u = warp; u < n_groups * n_split; u += n_warps) {
+  // units (32 pairs x a share of the lag tiles) are handed out on demand: the warps of a CTA do not progress equally
+  // (each unit writes its own result slots, so the outcome does not depend on who takes which)
+  for (;;) {
+    int u = 0;
+    if (lane == 0) u = atomicAdd(sm.flag + 1, 1);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= n_groups * n_split) break;
     const int g = u / n_split, s = u - g * n_split;
     const int tile0 = static_cast<int>(static_cast<long>(n_tiles) * s / n_split);
     const int tile1 = static_cast<int>(static_cast<long>(n_tiles) * (s + 1) / n_split);
@@ -308,8 +317,7 @@ __global__ void __launch_bounds__(kMeasureThreads, 1) measure_kernel(const Measu
 int measure_split(int S, int n, size_t smem_max, size_t* smem) {
   const int P = S * (S - 1) / 2, n_groups = (P + 31) / 32, n_warps = kMeasureThreads / 32;
   const int n_tiles = (n + kLagTile - 1) / kLagTile;
-  int n_split = (4 * n_warps + n_groups - 1) / n_groups;
-  if (n_split > kMaxSplit) n_split = kMaxSplit;
+  int n_split = (kUnitsPerWarp * n_warps + n_groups - 1) / n_groups;  // enough units for the queue to even out the warps
   if (n_split > n_tiles) n_split = n_tiles;
   if (n_split < 1) n_split = 1;
   while (n_split > 1 && measure_smem(S, n, n_split) > smem_max) --n_split;
