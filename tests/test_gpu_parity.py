@@ -676,6 +676,37 @@ def test_blocked_gibbs_float32_shared_parameter_ratio_at_20000_events():
     assert worst < 1e-2, worst
 
 
+@pytest.mark.parametrize("scale", [1e-4, 1.0, 1e3])
+def test_blocked_gibbs_float32_integer_sums_over_the_whole_range(scale):
+    """The per-chain sums over events cross CTAs as two-limb fixed-point integers (htm_gibbs_f32.cu: publish_sum,
+    2^-32 resolution).  With the observation errors scaled by 1e-4 a chain's sum is ~ -1e12 (1e22 units: far beyond one
+    64-bit word, the high limb carries it), with 1e3 every event contributes ~ 1e-5: in both the judged sums must
+    still equal a float64 evaluation of the same states to float32 accuracy."""
+    E, S, R, K = 3000, 20, 2, 3
+    J = R * K
+    syn = H.Synthetic(E, S, 31)
+    syn.t_stdv = syn.t_stdv * scale
+    syn.a_stdv = syn.a_stdv * scale
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=20, n_burn=0, n_interval=10,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=32)
+    cfg64 = H.default_config(n_sta=S, n_events=E, mode=H.MODE_FACTORISED, precision=64, **NOSOLVE)
+    with H.HypoTremorB200(cfg) as g, H.HypoTremorB200(cfg64) as g64:
+        g.load(syn)
+        g64.load(syn)
+        g.init_chains()
+        g.run(1, 3)
+        before = [g.get_chain_state(c // K, c % K) for c in range(J)]
+        g.run(4, 4)
+        cur32, prop32 = g.gibbs_last_sums()
+        after = [g.get_chain_state(c // K, c % K) for c in range(J)]
+        L_cur = g64.loglik(np.stack([s["hypo"] for s in after]), np.stack([s["t_corr"] for s in before]),
+                           np.stack([s["a_corr"] for s in before]), [s["vs"] for s in before], [s["qs"] for s in before])
+    assert np.all(np.isfinite(cur32)) and np.all(np.isfinite(prop32))
+    if scale < 1.0:
+        assert np.abs(L_cur).min() > 2.0 ** 31 * 100          # the sums do not fit one 64-bit word of 2^-32 units
+    assert np.all(np.abs(cur32 - L_cur) <= 3e-5 * np.abs(L_cur)), (cur32, L_cur)
+
+
 def test_blocked_gibbs_float32_many_joint_chains():
     """600 joint chains x 40 stations: the chain-level station terms (J x S x 2 doubles = 384 KB) no longer have to
     fit a CTA's shared memory -- the float32 kernel keeps them in global memory.  Size-independent invariants."""
