@@ -24,7 +24,7 @@ EXPORTS = [
     "htm_discard_samples", "htm_get_counts", "htm_get_histograms", "htm_device_ptr",
     "htm_last_run_stats", "htm_measure_fp32_peak", "htm_comm_unique_id", "htm_comm_init", "htm_gather",
     "htm_comm_p2p_export", "htm_comm_p2p_import", "htm_gather_samples", "htm_gibbs_pending", "htm_gibbs_last_sums",
-    "htm_posterior_quantiles", "htm_measure_fp64_peak", "htm_select_events", "htm_measure_windows",
+    "htm_posterior_quantiles", "htm_measure_fp64_peak", "htm_select_events", "htm_measure_windows", "htm_detect_windows",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library():
         "htm_select_events": [i32, i32, i32, dp, dp, dp, ctypes.c_double, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double,
                               ctypes.c_double, ctypes.c_double, dp, dp, dp, dp, dp, dp, ip, dp],
         "htm_measure_windows": [i32, i32, ctypes.c_int64, dp, ctypes.c_double, i32, i32, i32, ip, dp, dp, dp, dp, ip, dp],
+        "htm_detect_windows": [i32, i32, ctypes.c_int64, dp, i32, i32, ctypes.c_double, i32, i32, dp, dp, ip, ip, dp],
         "htm_comm_unique_id": [ctypes.c_char_p],
         "htm_comm_init": [vp, ctypes.c_char_p],
         "htm_gather": [vp, ctypes.POINTER(ctypes.c_uint32), lp, lp],
@@ -169,6 +170,30 @@ def measure_windows(env, dt, n_smp, n_step, win_id, want_lag=False, device=0):
     if want_lag:
         r["lag"] = lag
     return r
+
+
+def detect_windows(env, n_smp, n_step, alpha, n_pair_thred, n_win=None, device=0):
+    """hypo_tremor_measure's scan_cc with the correlation functions of hypo_tremor_correlate recomputed on the device.
+    env: [n_sta, n_total].  Returns dict(cc_thred [n_pair], cc_max [n_pair, n_win], detected [n_win] (bool),
+    n_pairs_above [n_win], win_id (1-based ids of the detected windows), kernel_ms)."""
+    lib = load_library()
+    env = _f64(env)
+    S, n_total = env.shape
+    if n_win is None:
+        n_win = (n_total - n_smp) // n_step                       # src/cls_correlator.f90:80
+    P = S * (S - 1) // 2
+    thr, mx = np.empty(P), np.empty((P, n_win))
+    det, cnt = np.zeros(n_win, dtype=np.int32), np.zeros(n_win, dtype=np.int32)
+    ms = ctypes.c_double()
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    rc = lib.htm_detect_windows(device, S, n_total, _dptr(env), n_smp, n_step, alpha, n_pair_thred, n_win, _dptr(thr), _dptr(mx),
+                                det.ctypes.data_as(i32p), cnt.ctypes.data_as(i32p), ctypes.byref(ms))
+    if rc != HTM_OK:
+        buf = ctypes.create_string_buffer(512)
+        lib.htm_last_error(None, buf, 512)
+        raise HtmError(rc, buf.value.decode())
+    return dict(cc_thred=thr, cc_max=mx, detected=det.astype(bool), n_pairs_above=cnt, win_id=np.nonzero(det)[0] + 1,
+                kernel_ms=ms.value)
 
 
 def measure_fp64_peak(device=0):

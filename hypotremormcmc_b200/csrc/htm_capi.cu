@@ -1841,6 +1841,95 @@ int32_t htm_measure_windows(int32_t device, int32_t n_sta, int64_t n_total, cons
   return HTM_OK;
 }
 
+int32_t htm_detect_windows(int32_t device, int32_t n_sta, int64_t n_total, const double* env, int32_t n_smp, int32_t n_step,
+                           double alpha, int32_t n_pair_thred, int32_t n_win, double* cc_thred, double* cc_max,
+                           int32_t* detected, int32_t* n_pairs_above, double* kernel_ms) {
+  if (!env || !cc_thred || !detected) return fail(nullptr, HTM_ERR_ARG, "null argument");
+  if (n_sta < 2 || n_smp < 2 || (n_smp & 1) || n_step < 1 || n_win < 1 || !(alpha >= 0.0) || !(alpha < 1.0))
+    return fail(nullptr, HTM_ERR_ARG, "need n_sta >= 2, an even n_smp >= 2, n_step >= 1, n_win >= 1, 0 <= alpha < 1");
+  if (static_cast<int64_t>(n_win - 1) * n_step + n_smp > n_total) return fail(nullptr, HTM_ERR_ARG, "windows outside the envelopes");
+  const size_t S = n_sta, W = n_win, P = S * (S - 1) / 2, N = W * static_cast<size_t>(n_smp);
+  if (N > 0x7fffffffull) return fail(nullptr, HTM_ERR_UNSUPPORTED, "n_win * n_smp exceeds 2^31");
+  // src/cls_measurer.f90:223: cc_thred = sorted(int(n * n_win * alpha)), 1-based
+  const long rank1 = static_cast<long>(static_cast<double>(N) * alpha);
+  if (rank1 < 1) return fail(nullptr, HTM_ERR_ARG, "int(n_smp * n_win * alpha) must be >= 1");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(nullptr, HTM_ERR_CUDA, "no CUDA device (libhtm_b200 has no CPU fallback)");
+  if (device < 0 || device >= n_dev) return fail(nullptr, HTM_ERR_ARG, "device ordinal out of range");
+  cudaError_t e = cudaSetDevice(device);
+  size_t free_b = 0, total_b = 0;
+  if (e == cudaSuccess) e = cudaMemGetInfo(&free_b, &total_b);
+  const size_t need = (P * N + P * W + 3 * P + S * static_cast<size_t>(n_total)) * sizeof(double) + 2 * W * sizeof(int32_t);
+  if (e == cudaSuccess && need + (static_cast<size_t>(1) << 28) > free_b)
+    return fail(nullptr, HTM_ERR_UNSUPPORTED,
+                "htm_detect_windows: the correlation functions of all pairs and windows (n_pair * n_win * n_smp * 8 B) do not "
+                "fit the device memory; split the time range");
+  double *d_env = nullptr, *d_cc = nullptr, *d_max = nullptr, *d_thr = nullptr;
+  int32_t *d_det = nullptr, *d_cnt = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = cudaMalloc(&d_env, S * static_cast<size_t>(n_total) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_cc, P * N * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_max, P * W * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_thr, 3 * P * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_det, W * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_cnt, W * sizeof(int32_t));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_env, env, S * static_cast<size_t>(n_total) * sizeof(double), cudaMemcpyHostToDevice, st);
+  MeasureArgs ma;
+  ma.S = n_sta;
+  ma.n = n_smp;
+  ma.n_step = n_step;
+  ma.n_win = n_win;
+  ma.n_total = static_cast<long>(n_total);
+  ma.dt = 1.0;
+  ma.env = d_env;
+  ma.mode = 1;
+  ma.cc = d_cc;
+  ma.cc_max = d_max;
+  if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+  bool unsupported = false;
+  if (e == cudaSuccess) {
+    e = launch_measure(ma, st);
+    unsupported = e == cudaErrorNotSupported;
+  }
+  const int rank0 = static_cast<int>(rank1 - 1);
+  if (e == cudaSuccess) e = launch_quantile_select(64, d_cc, N, static_cast<int>(P), static_cast<int>(N), rank0, rank0, rank0, d_thr, st);
+  if (e == cudaSuccess) e = launch_detect(d_max, d_thr, static_cast<int>(P), n_win, n_pair_thred, d_det, d_cnt, st);
+  if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(cc_thred, sizeof(double), d_thr, 3 * sizeof(double), sizeof(double), P, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && cc_max) e = cudaMemcpyAsync(cc_max, d_max, P * W * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(detected, d_det, W * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && n_pairs_above) e = cudaMemcpyAsync(n_pairs_above, d_cnt, W * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && kernel_ms) {
+    float ms = 0;
+    e = cudaEventElapsedTime(&ms, e0, e1);
+    *kernel_ms = ms;
+  }
+  free_dev(d_env);
+  free_dev(d_cc);
+  free_dev(d_max);
+  free_dev(d_thr);
+  free_dev(d_det);
+  free_dev(d_cnt);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (st) cudaStreamDestroy(st);
+  if (unsupported) {
+    cudaGetLastError();
+    return fail(nullptr, HTM_ERR_UNSUPPORTED,
+                "htm_detect_windows: n_sta x n_smp does not fit one CTA's shared memory (about n_sta (n_smp + 48) 8 B + "
+                "n_sta^2 8 B <= 227 KB)");
+  }
+  if (e != cudaSuccess) return fail(nullptr, HTM_ERR_CUDA, std::string("htm_detect_windows: ") + cudaGetErrorString(e));
+  return HTM_OK;
+}
+
 int32_t htm_measure_fp64_peak(int32_t device, double* tflops) {
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(nullptr, HTM_ERR_CUDA, "no CUDA device");

@@ -200,8 +200,14 @@ struct MeasureArgs {
   const int32_t* win_id = nullptr;          // [n_win] 1-based window numbers
   double *t = nullptr, *t_stdv = nullptr, *amp = nullptr, *amp_stdv = nullptr;  // [n_win][S]
   int32_t* lag = nullptr;                   // optional [n_win][S (S - 1) / 2]: sample index of each pair's maximum
+  // mode 1: the correlation functions of hypo_tremor_correlate instead (win_id null: windows 1 .. n_win)
+  int mode = 0;
+  double* cc = nullptr;                     // optional [S (S - 1) / 2][n_win][n]: correlation value at circular lag k
+  double* cc_max = nullptr;                 // optional [S (S - 1) / 2][n_win]
 };
 cudaError_t launch_measure(const MeasureArgs& a, cudaStream_t stream);
+cudaError_t launch_detect(const double* cc_max, const double* thr, int n_pair, int n_win, int n_pair_thred, int32_t* detected,
+                          int32_t* count, cudaStream_t stream);
 
 // FFMA / MUFU microbenchmark (roofline denominators)
 cudaError_t measure_fp32_peak(int device, double* tflops, double* mufu_gops);

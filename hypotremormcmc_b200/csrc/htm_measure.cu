@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kMeasureThreads, 1) measure_kernel(const Measu
   const MeasureSm sm = carve_measure(measure_smem_raw, S, n, n_split);
   const int w = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   // src/cls_measurer.f90:331-333: window id -> first sample (0-based) of the merged envelopes
-  const long j1 = static_cast<long>(a.win_id[w] - 1) * a.n_step;
+  const long j1 = static_cast<long>(a.win_id ? a.win_id[w] - 1 : w) * a.n_step;
 
   for (int i = threadIdx.x; i < S - 1; i += blockDim.x) {
     int p = pair_index(S, i, i + 1);
@@ -149,21 +149,44 @@ __global__ void __launch_bounds__(kMeasureThreads, 1) measure_kernel(const Measu
   }
   if (threadIdx.x == 0) sm.flag[0] = sm.flag[1] = 0;  // negative-product flag, next unit of the correlation phase
 
-  // ---- optimize_cc :478-486: a_i = taper(x_i) / sum(x_i^2) -------------------------------------------------------
+  // ---- the tapered, normalised windows -----------------------------------------------------------------------------
+  // measure  (optimize_cc, src/cls_measurer.f90:478-486):          a_i = taper(x_i) / sum(x_i^2)
+  // correlate (run_cross_corr, src/cls_correlator.f90:207-226):     a_i = (taper(x_i) - mean) / |taper(x_i) - mean|
   const int nleng = static_cast<int>(n * 0.05);
   const double pi_d = 3.14159265358979323846;
   for (int i = warp; i < S; i += n_warps) {
     const double* x = a.env + static_cast<size_t>(i) * a.n_total + j1;
-    double l = 0.0;
-    for (int m = lane; m < n; m += 32) l = fma(x[m], x[m], l);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
     double* r = sm.rows + static_cast<size_t>(i) * stride;
+    double l = 0.0, sum = 0.0;
     for (int m = lane; m < n; m += 32) {
       const int e = m < nleng ? m : (n - 1 - m < nleng ? n - 1 - m : -1);
-      double v = x[m];
+      const double xv = x[m];
+      double v = xv;
       if (e >= 0) v = v * (0.5 * (1.0 - cos(e * pi_d / nleng)));
-      r[m] = v / l;
+      r[m] = v;
+      l = fma(xv, xv, l);
+      sum += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, o);
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    __syncwarp();
+    if (a.mode == 0) {
+      for (int m = lane; m < n; m += 32) r[m] = r[m] / l;
+    } else {
+      const double mean = sum / n;
+      double l2 = 0.0;
+      for (int m = lane; m < n; m += 32) {
+        const double v = r[m] - mean;
+        l2 = fma(v, v, l2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+      const double len = sqrt(l2);
+      // (a window of zeros: the reference leaves its work array untouched, :211-213; here the row is zero)
+      for (int m = lane; m < n; m += 32) r[m] = len != 0.0 ? (r[m] - mean) / len : 0.0;
     }
     __syncwarp();
     for (int e = lane; e < kRowExt; e += 32) r[n + e] = r[e % n];
@@ -212,6 +235,12 @@ __global__ void __launch_bounds__(kMeasureThreads, 1) measure_kernel(const Measu
         else
           corr_block<true, false>(ri + n_blk * kLagTile, rj + base + kLagTile, W, acc, n - n_blk * kLagTile);
       }
+      if (a.cc && 32 * g + lane < P) {  // correlate: the pair's correlation function of this window, lags k0 .. k0+15
+        double* dst = a.cc + (static_cast<size_t>(p) * a.n_win + w) * n + k0;
+#pragma unroll
+        for (int t = 0; t < kLagTile; ++t)
+          if (k0 + t < n) dst[t] = acc[t];
+      }
 #pragma unroll
       for (int t = 0; t < kLagTile; ++t) {
         if (k0 + t < n && acc[t] > best) {  // strict: maxloc keeps the first maximum
@@ -238,7 +267,9 @@ __global__ void __launch_bounds__(kMeasureThreads, 1) measure_kernel(const Measu
     }
     sm.lagk[p] = best_k;
     if (a.lag) a.lag[static_cast<size_t>(w) * P + p] = best_k;
+    if (a.cc_max) a.cc_max[static_cast<size_t>(p) * a.n_win + w] = best;  // maxval(cc(:, i)), src/cls_correlator.f90:233
   }
+  if (a.mode != 0) return;
   __syncthreads();
 
   // ---- optimize_cc :507-520: station times and their scatter (sums in the reference's order) ---------------------
@@ -311,6 +342,25 @@ __global__ void __launch_bounds__(kMeasureThreads, 1) measure_kernel(const Measu
     a.amp[o] = zeroed ? 0.0 : ai;
     a.amp_stdv[o] = zeroed ? 0.0 : sqrt(s / (S - 2));
   }
+}
+
+// scan_cc (src/cls_measurer.f90:228-258): a window is detected when more than n_pair_thred station pairs have their
+// maximum correlation at or above the pair's threshold
+__global__ void detect_kernel(const double* __restrict__ cc_max /* [P][n_win] */, const double* __restrict__ thr /* [P][3] */,
+                              const int P, const int n_win, const int n_pair_thred, int32_t* __restrict__ detected,
+                              int32_t* __restrict__ count) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_win) return;
+  int c = 0;
+  for (int p = 0; p < P; ++p) c += cc_max[static_cast<size_t>(p) * n_win + w] >= thr[3 * p] ? 1 : 0;
+  detected[w] = c > n_pair_thred ? 1 : 0;
+  if (count) count[w] = c;
+}
+
+cudaError_t launch_detect(const double* cc_max, const double* thr, int P, int n_win, int n_pair_thred, int32_t* detected,
+                          int32_t* count, cudaStream_t stream) {
+  detect_kernel<<<(n_win + 127) / 128, 128, 0, stream>>>(cc_max, thr, P, n_win, n_pair_thred, detected, count);
+  return cudaGetLastError();
 }
 
 // 0 = the window does not fit the CTA's shared memory

@@ -108,6 +108,10 @@ __global__ void __launch_bounds__(256) quantile_select_kernel(const T* __restric
   const T* x = store + static_cast<size_t>(blockIdx.x) * cap;
   const int ranks[3] = {r0, r1, r2};
   for (int q = 0; q < 3; ++q) {
+    if (q > 0 && ranks[q] == ranks[q - 1]) {  // a repeated rank: the same element
+      if (threadIdx.x == 0) out[static_cast<size_t>(blockIdx.x) * 3 + q] = out[static_cast<size_t>(blockIdx.x) * 3 + q - 1];
+      continue;
+    }
     key_t prefix = 0, mask = 0;
     unsigned int rank = static_cast<unsigned int>(ranks[q]);  // rank among the keys that match the prefix so far
     for (int shift = Key<T>::kBits - 8; shift >= 0; shift -= 8) {

@@ -356,6 +356,23 @@ module htm_b200_binding
        integer(c_int32_t) :: rc
      end function htm_measure_windows
 
+     ! hypo_tremor_measure: scan_cc with the correlation functions recomputed from the envelopes (env (n_total, n_sta)
+     ! column-major; cc_max (n_win, n_pair)); c_null_ptr for cc_max / n_pairs_above to skip them
+     function htm_detect_windows(device, n_sta, n_total, env, n_smp, n_step, alpha, n_pair_thred, n_win, cc_thred, &
+          & cc_max, detected, n_pairs_above, kernel_ms) bind(c, name="htm_detect_windows") result(rc)
+       import
+       integer(c_int32_t), value :: device, n_sta, n_smp, n_step, n_pair_thred, n_win
+       integer(c_int64_t), value :: n_total
+       real(c_double), intent(in) :: env(*)
+       real(c_double), value :: alpha
+       real(c_double), intent(out) :: cc_thred(*)
+       type(c_ptr), value :: cc_max
+       integer(c_int32_t), intent(out) :: detected(*)
+       type(c_ptr), value :: n_pairs_above
+       real(c_double), intent(out) :: kernel_ms
+       integer(c_int32_t) :: rc
+     end function htm_detect_windows
+
      function htm_measure_fp64_peak(device, tflops) bind(c, name="htm_measure_fp64_peak") result(rc)
        import
        integer(c_int32_t), value :: device

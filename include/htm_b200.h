@@ -364,6 +364,23 @@ int32_t htm_measure_windows(int32_t device, int32_t n_sta, int64_t n_total, cons
                             int32_t n_step, int32_t n_win, const int32_t* win_id, double* t, double* t_stdv, double* amp,
                             double* amp_stdv, int32_t* lag, double* kernel_ms);
 
+/* Replaces `call msr%scan_cc()` (src/hypo_tremor_measure.f90:55; src/cls_measurer.f90:189-315) TOGETHER WITH the
+ * correlation functions it reads: scan_cc takes, per station pair, the order statistic int(n n_win alpha) of ALL
+ * correlation values of all windows as the pair's threshold (:213-223), marks the windows whose maximum correlation
+ * reaches it (:228-236) and detects a window when more than n_pair_thred pairs are marked (:247-253).  The reference
+ * reads those values from the STA1.STA2.corr / .max_corr files that hypo_tremor_correlate wrote (24 B per value: 10 GB
+ * for two days of 50 stations); here they are recomputed from the envelopes on the device, as run_cross_corr does
+ * (src/cls_correlator.f90:200-233: 5 % taper, mean removed, unit length, circular cross-correlation / n), at about
+ * 10 us per window, kept in device memory, and the thresholds are selected there (radix selection, no sort).
+ * env: [n_sta][n_total] merged envelopes; window w (1-based) = samples (w - 1) n_step ... + n_smp - 1, w = 1 .. n_win with
+ * n_win = (n_total - n_smp) / n_step as in src/cls_correlator.f90:80; n_smp even (:180-183).  Outputs: cc_thred [n_pair]
+ * (cc_thred.dat), detected [n_win] (1 = listed in detected_win.dat) and, if not NULL, cc_max [n_pair][n_win] (the
+ * .max_corr values) and n_pairs_above [n_win]; pairs in the order i < j.  HTM_ERR_UNSUPPORTED when n_pair n_win n_smp
+ * 8 B exceeds the free device memory (split the time range) or a window exceeds one CTA (see htm_measure_windows). */
+int32_t htm_detect_windows(int32_t device, int32_t n_sta, int64_t n_total, const double* env, int32_t n_smp, int32_t n_step,
+                           double alpha, int32_t n_pair_thred, int32_t n_win, double* cc_thred, double* cc_max,
+                           int32_t* detected, int32_t* n_pairs_above, double* kernel_ms);
+
 /* FFMA/MUFU microbenchmark used as the FP32 roofline denominator (no driver-measured
  * FP32 vector peak exists).  Returns TFLOP/s (FFMA = 2 flops). */
 int32_t htm_measure_fp32_peak(int32_t device, double* tflops, double* mufu_gops);

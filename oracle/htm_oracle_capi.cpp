@@ -287,4 +287,10 @@ void hto_measure(int32_t S, int64_t n_total, const double* env, double dt, int32
   }
 }
 
+void hto_detect(int32_t S, int64_t n_total, const double* env, int32_t n, int32_t n_step, double alpha, int32_t n_pair_thred,
+                int32_t n_win, double* cc_thred, double* cc_max, int32_t* detected, int32_t* n_above) {
+  hto::detect_windows(S, static_cast<long>(n_total), env, n, n_step, alpha, n_pair_thred, n_win, cc_thred, cc_max, detected,
+                      n_above);
+}
+
 }  // extern "C"

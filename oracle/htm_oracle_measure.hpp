@@ -14,6 +14,7 @@
 // (FFTW is not in this image).  tests/test_measure.py holds the transform route in numpy and pins this file to it.
 // Parity unpinned by the reference (no tests, no Fortran compiler, no FFTW here).  Never linked by the product.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <vector>
@@ -124,6 +125,61 @@ inline void measure_window(int S, int n, double dt, const double* x, double* t, 
                            double* amp_stdv, int32_t* lag_k) {
   optimize_cc(S, n, dt, x, t, t_stdv, lag_k);
   optimize_amp(S, n, dt, x, t, amp, amp_stdv);
+}
+
+
+// ---- scan_cc on correlation functions recomputed as hypo_tremor_correlate forms them ------------------------------
+//   src/cls_correlator.f90:200-233   per window and station: taper, remove the mean, divide by the Euclidean length;
+//                                    per pair: circular cross-correlation / n (FFTW there, the direct sum here), maxval
+//   src/cls_correlator.f90:80        n_win = (n_smp_total - n) / n_step
+//   src/cls_measurer.f90:205-236     per pair: all n * n_win values sorted, threshold = element int(n * n_win * alpha)
+//                                    (1-based); a window is marked for the pair when its maximum >= threshold
+//   src/cls_measurer.f90:247-253     detected when more than n_pair_thred pairs are marked
+// env [S][n_total]; cc_thred [P]; cc_max [P][n_win]; detected, n_above [n_win]
+inline void detect_windows(int S, long n_total, const double* env, int n, int n_step, double alpha, int n_pair_thred,
+                           int n_win, double* cc_thred, double* cc_max, int32_t* detected, int32_t* n_above) {
+  const int P = S * (S - 1) / 2;
+  const size_t N = static_cast<size_t>(n) * n_win;
+  std::vector<double> a(static_cast<size_t>(S) * n), tmp(n);
+  std::vector<std::vector<double>> histo(P, std::vector<double>(N));
+  for (int w = 0; w < n_win; ++w) {
+    const long j1 = static_cast<long>(w) * n_step;
+    for (int i = 0; i < S; ++i) {
+      apply_taper(n, env + static_cast<size_t>(i) * n_total + j1, tmp.data());
+      double sum = 0.0, l = 0.0;
+      for (int m = 0; m < n; ++m) sum = sum + tmp[m];
+      for (int m = 0; m < n; ++m) tmp[m] = tmp[m] - sum / n;
+      for (int m = 0; m < n; ++m) l = l + tmp[m] * tmp[m];
+      l = std::sqrt(l);
+      for (int m = 0; m < n; ++m) a[static_cast<size_t>(i) * n + m] = l != 0.0 ? tmp[m] / l : 0.0;
+    }
+    for (int i = 0; i < S - 1; ++i) {
+      for (int j = i + 1; j < S; ++j) {
+        const int p = pair_index(S, i, j);
+        const double *ai = a.data() + static_cast<size_t>(i) * n, *aj = a.data() + static_cast<size_t>(j) * n;
+        double mx = 0.0;
+        for (int k = 0; k < n; ++k) {
+          double s = 0.0;
+          for (int m = 0; m < n - k; ++m) s = s + ai[m] * aj[m + k];
+          for (int m = n - k; m < n; ++m) s = s + ai[m] * aj[m + k - n];
+          histo[p][static_cast<size_t>(w) * n + k] = s;
+          if (k == 0 || s > mx) mx = s;
+        }
+        cc_max[static_cast<size_t>(p) * n_win + w] = mx;
+      }
+    }
+  }
+  const long rank1 = static_cast<long>(static_cast<double>(N) * alpha);
+  for (int p = 0; p < P; ++p) {
+    std::sort(histo[p].begin(), histo[p].end());
+    cc_thred[p] = histo[p][rank1 - 1];
+  }
+  for (int w = 0; w < n_win; ++w) {
+    int c = 0;
+    for (int p = 0; p < P; ++p) c += cc_max[static_cast<size_t>(p) * n_win + w] >= cc_thred[p] ? 1 : 0;
+    n_above[w] = c;
+    detected[w] = c > n_pair_thred ? 1 : 0;
+  }
 }
 
 }  // namespace hto

@@ -111,6 +111,24 @@ def measure_windows(env, dt, n_smp, n_step, win_id, want_lag=False):
     return r
 
 
+def detect_windows(env, n_smp, n_step, alpha, n_pair_thred, n_win=None):
+    """scan_cc on recomputed correlation functions (oracle/htm_oracle_measure.hpp: detect_windows)"""
+    env = np.ascontiguousarray(env, dtype=np.float64)
+    S, n_total = env.shape
+    if n_win is None:
+        n_win = (n_total - n_smp) // n_step
+    P = S * (S - 1) // 2
+    thr, mx = np.empty(P), np.empty((P, n_win))
+    det, cnt = np.zeros(n_win, dtype=np.int32), np.zeros(n_win, dtype=np.int32)
+    f = lib().hto_detect
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+    f.argtypes = [ctypes.c_int32, ctypes.c_int64, dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_int32,
+                  ctypes.c_int32, dp, dp, ip, ip]
+    f.restype = None
+    f(S, n_total, _d(env), n_smp, n_step, alpha, n_pair_thred, n_win, _d(thr), _d(mx), det.ctypes.data_as(ip), cnt.ctypes.data_as(ip))
+    return dict(cc_thred=thr, cc_max=mx, detected=det.astype(bool), n_pairs_above=cnt, win_id=np.nonzero(det)[0] + 1)
+
+
 class Oracle:
     def __init__(self, cfg, syn, event_offset=0):
         self.L = lib()

@@ -68,6 +68,42 @@ def numpy_measure(env, dt, n, n_step, win_id):
     return {k: np.array(v) for k, v in out.items()}
 
 
+def numpy_detect(env, n, n_step, alpha, n_pair_thred, n_win):
+    """src/cls_correlator.f90:200-233 + src/cls_measurer.f90:205-253 with numpy's FFT in the place of FFTW and a full sort"""
+    S = env.shape[0]
+    nleng = int(n * 0.05)
+    tap = np.ones(n)
+    fac = 0.5 * (1.0 - np.cos(np.arange(nleng) * np.pi / nleng)) if nleng else np.zeros(0)
+    tap[:nleng] = fac
+    tap[n - nleng:] = fac[::-1]
+    P = S * (S - 1) // 2
+    cc = np.empty((P, n_win, n))
+    for w in range(n_win):
+        x = env[:, w * n_step:w * n_step + n] * tap
+        x = x - x.sum(1, keepdims=True) / n
+        a = x / np.sqrt((x ** 2).sum(1))[:, None]
+        cx = np.fft.rfft(a, axis=1)
+        p = 0
+        for i in range(S - 1):
+            for j in range(i + 1, S):
+                cc[p, w] = np.fft.irfft(np.conj(cx[i]) * cx[j], n)
+                p += 1
+    mx = cc.max(2)
+    N = n * n_win
+    srt = np.sort(cc.reshape(P, N), axis=1)
+    thr = srt[:, int(N * alpha) - 1]
+    cnt = (mx >= thr[:, None]).sum(0)
+    return dict(cc_thred=thr, cc_max=mx, n_pairs_above=cnt, detected=cnt > n_pair_thred)
+
+
+def compare_detect(g, o):
+    assert np.allclose(g["cc_max"], o["cc_max"], rtol=0, atol=1e-12) and np.allclose(g["cc_thred"], o["cc_thred"], rtol=0, atol=1e-12)
+    # a window's count may differ only where a pair's maximum sits within rounding of the pair's threshold
+    close = (np.abs(o["cc_max"] - o["cc_thred"][:, None]) < 1e-12).sum(0)
+    assert np.all(np.abs(g["n_pairs_above"] - o["n_pairs_above"]) <= close)
+    assert np.array_equal(g["detected"][close == 0], o["detected"][close == 0])
+
+
 def tremor_envelopes(S, n_total, seed, max_shift=12, noise=0.3):
     """a common smooth positive source signal, delayed and scaled per station, plus station noise"""
     rng = np.random.default_rng(seed)
@@ -141,6 +177,79 @@ def test_oracle_measure_properties():
     env4[5] = -env4[5]
     o4 = pyoracle.measure_windows(env4, 1.0, n, n_step, win)
     assert np.all(o4["amp"] == 0.0) and np.all(o4["amp_stdv"] == 0.0) and np.abs(o4["t"]).max() > 0
+
+
+@pytest.mark.parametrize("S,n,n_step,alpha,thred", [(6, 40, 20, 0.98, 7), (4, 64, 16, 0.995, 1), (9, 30, 30, 0.995, 12)])
+def test_oracle_detect_equals_the_transform_route(S, n, n_step, alpha, thred):
+    """scan_cc on recomputed correlation functions: the direct sums of the oracle against rfft / irfft and a full sort"""
+    env, _, _ = tremor_envelopes(S, 1000, 90 + S)
+    n_win = (1000 - n) // n_step
+    o = pyoracle.detect_windows(env, n, n_step, alpha, thred)
+    r = numpy_detect(env, n, n_step, alpha, thred, n_win)
+    assert o["cc_max"].shape == (S * (S - 1) // 2, n_win)
+    compare_detect(o, r)
+    assert 0 < o["detected"].sum() < n_win          # the settings separate the windows
+    assert np.array_equal(o["win_id"], np.nonzero(o["detected"])[0] + 1)
+    # the threshold is the alpha quantile of the pair's values: about (1 - alpha) of them lie at or above it
+    assert np.all(o["cc_thred"] <= o["cc_max"].max(1)) and np.all(np.abs(o["cc_max"]) <= 1.0 + 1e-12)
+
+
+def test_oracle_detect_known_answer():
+    """two stations with identical envelopes correlate to exactly 1 at zero lag in every window; a third, unrelated one
+    does not: the thresholds order accordingly and cc_max of the identical pair is 1"""
+    rng = np.random.default_rng(6)
+    kern = np.hanning(9)
+    a = np.convolve(rng.normal(0, 1, 600) ** 2, kern, mode="same")
+    b = np.convolve(rng.normal(0, 1, 600) ** 2, kern, mode="same")
+    env = np.stack([a, 2.5 * a, b])                   # pairs in order: (0, 1), (0, 2), (1, 2)
+    o = pyoracle.detect_windows(env, 50, 25, 0.9, 0)
+    assert np.allclose(o["cc_max"][0], 1.0, atol=1e-12) and np.all(o["cc_max"][1:] < 0.999)
+    assert np.allclose(o["cc_max"][1], o["cc_max"][2], atol=1e-12)        # scaling a station changes nothing
+    assert o["cc_thred"][0] > 0 and np.all(o["n_pairs_above"] >= 1)        # the identical pair is marked in every window
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,n,n_step,alpha,thred", [(6, 40, 20, 0.98, 7), (4, 64, 16, 0.995, 1), (9, 30, 30, 0.995, 12),
+                                                    (20, 300, 150, 0.98, 60), (3, 18, 5, 0.5, 1)])
+def test_cuda_detect_equals_the_oracle(S, n, n_step, alpha, thred):
+    n_total = 1000 if n < 100 else 3000
+    env, _, _ = tremor_envelopes(S, n_total, 90 + S)
+    o = pyoracle.detect_windows(env, n, n_step, alpha, thred)
+    g = H.api.detect_windows(env, n, n_step, alpha, thred)
+    compare_detect(g, o)
+    assert np.array_equal(g["win_id"], np.nonzero(g["detected"])[0] + 1) and g["kernel_ms"] > 0
+
+
+@pytest.mark.gpu
+def test_cuda_detect_then_measure_full_size():
+    """one day of 50 stations at one sample per second (sample/hypo_tremor.in:74-92: 300 s windows every 150 s, alpha =
+    0.98, more than 300 of the 1225 pairs): detection from the envelopes alone, then the lag / amplitude optimisation
+    of the detected windows; the thresholds are order statistics of 172 200 values per pair, checked on the host for a
+    few pairs through cc_max properties, and the detected list feeds htm_measure_windows unchanged."""
+    S, n, n_step = 50, 300, 150
+    n_total = 86400
+    rng = np.random.default_rng(12)
+    kern = np.hanning(21)
+    env = np.stack([np.convolve(rng.normal(0, 1, n_total) ** 2, kern, mode="same") for _ in range(S)])
+    # tremor bursts: a common signal, delayed per station, in a tenth of the day
+    src = np.convolve(rng.normal(0, 1, n_total + 100) ** 2, kern, mode="same") * (np.sin(np.arange(n_total + 100) * 2 * np.pi / 8640.0) > 0.8)
+    shift = rng.integers(-10, 11, S)
+    for i in range(S):
+        env[i] += 4.0 * src[50 - shift[i]:50 - shift[i] + n_total]
+    g = H.api.detect_windows(env, n, n_step, 0.98, 300)
+    n_win = (n_total - n) // n_step
+    assert g["cc_max"].shape == (1225, n_win) and np.all(g["cc_max"] <= 1 + 1e-12)
+    frac_above = (g["cc_max"] >= g["cc_thred"][:, None]).mean()
+    assert 0.02 < frac_above < 0.9
+    assert np.array_equal(g["n_pairs_above"], (g["cc_max"] >= g["cc_thred"][:, None]).sum(0))
+    assert np.array_equal(g["detected"], g["n_pairs_above"] > 300) and 10 < g["detected"].sum() < n_win
+    burst = (np.sin((np.arange(n_win) * n_step + n / 2) * 2 * np.pi / 8640.0) > 0.85)
+    assert g["detected"][burst].mean() > 0.9 and g["detected"][~burst].mean() < 0.2
+    m = H.api.measure_windows(env, 1.0, n, n_step, g["win_id"][:200])
+    # the measured delays are the ones that were put in (windows at the edge of a burst see part of the signal only)
+    assert np.abs(np.median(m["t"], axis=0) - (shift - shift.mean())).max() <= 1.0
+    print("detect: %d windows x 1225 pairs x 300 lags in %.1f ms (correlation functions, %d thresholds by radix selection, "
+          "detection); %d windows detected" % (n_win, g["kernel_ms"], 1225, g["detected"].sum()))
 
 
 @pytest.mark.gpu
