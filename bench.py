@@ -414,8 +414,25 @@ def extra_upstream(H, a, local, peak64_tf):
                                    "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / peak64_tf, "traffic": None,
                                    "flop_per_window": flop / W, "kernel": "measure_kernel",
                                    "peak_source": "own-measured DFMA microbenchmark (htm_measure_fp64_peak)"}}
+    day = np.stack([np.convolve(rng.normal(0, 1, 86400) ** 2, kern, mode="same") for _ in range(S)])
+    ms = min(api.detect_windows(day, n, n // 2, 0.98, 300, device=local)["kernel_ms"] for _ in range(3))
+    n_win = (86400 - n) // (n // 2)
+    flop = 2.0 * n_win * (S * (S - 1) // 2) * n * n
+    out["detect"] = {"workload": "hypo_tremor_measure scan_cc with the correlation functions of hypo_tremor_correlate recomputed: "
+                                 "one day of %d stations at 1 sample/s = %d windows x %d pairs x %d lags, f64"
+                                 % (S, n_win, S * (S - 1) // 2, n),
+                     "value": n_win / (ms * 1e-3), "unit": "windows/s", "kernel_ms": ms, "gpu_launches": 3,
+                     "roofline": {"bound": "fp64", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peak64_tf, "unit": "TFLOP/s",
+                                  "frac": flop / (ms * 1e-3) / 1e12 / peak64_tf, "traffic": None,
+                                  "kernel": "measure_kernel (mode 1) + quantile_select_kernel + detect_kernel",
+                                  "note": "the time includes 8 selection passes over the %.1f GB of correlation values"
+                                          % (8.0 * n_win * n * (S * (S - 1) // 2) / 1e9)}}
     if not a.no_cpu:
         from oracle import pyoracle
+        t0 = time.time()
+        pyoracle.detect_windows(day[:, :n + 16 * (n // 2)], n, n // 2, 0.98, 300)
+        out["detect"]["cpu_baseline"] = {"value": 16 / (time.time() - t0), "unit": "windows/s", "cores": 1, "kind": "port",
+                                         "sample": "oracle detect_windows (direct float64 sums, full sort) on the first 16 windows"}
         t0 = time.time()
         pyoracle.select_events(*[v[:20000] if getattr(v, "ndim", 0) == 2 else v for v in args])
         out["select"]["cpu_baseline"] = {"value": 20000 / (time.time() - t0), "unit": "windows/s", "cores": 1, "kind": "port",
