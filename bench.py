@@ -425,7 +425,7 @@ def extra_upstream(H, a, local, peak64_tf):
                      "roofline": {"bound": "fp64", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peak64_tf, "unit": "TFLOP/s",
                                   "frac": flop / (ms * 1e-3) / 1e12 / peak64_tf, "traffic": None,
                                   "kernel": "measure_kernel (mode 1) + quantile_select_kernel + detect_kernel",
-                                  "note": "the time includes 8 selection passes over the %.1f GB of correlation values"
+                                  "note": "the time includes 3-4 selection scans of the %.1f GB of correlation values"
                                           % (8.0 * n_win * n * (S * (S - 1) // 2) / 1e9)}}
     if not a.no_cpu:
         from oracle import pyoracle
