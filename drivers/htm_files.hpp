@@ -80,7 +80,9 @@ struct ParamFile {
     return r;
   }
 
-  void read(const std::string& path) {
+  void read(const std::string& path) { read(path, required_mcmc()); }
+  // required: the keys the calling program needs (src/cls_param.f90 checks per from_where)
+  void read(const std::string& path, const std::vector<std::string>& required) {
     std::ifstream in(path);
     if (!in) throw std::runtime_error("cannot open parameter file " + path);
     std::string line;
@@ -97,7 +99,7 @@ struct ParamFile {
       if (!known().count(name)) throw std::runtime_error("Invalid parameter name : " + name + "  (?)");
       kv[name] = val;
     }
-    for (const std::string& k : required_mcmc())
+    for (const std::string& k : required)
       if (!kv.count(k)) throw std::runtime_error(k + " is not given.");
   }
   bool has(const std::string& k) const { return kv.count(k) != 0; }
@@ -137,6 +139,40 @@ inline std::vector<int> read_selected_windows(const std::string& path) {
   std::string a, b;
   while (in >> a >> b) ids.push_back(parse_int("win_id", a));
   return ids;
+}
+
+// detected_win.dat / selected_win.dat: window number and time, list-directed (src/cls_measurer.f90:289-292)
+inline void read_window_list(const std::string& path, std::vector<int>& ids, std::vector<double>& times) {
+  std::ifstream in(path);
+  if (!in) throw std::runtime_error("cannot open " + path);
+  std::string a, b;
+  while (in >> a >> b) {
+    ids.push_back(parse_int("win_id", a));
+    times.push_back(parse_real("win_time", b));
+  }
+}
+
+// STA.merged.env: unformatted stream of (time, envelope) float64 pairs (src/cls_convertor.f90:259-272), read by the
+// reference with direct access, recl = 8 (src/cls_measurer.f90:132-139, 345-349)
+inline void read_envelope(const std::string& path, bool big_endian, std::vector<double>& v, double* dt) {
+  std::ifstream in(path, std::ios::binary | std::ios::ate);
+  if (!in) throw std::runtime_error(path + " does not exist");
+  const std::streamsize bytes = in.tellg();
+  if (bytes < 32 || bytes % 16 != 0) throw std::runtime_error("bad envelope file " + path);
+  std::vector<unsigned char> raw(static_cast<size_t>(bytes));
+  in.seekg(0);
+  in.read(reinterpret_cast<char*>(raw.data()), bytes);
+  auto at = [&](size_t k) {
+    unsigned char b[8];
+    for (int i = 0; i < 8; ++i) b[i] = raw[8 * k + (big_endian ? 7 - i : i)];
+    double d;
+    std::memcpy(&d, b, 8);
+    return d;
+  };
+  const size_t n = static_cast<size_t>(bytes) / 16;
+  v.resize(n);
+  for (size_t i = 0; i < n; ++i) v[i] = at(2 * i + 1);
+  *dt = at(2) - at(0);
 }
 
 // obs arrays in Fortran (n_sta, n_events) column-major order == C [n_events][n_sta]
