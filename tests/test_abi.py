@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 import hypotremormcmc_b200 as H
@@ -88,6 +89,29 @@ def test_no_cpu_fallback():
     assert ei.value.code == H.config.HTM_ERR_CUDA and "no CPU fallback" in str(ei.value)
     with pytest.raises(H.HtmError):
         H.api.measure_fp32_peak(0)
+
+
+def test_upstream_entry_points_validate_before_they_need_a_device():
+    """htm_detect_windows / htm_measure_windows / htm_select_events: argument errors are reported as such on any box; with
+    valid arguments and no GPU the answer is HTM_ERR_CUDA, never a host computation"""
+    env = np.abs(np.random.default_rng(0).normal(0, 1, (4, 400)))
+    bad = [lambda: H.api.measure_windows(env, 1.0, 100, 50, [9]),            # window 9 = samples 400 .. 499: outside
+           lambda: H.api.measure_windows(env[:2], 1.0, 100, 50, [1]),        # fewer than three stations
+           lambda: H.api.measure_windows(env, 0.0, 100, 50, [1]),            # dt
+           lambda: H.api.detect_windows(env, 101, 50, 0.98, 2),              # odd window (src/cls_correlator.f90:180-183)
+           lambda: H.api.detect_windows(env, 100, 50, 1.0, 2),               # alpha < 1
+           lambda: H.api.detect_windows(env, 100, 50, 1e-9, 2),              # int(n n_win alpha) = 0: no such element
+           lambda: H.api.detect_windows(env, 100, 50, 0.98, 2, n_win=8)]     # windows beyond the data
+    for f in bad:
+        with pytest.raises(H.HtmError) as ei:
+            f()
+        assert ei.value.code == H.config.HTM_ERR_ARG, str(ei.value)
+    import torch
+    if not torch.cuda.is_available():
+        for f in (lambda: H.api.measure_windows(env, 1.0, 100, 50, [1, 2]), lambda: H.api.detect_windows(env, 100, 50, 0.98, 2)):
+            with pytest.raises(H.HtmError) as ei:
+                f()
+            assert ei.value.code == H.config.HTM_ERR_CUDA and "no CPU fallback" in str(ei.value)
 
 
 def test_product_does_not_touch_the_oracle():
