@@ -55,6 +55,10 @@ struct FactParams {
   uint32_t event_offset;
   real vs, qs, prior_z, width_z, width_xy, step_xy, step_z;
   real inv2s2_xy, inv2s2_z;  // 1/(2 sigma^2) of the x,y and z priors (host-computed: no division in the loop)
+  // 1/vs and pi f/(qs vs) as make_glob forms them, computed on the host in `real` arithmetic (same bits): values
+  // read from the parameter bank are warp-uniform to the compiler, so the packed FFMA2 that use them take a
+  // uniform-register operand instead of a third 64-bit register read (tools/micro/issue_mix.cu: 2.1 vs 3.6 cycles)
+  real g_ivs, g_B;
   unsigned long long* counts;
   real4* samples;
   int rec_origin, rec_cap;
@@ -192,14 +196,19 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
   const uint32_t below_me = (1u << lane) - 1u;
   const real4 evc = p.evc4[e];
   const typename R2<real>::type pxy = p.prior_xy[e];
-  const Glob<real> g = make_glob<real>(p.vs, p.qs);
+  Glob<real> g;
+  g.beta = p.vs;
+  g.ivs = p.g_ivs;
+  g.qbeta = p.qs * p.vs;
+  g.B = p.g_B;
   const uint32_t eg = static_cast<uint32_t>(e) + p.event_offset;
   bool valid[NSLOT];
   int rr[NSLOT];
   size_t ci[NSLOT];
   real x[NSLOT], y[NSLOT], z[NSLOT], L[NSLOT], T[NSLOT], iT[NSLOT], lgz[NSLOT];
   uint32_t cnt_p[3] = {0, 0, 0}, cnt_a[3] = {0, 0, 0};
-  uint32_t pk_p = 0, pk_a = 0;  // packed per-type counters of the last <= 512/NSLOT iterations
+  uint32_t pk_p = 0, pk_a = 0;  // packed per-type counters (three 10-bit fields) of the last pk_it iterations
+  int pk_it = 0;
 #pragma unroll
   for (int q = 0; q < NSLOT; ++q) {
     const int r = (we * NSLOT + q) * gpw + gl;
@@ -332,7 +341,9 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
       }
     }
     const bool rec_now = rec_left == 0;
-    // ---- judge, count, record, swap ----
+    // ---- judge, count, record, swap: each phase for all slots, so that the warp-uniform branches (record
+    //      iteration? swap draws to refill?) are taken once per iteration and the shuffles of the slots overlap ----
+    bool cold[NSLOT];
 #pragma unroll
     for (int q = 0; q < NSLOT; ++q) {
       const real Lnew = finish_loglik<real>(S1t[q], S2[q], S1a[q], static_cast<real>(0), evc);
@@ -340,10 +351,10 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
       const real ratio = M<real>::div(Lnew - L[q], T[q], iT[q]) + lpr[q];
       const real ru = M<real>::u_co(wacc[q]);
       const bool acc = ok[q] && (ru > static_cast<real>(0)) && (M<real>::log(ru) <= ratio);
-      const bool cold = is_cold<real>(T[q]);
+      cold[q] = is_cold<real>(T[q]);
       {  // cold-chain counters, three 10-bit fields per word (flushed every 512 iterations below);
          // invalid lanes clone a valid chain and must not count
-        const uint32_t inc = (cold && valid[q]) ? (1u << (10 * icmp[q])) : 0u;
+        const uint32_t inc = (cold[q] && valid[q]) ? (1u << (10 * icmp[q])) : 0u;
         pk_p += inc;
         pk_a += acc ? inc : 0u;
       }
@@ -367,12 +378,15 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
           p.trace[static_cast<size_t>(it - p.iter_first) * p.E * R * K + ci[q]] = t;
         }
       }
-      // record (src/hypo_tremor_mcmc.f90:270-280)
-      if (rec_now) {
-        const uint32_t coldmask = __ballot_sync(0xffffffffu, cold && valid[q]);
-        if (cold && valid[q]) {
+    }
+    // record (src/hypo_tremor_mcmc.f90:270-280)
+    if (rec_now) {
+      const int slot = (it - 1) / p.n_interval - p.rec_origin;
+#pragma unroll
+      for (int q = 0; q < NSLOT; ++q) {
+        const uint32_t coldmask = __ballot_sync(0xffffffffu, cold[q] && valid[q]);
+        if (cold[q] && valid[q]) {
           const int m = __popc(coldmask & gmask & below_me);
-          const int slot = (it - 1) / p.n_interval - p.rec_origin;
           if (p.samples && slot >= 0 && slot < p.rec_cap && m < p.n_cool) {
             real4 rec;
             rec.x = x[q];
@@ -384,9 +398,29 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
           if (p.hist && it > p.n_burn) hist_add<real>(p, e, x[q], y[q], z[q], pxy.x, pxy.y);
         }
       }
-      // swap inside the tempering group (src/cls_parallel.f90:100-216, 285-302)
-      if (K >= 2) {
-        if (sw_fill) {
+    }
+    // swap inside the tempering group (src/cls_parallel.f90:100-216, 285-302).  A group of ONE chain draws the pair
+    // (0, 0) and exchanges its temperature with itself, so only the traced kernels (which write a swap record) need
+    // the test.
+    if (sw_fill) {  // first iteration of a block of K: the rare per-block work shares this one branch
+      // the packed counters gain at most K * NSLOT per field until the next block starts: empty them before a
+      // 10-bit field can overflow
+      if ((pk_it + K) * NSLOT > 1023) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          cnt_p[c] += (pk_p >> (10 * c)) & 1023u;
+          cnt_a[c] += (pk_a >> (10 * c)) & 1023u;
+        }
+        pk_p = 0;
+        pk_a = 0;
+        pk_it = 0;
+      }
+      pk_it += K;
+    }
+    if (TRACE ? K >= 2 : true) {
+      if (sw_fill) {
+#pragma unroll
+        for (int q = 0; q < NSLOT; ++q) {
           const uint32_t grp = eg * R + rr[q];
           const u32x4 w = philox4x32_10(p.rk, static_cast<uint32_t>(sw_blk0 + k + 1), grp, PHX_SWAP, 0u);
           const int i1 = static_cast<int>(below(w.v[0], static_cast<uint32_t>(K)));
@@ -397,17 +431,29 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
           // ln r; r = 0 can never be accepted (r >= eps fails, :295): use -inf surrogate
           sw_lr[q] = ru2 > static_cast<real>(0) ? M<real>::log(ru2) : static_cast<real>(3.0e38);
         }
-        const int pair = __shfl_sync(0xffffffffu, sw_pair[q], base + sw_o);
-        const real lr = __shfl_sync(0xffffffffu, sw_lr[q], base + sw_o);
-        const int i1 = pair & 0xff, i2 = pair >> 8;
+      }
+      int pair[NSLOT];
+      real lr[NSLOT], Lp[NSLOT], Tp[NSLOT], iTp[NSLOT];
+#pragma unroll
+      for (int q = 0; q < NSLOT; ++q) {
+        pair[q] = __shfl_sync(0xffffffffu, sw_pair[q], base + sw_o);
+        lr[q] = __shfl_sync(0xffffffffu, sw_lr[q], base + sw_o);
+      }
+#pragma unroll
+      for (int q = 0; q < NSLOT; ++q) {
+        const int i1 = pair[q] & 0xff, i2 = pair[q] >> 8;
         // the two chains of the pair read each other; every other lane reads garbage it ignores
         const int partner = (k == i1) ? i2 : i1;
-        const real Lp = __shfl_sync(0xffffffffu, L[q], base + partner);
-        const real Tp = __shfl_sync(0xffffffffu, T[q], base + partner);
-        const real iTp = __shfl_sync(0xffffffffu, iT[q], base + partner);
+        Lp[q] = __shfl_sync(0xffffffffu, L[q], base + partner);
+        Tp[q] = __shfl_sync(0xffffffffu, T[q], base + partner);
+        iTp[q] = __shfl_sync(0xffffffffu, iT[q], base + partner);
+      }
+#pragma unroll
+      for (int q = 0; q < NSLOT; ++q) {
+        const int i1 = pair[q] & 0xff, i2 = pair[q] >> 8;
         // del_s = (L2 - L1)(1/T1 - 1/T2) is symmetric under exchanging the roles of 1 and 2
-        const real del_s = (Lp - L[q]) * (iT[q] - iTp);
-        const bool sacc = lr <= del_s;
+        const real del_s = (Lp[q] - L[q]) * (iT[q] - iTp[q]);
+        const bool sacc = lr[q] <= del_s;
         const bool mine = (k == i1) || (k == i2);
         if (TRACE) {
           const int a1 = __shfl_sync(0xffffffffu, sacc ? 1 : 0, base + i1);
@@ -423,19 +469,10 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
           }
         }
         if (sacc && mine) {
-          T[q] = Tp;
-          iT[q] = iTp;
+          T[q] = Tp[q];
+          iT[q] = iTp[q];
         }
       }
-    }
-    if (((it - p.iter_first) & (512 / NSLOT - 1)) == 512 / NSLOT - 1) {  // before a 10-bit field can overflow
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        cnt_p[c] += (pk_p >> (10 * c)) & 1023u;
-        cnt_a[c] += (pk_a >> (10 * c)) & 1023u;
-      }
-      pk_p = 0;
-      pk_a = 0;
     }
     // advance the swap-draw window and the recording countdown
     sw_fill = false;
@@ -924,6 +961,8 @@ static FactParams<real> make_params(const FactLaunch& a) {
   p.event_offset = a.event_offset;
   p.vs = static_cast<real>(a.vs);
   p.qs = static_cast<real>(a.qs);
+  p.g_ivs = static_cast<real>(1) / p.vs;
+  p.g_B = static_cast<real>(kPi * kFreq) / (p.qs * p.vs);
   p.prior_z = static_cast<real>(a.prior_z);
   p.width_z = static_cast<real>(a.width_z);
   p.width_xy = static_cast<real>(a.width_xy);

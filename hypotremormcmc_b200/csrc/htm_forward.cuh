@@ -138,39 +138,48 @@ constexpr int kPackedUnroll = HTM_PK_UNROLL;
 // chain (the lane kernel carries the weighted mean residual of the chain's accepted state, so no station
 // needs special treatment: chi2 = S2 - S1^2/W holds for any shift and S1 stays small).
 // Returns S1t = sum w_t (r_t - c_t), S1a, S2 = sum w (r - c)^2 per slot.
+// the per-thread operands of the packed station loop: NSLOT hypocentres and their running sums
 template <int NSLOT>
-__device__ __forceinline__ void forward_pairs(const float4* __restrict__ s_pk, const int n_pairs,
-                                              const float (&hx)[NSLOT], const float (&hy)[NSLOT],
-                                              const float (&hz)[NSLOT], const Glob<float>& g,
-                                              const float (&nct)[NSLOT], const float (&nca)[NSLOT],
-                                              float (&S1t)[NSLOT], float (&S1a)[NSLOT], float (&S2)[NSLOT]) {
-  const float2 ivs2 = f2(g.ivs, g.ivs), nB2 = f2(-g.B, -g.B);
-  const float2 nc2 = f2(-0.34657359027997264f, -0.34657359027997264f);
+struct PairAcc {
   float2 px[NSLOT], py[NSLOT], pz[NSLOT], hh[NSLOT], ct2[NSLOT], ca2[NSLOT], a1t[NSLOT], a1a[NSLOT], a2[NSLOT];
+  float2 ivs2, nB2, nc2;
+  __device__ __forceinline__ void init(const float (&hx)[NSLOT], const float (&hy)[NSLOT], const float (&hz)[NSLOT],
+                                       const Glob<float>& g, const float (&nct)[NSLOT], const float (&nca)[NSLOT]) {
+    ivs2 = f2(g.ivs, g.ivs);
+    nB2 = f2(-g.B, -g.B);
+    nc2 = f2(-0.34657359027997264f, -0.34657359027997264f);
 #pragma unroll
-  for (int q = 0; q < NSLOT; ++q) {
-    const float h2 = fmaf(hz[q], hz[q], fmaf(hy[q], hy[q], hx[q] * hx[q]));
-    px[q] = f2(hx[q], hx[q]);
-    py[q] = f2(hy[q], hy[q]);
-    pz[q] = f2(hz[q], hz[q]);
-    hh[q] = f2(h2, h2);
-    ct2[q] = f2(nct[q], nct[q]);
-    ca2[q] = f2(nca[q], nca[q]);
-    a1t[q] = f2(0.f, 0.f);
-    a1a[q] = f2(0.f, 0.f);
-    a2[q] = f2(0.f, 0.f);
+    for (int q = 0; q < NSLOT; ++q) {
+      const float h2 = fmaf(hz[q], hz[q], fmaf(hy[q], hy[q], hx[q] * hx[q]));
+      px[q] = f2(hx[q], hx[q]);
+      py[q] = f2(hy[q], hy[q]);
+      pz[q] = f2(hz[q], hz[q]);
+      hh[q] = f2(h2, h2);
+      ct2[q] = f2(nct[q], nct[q]);
+      ca2[q] = f2(nca[q], nca[q]);
+      a1t[q] = f2(0.f, 0.f);
+      a1a[q] = f2(0.f, 0.f);
+      a2[q] = f2(0.f, 0.f);
+    }
   }
-#pragma unroll kPackedUnroll
-  for (int m = 0; m < n_pairs; ++m) {
-    const float4 r0 = s_pk[4 * m], r1 = s_pk[4 * m + 1], r2 = s_pk[4 * m + 2], r3 = s_pk[4 * m + 3];
+  // one station pair (4 float4 of the packed record) for every slot
+  __device__ __forceinline__ void pair(const float4* __restrict__ rec) {
+    const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
     const float2 swt = f2(r2.x, r2.y), swa = f2(r3.x, r3.y);
 #pragma unroll
     for (int q = 0; q < NSLOT; ++q) {
       const float2 d2 = __ffma2_rn(px[q], f2(r0.x, r0.y),
                                    __ffma2_rn(py[q], f2(r0.z, r0.w),
                                               __ffma2_rn(pz[q], f2(r1.x, r1.y), __fadd2_rn(f2(r1.z, r1.w), hh[q]))));
+#ifdef HTM_ABL_NOMUFU  // tools/micro/pair_loop.cu only: the loop with its MUFU operations replaced by LOP3
+      const float2 d = __fmul2_rn(d2, f2(__int_as_float(__float_as_int(d2.x) ^ 0x100), __int_as_float(__float_as_int(d2.y) ^ 0x100)));
+      const float2 l2 = f2(__int_as_float(__float_as_int(d2.x) ^ 0x200), __int_as_float(__float_as_int(d2.y) ^ 0x200));
+#else
+      // (d = MUFU.SQRT(d2) saves the multiply and was measured: +2.8 % with one chain per lane, -2.4 % with two --
+      //  and the two layouts must agree bit for bit, so it is not used; profiles/r2bf_lane_phases.txt)
       const float2 d = __fmul2_rn(d2, f2(mufu_rsq(d2.x), mufu_rsq(d2.y)));
       const float2 l2 = f2(mufu_lg2(d2.x), mufu_lg2(d2.y));
+#endif
       const float2 ut = __ffma2_rn(swt, __ffma2_rn(d, ivs2, ct2[q]), f2(r2.z, r2.w));
       const float2 ua = __ffma2_rn(swa, __ffma2_rn(nc2, l2, __ffma2_rn(nB2, d, ca2[q])), f2(r3.z, r3.w));
       a2[q] = __ffma2_rn(ut, ut, a2[q]);
@@ -179,14 +188,27 @@ __device__ __forceinline__ void forward_pairs(const float4* __restrict__ s_pk, c
       a1a[q] = __ffma2_rn(swa, ua, a1a[q]);
     }
   }
+  __device__ __forceinline__ void finish(float (&S1t)[NSLOT], float (&S1a)[NSLOT], float (&S2)[NSLOT]) const {
 #pragma unroll
-  for (int q = 0; q < NSLOT; ++q) {
-    S1t[q] = a1t[q].x + a1t[q].y;
-    S1a[q] = a1a[q].x + a1a[q].y;
-    S2[q] = a2[q].x + a2[q].y;
+    for (int q = 0; q < NSLOT; ++q) {
+      S1t[q] = a1t[q].x + a1t[q].y;
+      S1a[q] = a1a[q].x + a1a[q].y;
+      S2[q] = a2[q].x + a2[q].y;
+    }
   }
+};
+template <int NSLOT>
+__device__ __forceinline__ void forward_pairs(const float4* __restrict__ s_pk, const int n_pairs,
+                                              const float (&hx)[NSLOT], const float (&hy)[NSLOT],
+                                              const float (&hz)[NSLOT], const Glob<float>& g,
+                                              const float (&nct)[NSLOT], const float (&nca)[NSLOT],
+                                              float (&S1t)[NSLOT], float (&S1a)[NSLOT], float (&S2)[NSLOT]) {
+  PairAcc<NSLOT> A;
+  A.init(hx, hy, hz, g, nct, nca);
+#pragma unroll kPackedUnroll
+  for (int m = 0; m < n_pairs; ++m) A.pair(s_pk + 4 * m);
+  A.finish(S1t, S1a, S2);
 }
-
 template <typename real>
 __device__ __forceinline__ real finish_loglik(real S1t, real S2t, real S1a, real S2a,
                                               const typename M<real>::real4 evc) {

@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+for lib in variants/libhtm_old.so "" variants/libhtm_sqrt.so; do
+  if [ -n "$lib" ]; then export HTM_B200_LIB=$PWD/$lib; else unset HTM_B200_LIB; fi
+  timeout 300 python tools/lane_variant_check.py >> gpurun_out/r2bf_check.txt 2>&1
+  SLOTS=1,2 timeout 300 python tools/variant_sweep.py >> gpurun_out/r2bf_sweep.txt 2>&1
+  timeout 400 python tools/lane_s_scaling.py >> gpurun_out/r2bf_s_scaling.txt 2>&1
+done
+cat gpurun_out/r2bf_check.txt gpurun_out/r2bf_sweep.txt gpurun_out/r2bf_s_scaling.txt
