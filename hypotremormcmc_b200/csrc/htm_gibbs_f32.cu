@@ -817,7 +817,33 @@ struct F32Shape {
 template <bool TRACE, bool INIT>
 static cudaError_t f32_shape(const GibbsLaunch& a, F32Shape* s) {
   const int quads = (a.J + kQuad - 1) / kQuad;
+  // CTA rows (chain groups).  Every row streams the whole event table, so few rows are cheap in traffic; but the
+  // warps a row's CTAs carry decide how many CTAs fit an SM (registers, shared memory), and 25 chain quads in 4 rows
+  // of 7 + 6 + 6 + 6 warps leave an SM with 12-13 resident warps where 5 rows of 5 warps give it 15.  Take the fewest
+  // rows unless more rows raise the resident warps per SM by more than 8 % (sample shape, 100 joint chains:
+  // 111 -> 105 us per iteration at 10 000 events, 1029 -> 930 us at 100 000; profiles/r2bi_gibbs_rows.txt).
   s->gy = (quads + kCW - 1) / kCW;
+  {
+    double best = 0.0;
+    int last_gy = 0;
+    for (int target = kCW; target >= 4; --target) {
+      const int gy = (quads + target - 1) / target;
+      if (gy == last_gy) continue;
+      last_gy = gy;
+      const int nw = (quads + gy - 1) / gy;
+      const size_t smem = ((f32_sweep_smem(a.S, nw * kQuad, 2) + 15) & ~static_cast<size_t>(15)) + chain_sm_small_bytes(a.J);
+      if (smem > 200 * 1024) continue;
+      if (cudaFuncSetAttribute(gibbs_f32_kernel<TRACE, INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) continue;
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_f32_kernel<TRACE, INIT>, nw * 32, smem) != cudaSuccess) continue;
+      const double warps_per_sm = static_cast<double>(occ) * quads / gy;
+      if (warps_per_sm > best * 1.08) {
+        best = warps_per_sm;
+        s->gy = gy;
+      }
+    }
+  }
+  if (const char* v = std::getenv("HTM_GIBBS_ROWS")) s->gy = std::max((quads + kCW - 1) / kCW, std::min(quads, std::atoi(v)));  // tuning
   s->n_warps = (quads + s->gy - 1) / s->gy;
   // ring depth: as deep as possible (fast warps may then run ahead of the slowest one, and the row copies have
   // several visits to land) WITHOUT lowering the number of resident CTAs per SM that two stages allow
