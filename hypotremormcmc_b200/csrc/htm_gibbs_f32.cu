@@ -135,7 +135,7 @@ __device__ __forceinline__ RowHead row_head(const float4* __restrict__ row, cons
 }
 
 #ifndef HTM_GIBBS_PK_UNROLL
-#define HTM_GIBBS_PK_UNROLL 2
+#define HTM_GIBBS_PK_UNROLL 4  // 2: 105.5 / 929 us per iteration at 10 000 / 100 000 events x 50 x 100 chains, 4: 100.3 / 875, 6-12: 102 / 892-905 (profiles/r2bm_gibbs_unroll.txt)
 #endif
 constexpr int kMomentsUnroll = HTM_GIBBS_PK_UNROLL;
 // cp[m] = {-tc_j0, -tc_j1, -ac_j0, -ac_j1}: the chain's station terms of pair m; ntc0 / nac0 those of station 0

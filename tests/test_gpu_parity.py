@@ -776,7 +776,7 @@ def test_blocked_gibbs_full_size_properties():
 
 
 def test_blocked_gibbs_float32_long_run_is_reproducible_and_consistent():
-    """20 000 iterations of 100 joint chains (four CTA rows, many CTAs per row) run twice: every state, counter and
+    """20 000 iterations of 100 joint chains (five CTA rows, many CTAs per row) run twice: every state, counter and
     record must be bit-identical (the kernel's cross-CTA traffic -- redundant writes of the accepted station terms,
     partial sums, the grid barrier -- leaves no room for a timing-dependent result), and the carried sums must still
     be the likelihood of the state after ~7000 incremental shared-parameter commits per chain."""
@@ -810,6 +810,39 @@ def test_blocked_gibbs_float32_long_run_is_reproducible_and_consistent():
     assert p[:4].sum() == n_it * R and acc[:4].sum() > 0.05 * p[:4].sum()     # shared parameters do get accepted
     for s, L in zip(a[0], a[3]):
         assert abs(s["log_likelihood"] - L) <= 2e-5 * abs(L), (s["log_likelihood"], L)
+
+
+def test_blocked_gibbs_float32_result_does_not_depend_on_the_cta_rows(monkeypatch):
+    """The launcher deals the chain quads to CTA rows for resident warps per SM (100 chains: 5 rows of 5 warps); the
+    shape only regroups which CTA visits which (chain, event), so every decision must be the same with the fewest
+    rows (HTM_GIBBS_ROWS=0: 4 rows of 7 + 6 + 6 + 6 warps) and with one quad per row (25 rows); the carried sums are
+    float64 sums of the same float32 terms in another grouping."""
+    E, S, R, K, n_it = 300, 21, 20, 5, 30
+    syn = H.Synthetic(E, S, 9)
+    cfg = H.default_config(n_sta=S, n_events=E, n_procs=R, n_chains=K, n_cool=1, n_iter=n_it, n_burn=0, n_interval=5,
+                           mode=H.MODE_BLOCKED_GIBBS, precision=32, max_samples=8)
+    runs = []
+    for rows in (None, "0", "25"):
+        if rows is None:
+            monkeypatch.delenv("HTM_GIBBS_ROWS", raising=False)
+        else:
+            monkeypatch.setenv("HTM_GIBBS_ROWS", rows)
+        with H.HypoTremorB200(cfg) as g:
+            g.load(syn)
+            g.init_chains()
+            tr, sw = g.run_traced(1, n_it)
+            runs.append((tr, sw, [g.get_chain_state(r, k) for r in range(R) for k in range(K)], g.get_counts()))
+    ref = runs[0]
+    assert ref[0]["accepted"].sum() > 0
+    for other in runs[1:]:
+        for f in ("proposal_type", "index", "prior_ok", "accepted"):
+            assert np.array_equal(ref[0][f], other[0][f]), f
+        assert np.array_equal(ref[1], other[1])
+        assert np.array_equal(ref[3][0], other[3][0]) and np.array_equal(ref[3][1], other[3][1])
+        for x, y in zip(ref[2], other[2]):
+            assert np.array_equal(x["hypo"], y["hypo"]) and x["vs"] == y["vs"] and x["qs"] == y["qs"] and x["temp"] == y["temp"]
+            assert np.array_equal(x["t_corr"], y["t_corr"]) and np.array_equal(x["a_corr"], y["a_corr"])
+            assert abs(x["log_likelihood"] - y["log_likelihood"]) <= 1e-12 * abs(x["log_likelihood"])
 
 
 def test_blocked_gibbs_chunked_runs_equal_one_run():
