@@ -489,8 +489,13 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
     fence_proxy_async();
   }
   __syncthreads();
-  auto issue = [&](long t) {  // visit t of this CTA -> ring stage t mod n_stages
-    const int buf = static_cast<int>(t % n_stages), o = o_begin + static_cast<int>(t % n_my);
+  // The ring indices advance by increments: visit t uses stage t mod n_stages with phase (t / n_stages) & 1 and octet
+  // o_begin + t mod n_my, but t is a 64-bit count and the divisors are run-time values -- formed by division, these
+  // cost every warp two 64-bit divide subroutines per visit (a quarter of the instructions outside the station loop).
+  int iss_i = 0;  // producer: (next visit to issue) mod n_my
+  auto issue = [&](const int buf) {  // the next visit of this CTA -> ring stage buf
+    const int o = o_begin + iss_i;
+    if (++iss_i == n_my) iss_i = 0;
     const int n_ev = min(kOct, E - o * kOct);
     if (lane == 0) mbar_expect_tx(m.full + buf, row_bytes * n_ev);
     __syncwarp();
@@ -523,6 +528,8 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
   float4* const pf1 = pf0 + static_cast<size_t>(blockDim.x) * 4;                       // stage 1
   uint32_t cnt_p[3] = {0, 0, 0}, cnt_a[3] = {0, 0, 0};
   long t_run = 0;
+  int buf = 0;       // t_run mod n_stages
+  uint32_t ph = 0;   // (t_run / n_stages) & 1
 
   for (int it = iter_first; it < iter_first + n_it; ++it) {
     // three accumulator sets in rotation: this iteration's, the next one's (already zero) and the one the writer
@@ -574,8 +581,6 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
       g_cta_done_ns[2 * (blockIdx.y * gridDim.x + blockIdx.x)] = global_timer_ns();
 #endif
     for (int i = 0; i < (warp_ok ? n_my : 0); ++i, ++t_run) {
-      const int buf = static_cast<int>(t_run % n_stages);
-      const uint32_t ph = static_cast<uint32_t>((t_run / n_stages) & 1);
       const int o = o_begin + i;
       if (warp_ok) {
         if (i + 1 < n_my) {
@@ -694,7 +699,11 @@ __global__ void __maxnreg__(HTM_GIBBS_MAXREG)
       if (warp == 0 && t_run + n_stages < n_run) {
         if (lane == 0) mbar_wait(m.empty + buf, ph);
         __syncwarp();
-        issue(t_run + n_stages);
+        issue(buf);  // visit t_run + n_stages lands in the stage this visit has just released
+      }
+      if (++buf == n_stages) {
+        buf = 0;
+        ph ^= 1u;
       }
     }
     if (warp_ok) {
