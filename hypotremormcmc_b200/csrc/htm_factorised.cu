@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(128, HTM_LANE_MINB) fact_lane_kernel(const Fac
       const real ru = M<real>::u_co(wacc[q]);
       const bool acc = ok[q] && (ru > static_cast<real>(0)) && (M<real>::log(ru) <= ratio);
       cold[q] = is_cold<real>(T[q]);
-      {  // cold-chain counters, three 10-bit fields per word (flushed every 512 iterations below);
+      {  // cold-chain counters, three 10-bit fields per word (emptied under the refill branch below, before a field can overflow);
          // invalid lanes clone a valid chain and must not count
         const uint32_t inc = (cold[q] && valid[q]) ? (1u << (10 * icmp[q])) : 0u;
         pk_p += inc;
